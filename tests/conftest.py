@@ -1,0 +1,56 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, f'{name}.npz'), allow_pickle=False))
+
+
+@pytest.fixture(scope='session')
+def golden_quantizer():
+    return load_golden('quantizer')
+
+
+@pytest.fixture(scope='session')
+def golden_quant():
+    return load_golden('quant')
+
+
+@pytest.fixture(scope='session')
+def golden_gmm():
+    return load_golden('gmm')
+
+
+@pytest.fixture(scope='session')
+def golden_mfa():
+    return load_golden('mfa')
+
+
+GMM_TAGS = ['b1_zm', 'b1_mean', 'b2u_mean', 'b3l_zm', 'binf_mean', 'b1_pilots2', 'b2u_pilots2', 'b1_k1']
+GMM_MODES = {'all': 'all', 'top1': 1, 'top3': 3, 'cum90': 0.9}
+MFA_TAGS = ['b1_zm', 'b2u_mean', 'b3l_mean']
+MFA_MODES = {'all': 'all', 'top1': 1, 'top2': 2, 'cum90': 0.9}
+
+
+def golden_quantizer_tuple(g, tag):
+    if f'{tag}_thr' in g:
+        return (g[f'{tag}_thr'], g[f'{tag}_lab'], None)
+    return (None, None, None)
+
+
+def relerr(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
