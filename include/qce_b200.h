@@ -1,0 +1,146 @@
+/*
+ * qce_b200.h -- C ABI of the B200-native Bussgang-GMM / Bussgang-MFA inference path.
+ *
+ * The reference (benediktfesl/Quantized_Channel_Estimation) is pure Python and has no FFI of
+ * its own; its boundary for this path is the Python method surface
+ *     Gmm_nbit.estimate_from_y          modules/gmm_cplx_bussgang.py:166-243
+ *     Mofa.estimate_from_y              modules/mofa_cplx_bussgang.py:117-159
+ *     utils.quant                       modules/utils.py:189-203
+ *     utils.get_observation_nbit        modules/utils.py:241-251
+ * Each entry point below names the reference code whose per-sample arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; complex arrays are interleaved (re, im) doubles ("c128") or floats ("c64"),
+ *     row-major, exactly numpy's / torch's memory layout;
+ *   - "dev" pointers are CUDA device pointers owned by the caller, "host" pointers are host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all device work is
+ *     enqueued on it and the call returns without synchronising unless stated otherwise;
+ *   - every function returns QCE_OK (0) or a negative qce_status; qce_last_error_string() gives
+ *     the message of the last failure on the calling thread.  Nothing throws, nothing falls back
+ *     to the CPU.
+ */
+#ifndef QCE_B200_H
+#define QCE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCE_ABI_VERSION 1
+
+typedef int qce_status;
+enum {
+    QCE_OK = 0,
+    QCE_ERR_INVALID = -1,      /* bad argument (shape, mode, null pointer)                          */
+    QCE_ERR_CUDA = -2,         /* a CUDA runtime call or kernel launch failed                       */
+    QCE_ERR_UNSUPPORTED = -3,  /* shape / mode not supported by the requested kernel                */
+    QCE_ERR_NO_DEVICE = -4     /* no sm_100 device                                                  */
+};
+
+/* combination modes of estimate_from_y's `n_summands_or_proba` (gmm:197-242, mofa:125-158) */
+enum {
+    QCE_MODE_ALL = 0,      /* 'all'   : sum_k p_k h_k (not renormalised)                             */
+    QCE_MODE_TOP1 = 1,     /* int 1   : hard decision argmax_k                                       */
+    QCE_MODE_TOPN = 2,     /* int n>1 : n largest p_k, renormalised                                  */
+    QCE_MODE_CUMPROB = 3   /* float   : smallest descending prefix with cumsum >= rho, renormalised  */
+};
+
+/* arithmetic of the estimate kernel */
+enum {
+    QCE_PREC_FP64 = 0,     /* complex128 SIMT kernel (validation / arbitrary shapes)                  */
+    QCE_PREC_TC = 1        /* tcgen05 tensor-core kernel, FP16 hi/lo split operands, FP32 accumulate  */
+};
+
+/* flags for qce_model_create */
+enum {
+    QCE_FLAG_TOP1_EXP_ARGMAX = 1  /* Mofa.predict_proba_max quirk: argmax of exp(log p) (mofa:359-366):
+                                     if every exp underflows the label is 0                          */
+};
+
+typedef struct qce_model qce_model;
+typedef struct qce_quantizer qce_quantizer;
+
+int qce_abi_version(void);
+const char* qce_last_error_string(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches) */
+int64_t qce_launch_count(void);
+/* 1 if a CUDA device of compute capability 10.x is visible */
+int qce_device_ok(void);
+
+/* ---- quantiser (modules/utils.py:189-203; tables from utils.py:531-590) ----------------------- */
+
+/* n_bits == 1: thresholds/labels ignored (may be NULL).  Otherwise thresholds_host[2^b-1] ascending,
+ * labels_host[2^b].  The tables are copied to the device here, once. */
+qce_status qce_quantizer_create(int n_bits, const double* thresholds_host, const double* labels_host,
+                                qce_quantizer** out);
+void qce_quantizer_destroy(qce_quantizer* q);
+
+/* r = Q(y) per real dimension, bit-exact to utils.quant:
+ *   1 bit : 1/sqrt(2) * (sign(re) + j sign(im))   (sign(+-0) = 0, sign(NaN) = NaN)
+ *   b bit : labels[#{thresholds <= x}]            (np.digitize right=False; NaN -> last bin)
+ * y_dev: c128 [n_complex].  r_out_dev (c128 [n_complex]) and codes_out_dev (uint8 [n_complex][2], the
+ * level index; 1 bit: 0 neg / 1 zero / 2 pos / 3 NaN) may each be NULL. */
+qce_status qce_quantize(const qce_quantizer* q, void* stream, const void* y_dev, int64_t n_complex,
+                        void* r_out_dev, uint8_t* codes_out_dev);
+
+/* get_observation_nbit with A = I (utils.py:241-251): y = h + noise_scale * noise (two roundings, no
+ * FMA), then quantise.  h_dev is c64 (h_is_c64 = 1, SCMMulti's dtype) or c128; noise_dev c128.
+ * q == NULL means n_bits = inf (only y is produced).  y_out_dev / r_out_dev / codes_out_dev may be NULL. */
+qce_status qce_observe_quantize(const qce_quantizer* q, void* stream, const void* h_dev, int h_is_c64,
+                                const void* noise_dev, double noise_scale, int64_t n_complex,
+                                void* y_out_dev, void* r_out_dev, uint8_t* codes_out_dev);
+
+/* ---- per-SNR model: host-precomputed component parameters ------------------------------------- */
+
+/* n_obs = rows of the pilot matrix A (length of r), n_ant = channel length N, n_comp = K. */
+qce_status qce_model_create(int n_obs, int n_ant, int n_comp, int flags, qce_model** out);
+void qce_model_destroy(qce_model* m);
+
+/* Parameters of one (snr, n_bits, quantiser) setting -- the quantities Gmm_nbit._prepare_for_prediction
+ * (gmm:246-328) / Mofa._prepare_for_prediction (mofa:162-212) derive, folded so that per sample
+ *     z_k   = Linv_k r - zoff_k                 (whitened residual,   gmm:413-417)
+ *     l_k   = logc_k - |z_k|^2                  (weighted log-lik.,   gmm:380-386, :435 / mofa:346-381)
+ *     h_k   = W_k r + hoff_k                    (component LMMSE,     gmm:331-332 / mofa:215-216)
+ * with Linv_k = L_k^-1 (C_r,k = L_k L_k^H), zoff_k = Linv_k m_r,k, W_k = C_h,k A_eff,k^H C_r,k^-1,
+ * hoff_k = mu_k - W_k m_r,k, logc_k = ln w_k - n_obs ln(pi) - ln|C_r,k|.
+ * All arrays are device c128 / f64, row-major: Linv [K][n_obs][n_obs], W [K][n_ant][n_obs],
+ * zoff [K][n_obs], hoff [K][n_ant], logc [K].  The model copies / repacks them (caller may free).
+ * data_scale > 0 declares that every real and imaginary part of every r the caller will pass is an
+ * integer multiple m * data_scale with |m| <= 2048 (true for 1-bit and uniform quantisers); the
+ * tensor-core kernel then needs two instead of three FP16 passes.  Pass 0 for arbitrary data. */
+qce_status qce_model_set_params(qce_model* m, void* stream, const double* Linv_dev, const double* W_dev,
+                                const double* zoff_dev, const double* hoff_dev, const double* logc_dev,
+                                double data_scale);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* estimate_from_y after _prepare_for_prediction (gmm:196-243 / mofa:124-159) for a batch.
+ *   r_dev      c128 [B][n_obs]  quantised pilots
+ *   h_est_dev  c128 [B][n_ant]  output (may be NULL when only the accumulators are wanted)
+ *   logp_out_dev  f64 [B][K] weighted log-probabilities l_k (may be NULL)
+ *   h_true_dev c128 [B][n_ant] and acc_dev f64[3] (may both be NULL): acc += { sum|h_est-h|^2, sum|h|^2, B }
+ *   mode / n_top / rho: see QCE_MODE_*; precision: QCE_PREC_* */
+qce_status qce_estimate(qce_model* m, void* stream, const void* r_dev, int64_t B, int mode, int n_top,
+                        double rho, int precision, void* h_est_dev, double* logp_out_dev,
+                        const void* h_true_dev, double* acc_dev);
+
+/* Fused pipeline on device-resident channels: observe (A = I) -> quantise -> estimate -> NMSE
+ * accumulators, i.e. one Monte-Carlo step of Bussgang_GMM.py:284-289 for one SNR.
+ * h_dev c64/c128 [B][N], noise_dev c128 [B][N]; h_est_dev may be NULL; acc_dev f64[3] may be NULL. */
+qce_status qce_pipeline(qce_model* m, const qce_quantizer* q, void* stream, const void* h_dev, int h_is_c64,
+                        const void* noise_dev, double noise_scale, int64_t B, int mode, int n_top, double rho,
+                        int precision, void* h_est_dev, double* acc_dev);
+
+/* Host-buffer form of qce_estimate: r_host c128 [B][n_obs] -> h_est_host c128 [B][n_ant].  Copies are
+ * chunked through pinned staging buffers owned by the model and overlapped with the kernels on the
+ * model's own streams; returns after the last chunk has landed in h_est_host (synchronous). */
+qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho,
+                             int precision, void* h_est_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCE_B200_H */

@@ -1,0 +1,309 @@
+// C-ABI entry points of libqce_b200.so (declared in include/qce_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "qce_common.cuh"
+
+namespace qce {
+static thread_local char g_err[512] = "";
+int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace qce
+
+using namespace qce;
+
+namespace {
+struct HostStaging {            // qce_estimate_host: double-buffered pinned + device staging, shared by all models
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    void* pin_in[2] = {nullptr, nullptr};
+    void* pin_out[2] = {nullptr, nullptr};
+    void* dev_in[2] = {nullptr, nullptr};
+    void* dev_out[2] = {nullptr, nullptr};
+    size_t in_bytes = 0, out_bytes = 0;
+};
+HostStaging g_staging;
+}  // namespace
+
+extern "C" {
+
+int qce_abi_version(void) { return QCE_ABI_VERSION; }
+const char* qce_last_error_string(void) { return g_err; }
+int64_t qce_launch_count(void) { return g_launch_count; }
+
+int qce_device_ok(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+    int dev = 0, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    return major == 10;
+}
+
+static qce_status require_device() {
+    if (!qce_device_ok()) {
+        set_error("no sm_100 CUDA device visible: this library has no CPU fallback");
+        return QCE_ERR_NO_DEVICE;
+    }
+    return QCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------- quantiser
+
+qce_status qce_quantizer_create(int n_bits, const double* thr, const double* labels, qce_quantizer** out) {
+    if (!out || n_bits < 1 || n_bits > 8) { set_error("qce_quantizer_create: n_bits must be in 1..8"); return QCE_ERR_INVALID; }
+    if (n_bits > 1 && (!thr || !labels)) { set_error("qce_quantizer_create: tables required for n_bits > 1"); return QCE_ERR_INVALID; }
+    qce_status st = require_device();
+    if (st) return st;
+    qce_quantizer* q = new qce_quantizer();
+    q->t.n_bits = n_bits;
+    q->t.n_thr = (1 << n_bits) - 1;
+    q->t.thr = q->t.labels = nullptr;
+    q->dev_buf = nullptr;
+    if (n_bits > 1) {
+        const int nt = q->t.n_thr;
+        for (int i = 1; i < nt; ++i)
+            if (!(thr[i] >= thr[i - 1])) { delete q; set_error("qce_quantizer_create: thresholds must ascend"); return QCE_ERR_INVALID; }
+        cudaError_t e = cudaMalloc(&q->dev_buf, sizeof(double) * (2 * nt + 1));
+        if (e == cudaSuccess) e = cudaMemcpy(q->dev_buf, thr, sizeof(double) * nt, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(q->dev_buf + nt, labels, sizeof(double) * (nt + 1), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_error("qce_quantizer_create: %s", cudaGetErrorString(e));
+            if (q->dev_buf) cudaFree(q->dev_buf);
+            delete q;
+            return QCE_ERR_CUDA;
+        }
+        q->t.thr = q->dev_buf;
+        q->t.labels = q->dev_buf + nt;
+    }
+    *out = q;
+    return QCE_OK;
+}
+
+void qce_quantizer_destroy(qce_quantizer* q) {
+    if (!q) return;
+    if (q->dev_buf) cudaFree(q->dev_buf);
+    delete q;
+}
+
+qce_status qce_quantize(const qce_quantizer* q, void* stream, const void* y, int64_t n, void* r_out, uint8_t* codes_out) {
+    if (!q || n < 0 || (n > 0 && !y)) { set_error("qce_quantize: invalid argument"); return QCE_ERR_INVALID; }
+    return launch_quantize(&q->t, (cudaStream_t)stream, (const double*)y, n, (double*)r_out, codes_out);
+}
+
+qce_status qce_observe_quantize(const qce_quantizer* q, void* stream, const void* h, int h_is_c64, const void* noise,
+                                double noise_scale, int64_t n, void* y_out, void* r_out, uint8_t* codes_out) {
+    if (n < 0 || (n > 0 && (!h || !noise))) { set_error("qce_observe_quantize: invalid argument"); return QCE_ERR_INVALID; }
+    if (!q && (r_out || codes_out)) { set_error("qce_observe_quantize: r/codes requested without a quantiser"); return QCE_ERR_INVALID; }
+    return launch_observe_quantize(q ? &q->t : nullptr, (cudaStream_t)stream, h, h_is_c64, (const double*)noise,
+                                   noise_scale, n, (double*)y_out, (double*)r_out, codes_out);
+}
+
+// -------------------------------------------------------------------------------------------- model
+
+qce_status qce_model_create(int n_obs, int n_ant, int n_comp, int flags, qce_model** out) {
+    if (!out || n_obs < 1 || n_ant < 1 || n_comp < 1) { set_error("qce_model_create: invalid shape"); return QCE_ERR_INVALID; }
+    qce_status st = require_device();
+    if (st) return st;
+    qce_model* m = new qce_model();
+    m->n_obs = n_obs; m->n_ant = n_ant; m->n_comp = n_comp; m->flags = flags;
+    const size_t K = n_comp, No = n_obs, N = n_ant;
+    cudaError_t e = cudaMalloc(&m->Linv, K * No * No * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->W, K * N * No * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->zoff, K * No * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->hoff, K * N * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->logc, K * 8);
+    if (e != cudaSuccess) {
+        set_error("qce_model_create: %s", cudaGetErrorString(e));
+        qce_model_destroy(m);
+        return QCE_ERR_CUDA;
+    }
+    *out = m;
+    return QCE_OK;
+}
+
+void qce_model_destroy(qce_model* m) {
+    if (!m) return;
+    tc_free(m);
+    cudaFree(m->Linv); cudaFree(m->W); cudaFree(m->zoff); cudaFree(m->hoff); cudaFree(m->logc);
+    if (m->pipe_r) cudaFree(m->pipe_r);
+    delete m;
+}
+
+qce_status qce_model_set_params(qce_model* m, void* stream, const double* Linv, const double* W, const double* zoff,
+                                const double* hoff, const double* logc, double data_scale) {
+    if (!m || !Linv || !W || !zoff || !hoff || !logc || data_scale < 0) { set_error("qce_model_set_params: invalid argument"); return QCE_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t K = m->n_comp, No = m->n_obs, N = m->n_ant;
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->Linv, Linv, K * No * No * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->W, W, K * N * No * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->zoff, zoff, K * No * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->hoff, hoff, K * N * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->logc, logc, K * 8, cudaMemcpyDeviceToDevice, s));
+    m->data_scale = data_scale;
+    m->params_set = true;
+    m->tc.ready = false;
+    if (tc_supported(m, QCE_MODE_ALL)) {
+        qce_status st = tc_pack_params(m, s);
+        if (st) return st;
+    }
+    return QCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------- estimate
+
+static qce_status check_mode(int mode, int n_top, double rho, int K) {
+    switch (mode) {
+        case QCE_MODE_ALL: case QCE_MODE_TOP1: return QCE_OK;
+        case QCE_MODE_TOPN:
+            if (n_top < 1) { set_error("n_top must be >= 1"); return QCE_ERR_INVALID; }
+            return QCE_OK;
+        case QCE_MODE_CUMPROB:
+            if (!(rho == rho)) { set_error("rho is NaN"); return QCE_ERR_INVALID; }
+            return QCE_OK;
+        default: set_error("unknown mode %d", mode); return QCE_ERR_INVALID;
+    }
+    (void)K;
+}
+
+static qce_status estimate_impl(qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
+                                int precision, double* h_est, double* logp_out, const void* h_true, int h_true_c64,
+                                double* acc) {
+    if (!m || !m->params_set) { set_error("qce_estimate: model has no parameters"); return QCE_ERR_INVALID; }
+    if (B < 0 || (B > 0 && !r)) { set_error("qce_estimate: invalid batch"); return QCE_ERR_INVALID; }
+    qce_status st = check_mode(mode, n_top, rho, m->n_comp);
+    if (st) return st;
+    if (precision == QCE_PREC_FP64)
+        return launch_dense_fp64_raw(m, s, r, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
+    if (precision == QCE_PREC_TC) {
+        if (!tc_supported(m, mode) || !m->tc.ready) {
+            set_error("tensor-core kernel does not support n_obs=%d n_ant=%d K=%d mode=%d", m->n_obs, m->n_ant, m->n_comp, mode);
+            return QCE_ERR_UNSUPPORTED;
+        }
+        return launch_dense_tc(m, s, r, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
+    }
+    set_error("unknown precision %d", precision);
+    return QCE_ERR_INVALID;
+}
+
+qce_status qce_estimate(qce_model* m, void* stream, const void* r, int64_t B, int mode, int n_top, double rho, int precision,
+                        void* h_est, double* logp_out, const void* h_true, double* acc) {
+    return estimate_impl(m, (cudaStream_t)stream, (const double*)r, B, mode, n_top, rho, precision, (double*)h_est, logp_out,
+                         h_true, 0, acc);
+}
+
+qce_status qce_pipeline(qce_model* m, const qce_quantizer* q, void* stream, const void* h, int h_is_c64, const void* noise,
+                        double noise_scale, int64_t B, int mode, int n_top, double rho, int precision, void* h_est,
+                        double* acc) {
+    if (!m || !q || B < 0 || (B > 0 && (!h || !noise))) { set_error("qce_pipeline: invalid argument"); return QCE_ERR_INVALID; }
+    if (m->n_obs != m->n_ant) { set_error("qce_pipeline: A = I requires n_obs == n_ant"); return QCE_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t N = m->n_ant;
+    // quantised pilots of one chunk live in a model-owned scratch buffer (grown on first use, then reused)
+    const int64_t chunk_max = (int64_t)1 << 20;
+    const int64_t cap = B < chunk_max ? B : chunk_max;
+    if (cap > m->pipe_cap) {
+        if (m->pipe_r) QCE_CUDA_TRY(cudaFree(m->pipe_r));
+        m->pipe_r = nullptr; m->pipe_cap = 0;
+        QCE_CUDA_TRY(cudaMalloc(&m->pipe_r, (size_t)cap * N * 16));
+        m->pipe_cap = cap;
+    }
+    const size_t hstride = h_is_c64 ? 8 : 16;
+    for (int64_t b0 = 0; b0 < B; b0 += m->pipe_cap) {
+        const int64_t nb = (B - b0) < m->pipe_cap ? (B - b0) : m->pipe_cap;
+        const char* hp = (const char*)h + (size_t)b0 * N * hstride;
+        qce_status st = launch_observe_quantize(&q->t, s, hp, h_is_c64, (const double*)noise + (size_t)b0 * N * 2, noise_scale,
+                                                nb * N, nullptr, (double*)m->pipe_r, nullptr);
+        if (st) return st;
+        st = estimate_impl(m, s, (const double*)m->pipe_r, nb, mode, n_top, rho, precision,
+                           h_est ? (double*)h_est + (size_t)b0 * N * 2 : nullptr, nullptr, hp, h_is_c64, acc);
+        if (st) return st;
+    }
+    return QCE_OK;
+}
+
+qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
+                             void* h_est_host) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
+    const size_t in_row = (size_t)m->n_obs * 16, out_row = (size_t)m->n_ant * 16;
+    // process-wide staging: two slots, each 64 MiB of pilots / estimates (pinned host + device), grown on demand
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    HostStaging* hs = &g_staging;
+    const size_t slot_bytes = (size_t)64 << 20;
+    int64_t chunk = (int64_t)(slot_bytes / (in_row > out_row ? in_row : out_row));
+    if (chunk < 128) chunk = 128;
+    {
+        const size_t need_in = (size_t)chunk * in_row, need_out = (size_t)chunk * out_row;
+        for (int i = 0; i < 2; ++i) {
+            if (!hs->streams[i]) {
+                QCE_CUDA_TRY(cudaStreamCreateWithFlags(&hs->streams[i], cudaStreamNonBlocking));
+                QCE_CUDA_TRY(cudaEventCreateWithFlags(&hs->done[i], cudaEventDisableTiming));
+            }
+            if (hs->in_bytes < need_in) {
+                if (hs->pin_in[i]) { cudaFreeHost(hs->pin_in[i]); cudaFree(hs->dev_in[i]); hs->pin_in[i] = hs->dev_in[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMallocHost(&hs->pin_in[i], need_in));
+                QCE_CUDA_TRY(cudaMalloc(&hs->dev_in[i], need_in));
+            }
+            if (hs->out_bytes < need_out) {
+                if (hs->pin_out[i]) { cudaFreeHost(hs->pin_out[i]); cudaFree(hs->dev_out[i]); hs->pin_out[i] = hs->dev_out[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMallocHost(&hs->pin_out[i], need_out));
+                QCE_CUDA_TRY(cudaMalloc(&hs->dev_out[i], need_out));
+            }
+        }
+        if (hs->in_bytes < need_in) hs->in_bytes = need_in;
+        if (hs->out_bytes < need_out) hs->out_bytes = need_out;
+    }
+    // parameters were packed on the caller's stream: make them visible to the private streams
+    QCE_CUDA_TRY(cudaDeviceSynchronize());
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly;
+    // pageable ones go through the model's pinned staging slots
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool in_pinned = is_pinned(r_host), out_pinned = is_pinned(h_est_host);
+    int64_t pending_b0[2] = {-1, -1}, pending_nb[2] = {0, 0};
+    auto drain = [&](int slot) -> qce_status {
+        if (pending_b0[slot] < 0) return QCE_OK;
+        QCE_CUDA_TRY(cudaEventSynchronize(hs->done[slot]));
+        if (!out_pinned)
+            memcpy((char*)h_est_host + (size_t)pending_b0[slot] * out_row, hs->pin_out[slot], (size_t)pending_nb[slot] * out_row);
+        pending_b0[slot] = -1;
+        return QCE_OK;
+    };
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int slot = (int)(c & 1);
+        qce_status st = drain(slot);
+        if (st) return st;
+        const int64_t b0 = c * chunk, nb = (B - b0) < chunk ? (B - b0) : chunk;
+        const char* src = (const char*)r_host + (size_t)b0 * in_row;
+        if (!in_pinned) { memcpy(hs->pin_in[slot], src, (size_t)nb * in_row); src = (const char*)hs->pin_in[slot]; }
+        cudaStream_t s = hs->streams[slot];
+        QCE_CUDA_TRY(cudaMemcpyAsync(hs->dev_in[slot], src, (size_t)nb * in_row, cudaMemcpyHostToDevice, s));
+        st = estimate_impl(m, s, (const double*)hs->dev_in[slot], nb, mode, n_top, rho, precision,
+                           (double*)hs->dev_out[slot], nullptr, nullptr, 0, nullptr);
+        if (st) return st;
+        void* dst = out_pinned ? (void*)((char*)h_est_host + (size_t)b0 * out_row) : hs->pin_out[slot];
+        QCE_CUDA_TRY(cudaMemcpyAsync(dst, hs->dev_out[slot], (size_t)nb * out_row, cudaMemcpyDeviceToHost, s));
+        QCE_CUDA_TRY(cudaEventRecord(hs->done[slot], s));
+        pending_b0[slot] = b0; pending_nb[slot] = nb;
+    }
+    for (int slot = 0; slot < 2; ++slot) {
+        qce_status st = drain(slot);
+        if (st) return st;
+    }
+    return QCE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Quantiser prologue: utils.quant (modules/utils.py:189-203) and get_observation_nbit with A = I
+// (modules/utils.py:241-251).  HBM-bound elementwise kernels: one complex sample (16 B) per thread
+// per iteration, coalesced 128-bit loads/stores, grid-stride over a grid sized in multiples of the
+// SM count.  All arithmetic is IEEE double with explicit round-to-nearest mul/add (no FMA
+// contraction) so that the quantised pilots are bit-exact to numpy for identical noise draws.
+#include "qce_common.cuh"
+
+namespace qce {
+
+// 1/np.sqrt(2) = 0x3FE6A09E667F3BCC (NOT sqrt(0.5) = ...BCD), SURVEY.md section 7 "bit-exact quantiser"
+__device__ __forceinline__ double inv_sqrt2() { return __longlong_as_double(0x3FE6A09E667F3BCCLL); }
+
+__device__ __forceinline__ double sign_np(double x) {   // np.sign: -1, 0, +1, NaN
+    return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : ((x == 0.0) ? 0.0 : x));
+}
+
+__device__ __forceinline__ int digitize(double x, const double* __restrict__ thr, int n_thr) {
+    // np.digitize(x, thr) with right=False on ascending thr: #{thr <= x}; NaN sorts last.
+    if (x != x) return n_thr;
+    int lo = 0, hi = n_thr;                // first index with thr[idx] > x
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (thr[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <bool OBSERVE, bool H_C64>
+__global__ void __launch_bounds__(256) quantize_kernel(QuantTables t, bool have_q, const void* __restrict__ src,
+                                                       const double2* __restrict__ noise, double noise_scale,
+                                                       int64_t n, double2* __restrict__ y_out,
+                                                       double2* __restrict__ r_out, uchar2* __restrict__ codes_out) {
+    extern __shared__ double s_tab[];      // thr[n_thr] then labels[n_thr + 1] (b > 1 only)
+    const int n_thr = t.n_thr;
+    if (have_q && t.n_bits > 1) {
+        for (int i = threadIdx.x; i < 2 * n_thr + 1; i += blockDim.x)
+            s_tab[i] = (i < n_thr) ? t.thr[i] : t.labels[i - n_thr];
+        __syncthreads();
+    }
+    const double* s_thr = s_tab;
+    const double* s_lab = s_tab + n_thr;
+    const double c = inv_sqrt2();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 y;
+        if (OBSERVE) {
+            double2 h;
+            if (H_C64) {
+                float2 hf = reinterpret_cast<const float2*>(src)[i];
+                h = make_double2((double)hf.x, (double)hf.y);
+            } else {
+                h = reinterpret_cast<const double2*>(src)[i];
+            }
+            double2 w = noise[i];
+            // y = h + s*n: two roundings (utils.py:247), never an FMA
+            y.x = __dadd_rn(h.x, __dmul_rn(noise_scale, w.x));
+            y.y = __dadd_rn(h.y, __dmul_rn(noise_scale, w.y));
+            if (y_out) y_out[i] = y;
+        } else {
+            y = reinterpret_cast<const double2*>(src)[i];
+        }
+        if (!have_q) continue;
+        double2 r;
+        uchar2 code;
+        if (t.n_bits == 1) {
+            double sr = sign_np(y.x), si = sign_np(y.y);
+            code.x = (sr != sr) ? 3 : (unsigned char)((int)sr + 1);
+            code.y = (si != si) ? 3 : (unsigned char)((int)si + 1);
+            if (sr != sr || si != si) {        // numpy's complex product spreads a NaN to both parts
+                r.x = r.y = __longlong_as_double(0x7FF8000000000000LL);
+            } else {
+                r.x = __dmul_rn(c, sr) + 0.0;  // + 0.0: -0 -> +0 like numpy's (c*a - 0*b)
+                r.y = __dmul_rn(c, si) + 0.0;
+            }
+        } else {
+            int ir = digitize(y.x, s_thr, n_thr), ii = digitize(y.y, s_thr, n_thr);
+            code.x = (unsigned char)ir;
+            code.y = (unsigned char)ii;
+            r.x = s_lab[ir];
+            r.y = s_lab[ii];
+        }
+        if (r_out) r_out[i] = r;
+        if (codes_out) codes_out[i] = code;
+    }
+}
+
+static int quant_grid(int64_t n) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t need = (n + 255) / 256;
+    int64_t cap = (int64_t)sms * 8;        // 8 resident CTAs of 256 threads per SM
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+qce_status launch_quantize(const QuantTables* t, cudaStream_t s, const double* y, int64_t n, double* r_out,
+                           uint8_t* codes_out) {
+    if (n == 0) return QCE_OK;
+    size_t smem = (t->n_bits > 1) ? (size_t)(2 * t->n_thr + 1) * sizeof(double) : 0;
+    quantize_kernel<false, false><<<quant_grid(n), 256, smem, s>>>(*t, true, y, nullptr, 0.0, n, nullptr,
+                                                                   (double2*)r_out, (uchar2*)codes_out);
+    QCE_CHECK_LAUNCH("quantize_kernel");
+    return QCE_OK;
+}
+
+qce_status launch_observe_quantize(const QuantTables* t, cudaStream_t s, const void* h, int h_is_c64,
+                                   const double* noise, double noise_scale, int64_t n, double* y_out, double* r_out,
+                                   uint8_t* codes_out) {
+    if (n == 0) return QCE_OK;
+    QuantTables tt{};
+    bool have_q = (t != nullptr);
+    if (have_q) tt = *t;
+    size_t smem = (have_q && tt.n_bits > 1) ? (size_t)(2 * tt.n_thr + 1) * sizeof(double) : 0;
+    if (h_is_c64)
+        quantize_kernel<true, true><<<quant_grid(n), 256, smem, s>>>(tt, have_q, h, (const double2*)noise, noise_scale,
+                                                                     n, (double2*)y_out, (double2*)r_out,
+                                                                     (uchar2*)codes_out);
+    else
+        quantize_kernel<true, false><<<quant_grid(n), 256, smem, s>>>(tt, have_q, h, (const double2*)noise, noise_scale,
+                                                                      n, (double2*)y_out, (double2*)r_out,
+                                                                      (uchar2*)codes_out);
+    QCE_CHECK_LAUNCH("observe_quantize_kernel");
+    return QCE_OK;
+}
+
+}  // namespace qce

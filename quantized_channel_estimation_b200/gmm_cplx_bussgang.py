@@ -1,0 +1,142 @@
+"""``Gmm_nbit``: Bussgang-GMM channel estimator for quantised pilots -- the API of the reference's
+``modules/gmm_cplx_bussgang.py`` (``fit`` :96-163, ``estimate_from_y`` :166-243) over the CUDA kernels.
+
+Fitted state (``means_cplx [K,N]``, ``covs_cplx [K,N,N]``, ``gm.weights_ [K]``, ``params['zero_mean']``)
+has the reference's names so that a model fitted by the reference can be transplanted with
+:meth:`Gmm_nbit.from_reference`.  Unlike the reference, ``estimate_from_y`` does not mutate the model:
+the per-(SNR, bit width, quantiser, A) parameter blocks are cached as immutable GPU handles.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import engine, precompute
+
+_SUPPORTED_TYPES = ('full', 'circulant', 'block-circulant', 'toeplitz', 'block-toeplitz')
+
+
+def _table_key(quantizer):
+    if quantizer is None or quantizer[0] is None:
+        return None
+    return (np.asarray(quantizer[0], dtype=np.float64).tobytes(), np.asarray(quantizer[1], dtype=np.float64).tobytes())
+
+
+class _PreparedCache:
+    """LRU of DenseModel handles keyed by everything _prepare_for_prediction depends on."""
+
+    def __init__(self, capacity=32):
+        self.capacity = capacity
+        self.items = {}
+
+    def get(self, key, make):
+        if key in self.items:
+            self.items[key] = self.items.pop(key)
+            return self.items[key]
+        val = make()
+        self.items[key] = val
+        while len(self.items) > self.capacity:
+            self.items.pop(next(iter(self.items)))
+        return val
+
+    def clear(self):
+        self.items.clear()
+
+
+class Gmm_nbit:
+    def __init__(self, *gmm_args, **gmm_kwargs):
+        names = ('n_components', 'covariance_type', 'tol', 'reg_covar', 'max_iter', 'n_init', 'init_params')
+        kw = dict(n_components=1, covariance_type='full', tol=1e-3, reg_covar=1e-6, max_iter=100, n_init=1,
+                  init_params='kmeans', random_state=None, verbose=0)
+        kw.update(dict(zip(names, gmm_args)))
+        kw.update(gmm_kwargs)
+        # attribute container with sklearn.mixture.GaussianMixture's names (the reference keeps one, gmm:87)
+        self.gm = SimpleNamespace(weights_=None, means_=None, covariances_=None, precisions_cholesky_=None,
+                                  converged_=False, n_iter_=0, lower_bound_=-np.inf, **kw)
+        self.means_cplx = None
+        self.covs_cplx = None
+        self.fft_covs = None
+        self.fft_means = None
+        self.chol = None
+        self.params = dict()
+        self.F2 = None
+        self.precision = 'auto'            # 'auto' | 'tc' | 'fp64' (arithmetic of the estimate kernel)
+        self._cache = _PreparedCache()
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_reference(cls, obj):
+        """Transplant a fitted reference ``Gmm_nbit`` (or anything with the same attributes)."""
+        new = cls(n_components=int(np.asarray(obj.means_cplx).shape[0]), covariance_type='full')
+        new.set_parameters(obj.means_cplx, obj.covs_cplx, obj.gm.weights_, zero_mean=obj.params.get('zero_mean', False))
+        return new
+
+    def set_parameters(self, means, covs, weights, zero_mean=False):
+        self.means_cplx = np.array(means, dtype=complex)
+        self.covs_cplx = np.array(covs, dtype=complex)
+        self.gm.weights_ = np.array(weights, dtype=float)
+        self.gm.n_components = self.means_cplx.shape[0]
+        self.gm.covariance_type = 'full'       # every type is dense after fit (gmm:110-153)
+        self.params['zero_mean'] = bool(zero_mean)
+        self._cache.clear()
+        return self
+
+    def fit(self, h, blocks=None, zero_mean=False):
+        """Fit the complex GMM with EM (reference :96-163).  See ``em.py``."""
+        from . import em
+        if self.gm.covariance_type not in _SUPPORTED_TYPES:
+            raise NotImplementedError(f'Fitting for covariance_type = {self.gm.covariance_type} is not implemented.')
+        em.fit_gmm(self, h, blocks=blocks, zero_mean=zero_mean)
+        self._cache.clear()
+        return self
+
+    # ------------------------------------------------------------------ inference
+    def _prepared(self, A, snr_dB, n_bits, quantizer_type, quantizer):
+        if self.means_cplx is None or self.covs_cplx is None or self.gm.weights_ is None:
+            raise RuntimeError('Gmm_nbit: model is not fitted (means_cplx / covs_cplx / gm.weights_ missing)')
+        if self.gm.covariance_type != 'full':
+            raise NotImplementedError(f'Estimation for covariance_type = {self.gm.covariance_type} is not implemented.')
+        A = np.asarray(A)
+        nb = 'inf' if (n_bits == 'inf' or n_bits == np.inf) else int(n_bits)
+        tables = _table_key(quantizer) if (nb != 1 and nb != 'inf' and quantizer_type == 'lloyd') else None
+        key = (float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, A.shape, A.tobytes(),
+               id(self.means_cplx), id(self.covs_cplx), id(self.gm.weights_))
+
+        def make():
+            prep = precompute.prepare(self.means_cplx, self.covs_cplx, self.gm.weights_, A, snr_dB,
+                                      np.inf if nb == 'inf' else nb, quantizer_type, quantizer)
+            return engine.DenseModel(prep, flags=0)
+        return self._cache.get(key, make)
+
+    def estimate_from_y(self, y, snr_dB, n_antennas, A=None, n_summands_or_proba=1, n_bits=1,
+                        quantizer_type='uniform', quantizer=None):
+        """Channel estimates ``[B, A.shape[-1]]`` complex128 from quantised pilots ``y [B, n_obs]``
+        (reference :166-243; arguments have the reference's meaning).  ``y`` may be a torch CUDA tensor
+        (result: CUDA tensor) or a numpy array / CPU tensor (result: numpy array / CPU tensor; the
+        host<->device copies are chunked and overlapped inside the library)."""
+        if A is None:
+            A = np.eye(n_antennas, dtype=complex)
+        model = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
+        if isinstance(y, torch.Tensor):
+            if y.is_cuda:
+                return model.estimate(y, n_summands_or_proba, self.precision)
+            return torch.from_numpy(model.estimate_host(y.numpy(), n_summands_or_proba, self.precision))
+        return model.estimate_host(y, n_summands_or_proba, self.precision)
+
+    def weighted_log_prob(self, y, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+        """``_estimate_weighted_log_prob`` of the prepared mixture (reference :369-386): ``[B, K]`` float64."""
+        if A is None:
+            A = np.eye(self.means_cplx.shape[1], dtype=complex)
+        model = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
+        yt = y if isinstance(y, torch.Tensor) and y.is_cuda else torch.as_tensor(np.asarray(y)).cuda()
+        _, lp = model.estimate(yt, 'all', 'fp64', want_logp=True)
+        return lp if isinstance(y, torch.Tensor) and y.is_cuda else lp.cpu().numpy()
+
+    def predict_proba_cplx(self, y, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+        """Responsibilities ``p(k | r)`` of the prepared mixture (reference :351-367)."""
+        lp = self.weighted_log_prob(y, snr_dB, A, n_bits, quantizer_type, quantizer)
+        if isinstance(lp, torch.Tensor):
+            return torch.softmax(lp, dim=1)
+        m = lp.max(axis=1, keepdims=True)
+        e = np.exp(lp - m)
+        return e / e.sum(axis=1, keepdims=True)

@@ -1,0 +1,118 @@
+"""Drop-in for the quantiser pieces of the reference's ``modules/utils.py``: ``quant`` (:189-203),
+``get_observation_nbit`` (:241-251), ``crandn`` (:13-14), ``get_quantizer`` / ``get_quantizer_gauss``
+(:531-590), ``cplx_1bit`` (:527-528), ``mse`` (:617-618), ``get_pilot_matrix`` semantics (:337-367).
+
+Array arguments may be torch CUDA tensors (results stay on the GPU) or numpy arrays (staged to
+the GPU and returned as numpy, like the reference).  The element-wise work runs in the CUDA kernels of
+libqce_b200.so; there is no CPU implementation here."""
+import numpy as np
+import torch
+
+from . import engine
+from .lloyd_max_quantizer import load_quantizer
+from .uniform_quantizer import get_uniform_quant_step
+
+_rng = np.random.default_rng()
+
+
+def crandn(*arg, rng=None):
+    """Circularly-symmetric complex standard normal draw (reference :13-14)."""
+    rng = _rng if rng is None else rng
+    return np.sqrt(0.5) * (rng.standard_normal(arg) + 1j * rng.standard_normal(arg))
+
+
+def _is_inf(n_bits):
+    return n_bits == 'inf' or n_bits == np.inf
+
+
+def _to_cuda(x, dtype=None):
+    if isinstance(x, torch.Tensor):
+        t = x if x.is_cuda else x.cuda()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None or t.dtype == dtype else t.to(dtype)
+
+
+def _like_input(t, proto):
+    if isinstance(proto, torch.Tensor):
+        return t if proto.is_cuda else t.cpu()
+    return t.cpu().numpy()
+
+
+def quant(inp, n_bits=1, thresholds=None, quant_labels=None):
+    """Quantise real and imaginary parts independently (reference :189-203), bit-exact."""
+    q = engine.Quantizer.get(n_bits, thresholds, quant_labels)
+    y = _to_cuda(inp, torch.complex128)
+    return _like_input(q.quantize(y), inp)
+
+
+def cplx_1bit(inp):
+    return quant(inp, 1)
+
+
+def get_observation_nbit(h, snr, A=None, n_bits=1, thresholds=None, cluster=None, agc=False, noise=None):
+    """``Q(A h + 10^(-snr/20) n)`` (reference :241-251).  ``noise`` lets the caller supply the draw
+    ``n = crandn(*y.shape)`` (the reference takes it from a module-global unseeded generator); ``h`` is
+    ``[B, N]``.  With ``A=None`` (all scripts) the synthesis and the quantiser are one fused kernel."""
+    ht = _to_cuda(h)
+    if not ht.is_complex():
+        ht = ht.to(torch.complex128)
+    if A is not None:
+        At = _to_cuda(A, torch.complex128)
+        ht = (ht.to(torch.complex128) @ At.T).contiguous()          # y = A h (plumbing GEMM, cuBLAS)
+    if noise is None:
+        noise = crandn(*ht.shape)
+    nt = _to_cuda(noise, torch.complex128)
+    scale = 10 ** (-snr / 20)
+    if _is_inf(n_bits):
+        y, _, _ = engine.observe_quantize(ht, nt, scale, None)
+        return _like_input(y, h)
+    q = engine.Quantizer.get(n_bits, thresholds, cluster)
+    _, r, _ = engine.observe_quantize(ht, nt, scale, q)
+    return _like_input(r, h)
+
+
+def get_quantizer(snrs, n_bits, quantizer_type='uniform'):
+    """Threshold / label tables per SNR: ``{snr: (thresholds, labels, rho_or_None)}`` (reference :531-562).
+    1 bit and infinite resolution need no table."""
+    quantizer = {}
+    if _is_inf(n_bits) or n_bits == 1:
+        return {snr: (None, None, None) for snr in snrs}
+    levels = int(2 ** n_bits)
+    half = (levels - 2) // 2
+    for snr in snrs:
+        if quantizer_type == 'uniform':
+            step = get_uniform_quant_step(snr, n_bits)
+            thresholds = np.zeros(levels - 1)
+            for nb in range(half):
+                thresholds[nb] = -((levels - 2) / 2 - nb) * step
+                thresholds[-nb - 1] = ((levels - 2) / 2 - nb) * step
+            labels = np.empty(levels)
+            labels[:-1] = thresholds - step / 2
+            labels[-1] = thresholds[-1] + step / 2
+            quantizer[snr] = (thresholds, labels, None)
+        elif quantizer_type == 'lloyd':
+            quantizer[snr] = load_quantizer(snr, n_bits)[snr]
+        else:
+            raise NotImplementedError(f'Quantizer type {quantizer_type} not implemented!')
+    return quantizer
+
+
+def get_quantizer_gauss(snrs, n_bits, quantizer_type='lloyd', params=None):
+    """Serial twin of :func:`get_quantizer` (reference :565-590)."""
+    return get_quantizer(snrs, n_bits, quantizer_type)
+
+
+def get_pilot_matrix(n_antennas, n_pilots=1, pilots=None):
+    """``A = kron(x, I_N)`` for a length-``n_pilots`` pilot sequence ``x`` (reference :366).  ``pilots=None``
+    gives the all-ones sequence (1 pilot: the identity, as in every script)."""
+    x = np.ones(n_pilots, dtype=complex) if pilots is None else np.asarray(pilots, dtype=complex).reshape(n_pilots)
+    return np.kron(x[:, None], np.eye(n_antennas)).astype(complex)
+
+
+def mse(h_est, h):
+    """The scripts' NMSE: ``sum |h_est - h|^2 / h.size`` (reference :617-618, Bussgang_GMM.py:289)."""
+    if isinstance(h_est, torch.Tensor) or isinstance(h, torch.Tensor):
+        a, b = torch.as_tensor(h_est), torch.as_tensor(h)
+        return float(((a - b.to(a.device)).abs() ** 2).sum() / b.numel())
+    return float(np.sum(np.abs(h_est - h) ** 2) / h.size)

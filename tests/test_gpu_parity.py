@@ -1,0 +1,232 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path, called through the C ABI,
+against (a) the golden vectors produced by the unmodified reference and (b) the numpy oracle on seeded
+inputs.  Tolerances: quantised pilots bit-exact; estimates 1e-4 relative (north_star) -- the complex128
+kernel is held to 1e-10, the tensor-core kernel to 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GMM_MODES, GMM_TAGS, MFA_MODES, MFA_TAGS, golden_quantizer_tuple, relerr
+from oracle import qce_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP64 = 1e-10
+TOL_TC = 1e-5          # FP16 hi/lo split operands, FP32 accumulation (north_star bound: 1e-4)
+
+
+@pytest.fixture(scope='module')
+def qce():
+    import quantized_channel_estimation_b200 as q
+    from quantized_channel_estimation_b200 import _lib
+    _lib.require_device()
+    return q
+
+
+def _bits_equal(a, b):
+    a = np.ascontiguousarray(a).view(np.uint64)
+    b = np.ascontiguousarray(b).view(np.uint64)
+    return np.array_equal(a, b)
+
+
+def _nb(g, tag):
+    nb = float(g[f'{tag}_nbits'])
+    return int(nb) if np.isfinite(nb) else np.inf
+
+
+# ----------------------------------------------------------------------------- quantiser: bit-exact
+
+def test_quant_golden_bit_exact(qce, golden_quant):
+    g = golden_quant
+    y = g['y']
+    ok = ~(np.isnan(y.real) | np.isnan(y.imag))
+    out = qce.quant(y, 1)
+    assert _bits_equal(out[ok], g['q1'][ok])
+    assert np.isnan(out[~ok].real).all() and np.isnan(out[~ok].imag).all()      # NaN spreads like numpy's complex product
+    qu = qce.get_quantizer([10], 2, 'uniform')[10]
+    assert _bits_equal(qce.quant(g['yu'], 2, qu[0], qu[1]), g['q2u'])
+    assert _bits_equal(qce.quant(y, 3, g['q3l_thr'], g['q3l_lab']), g['q3l'])
+
+
+def test_observation_golden_bit_exact(qce, golden_quant):
+    g = golden_quant
+    for snr in (-5, 10):
+        assert _bits_equal(qce.get_observation_nbit(g['obs_h'], snr, n_bits=1, noise=g['obs_noise']), g[f'obs1_s{snr}'])
+        qs = qce.get_quantizer([snr], 2, 'uniform')[snr]
+        assert _bits_equal(qce.get_observation_nbit(g['obs_h'], snr, n_bits=2, thresholds=qs[0], cluster=qs[1],
+                                                    noise=g['obs_noise']), g[f'obs2u_s{snr}'])
+        assert _bits_equal(qce.get_observation_nbit(g['obs_h'], snr, n_bits=np.inf, noise=g['obs_noise']), g[f'obsinf_s{snr}'])
+
+
+@pytest.mark.parametrize('nb,qt', [(1, 'uniform'), (2, 'uniform'), (3, 'lloyd'), (4, 'uniform'), (8, 'uniform')])
+def test_quant_large_vs_oracle(qce, nb, qt):
+    rng = np.random.default_rng(nb)
+    h = orc.crandn(40000, 64, rng=rng).astype(np.complex64)
+    n = orc.crandn(40000, 64, rng=rng)
+    snr = 5
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    ref = orc.get_observation_nbit(h, snr, n, None, nb, qz[0], qz[1])
+    out = qce.get_observation_nbit(h, snr, n_bits=nb, thresholds=qz[0], cluster=qz[1], noise=n)
+    assert _bits_equal(out, ref)
+    # codes reproduce the labels; torch CUDA in -> torch CUDA out
+    from quantized_channel_estimation_b200 import engine
+    q = engine.Quantizer.get(nb, qz[0], qz[1])
+    y = torch.from_numpy(orc.observe(h, snr, n)).cuda()
+    r, codes = q.quantize(y, want_codes=True)
+    assert r.is_cuda and _bits_equal(r.cpu().numpy(), ref)
+    assert np.array_equal(codes.cpu().numpy(), orc.quant_codes(orc.observe(h, snr, n), nb, qz[0]))
+
+
+def test_quant_empty_and_ragged(qce):
+    assert qce.quant(np.zeros((0, 8), complex), 1).shape == (0, 8)
+    y = orc.crandn(7, 3, rng=np.random.default_rng(0))
+    assert _bits_equal(qce.quant(y, 1), orc.quant(y, 1))
+
+
+# ----------------------------------------------------------------------------- estimates vs golden
+
+def _gmm(qce, g, tag, precision):
+    m = qce.Gmm_nbit(n_components=g[f'{tag}_means'].shape[0], covariance_type='full')
+    m.set_parameters(g[f'{tag}_means'], g[f'{tag}_covs'], g[f'{tag}_w'])
+    m.precision = precision
+    return m
+
+
+@pytest.mark.parametrize('tag', GMM_TAGS)
+def test_gmm_golden_fp64(qce, golden_gmm, tag):
+    g = golden_gmm
+    qz = golden_quantizer_tuple(g, tag)
+    m = _gmm(qce, g, tag, 'fp64')
+    N = g[f'{tag}_means'].shape[1]
+    for mtag, mode in GMM_MODES.items():
+        if f'{tag}_est_{mtag}' not in g:
+            continue
+        est = m.estimate_from_y(g[f'{tag}_r'], float(g[f'{tag}_snr']), N, A=g[f'{tag}_A'], n_summands_or_proba=mode,
+                                n_bits=_nb(g, tag), quantizer_type=str(g[f'{tag}_qtype']), quantizer=qz)
+        assert isinstance(est, np.ndarray) and est.dtype == np.complex128
+        assert relerr(est, g[f'{tag}_est_{mtag}']) < TOL_FP64, (tag, mtag)
+    lp = m.weighted_log_prob(g[f'{tag}_r'], float(g[f'{tag}_snr']), g[f'{tag}_A'], _nb(g, tag), str(g[f'{tag}_qtype']), qz)
+    np.testing.assert_allclose(lp, g[f'{tag}_wlp'], rtol=1e-11)
+    np.testing.assert_allclose(m.predict_proba_cplx(g[f'{tag}_r'], float(g[f'{tag}_snr']), g[f'{tag}_A'], _nb(g, tag),
+                                                    str(g[f'{tag}_qtype']), qz), g[f'{tag}_proba'], rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize('tag', MFA_TAGS)
+def test_mfa_golden_fp64(qce, golden_mfa, tag):
+    g = golden_mfa
+    qz = golden_quantizer_tuple(g, tag)
+    m = qce.Mofa(g[f'{tag}_means'].shape[0], g[f'{tag}_lambdas'].shape[-1], verbose=False)
+    m.set_parameters(g[f'{tag}_means'], g[f'{tag}_lambdas'], g[f'{tag}_psis'], g[f'{tag}_amps'])
+    m.precision = 'fp64'
+    np.testing.assert_allclose(m.covs, g[f'{tag}_covs'], rtol=1e-13)
+    for mtag, mode in MFA_MODES.items():
+        est = m.estimate_from_y(g[f'{tag}_r'], float(g[f'{tag}_snr']), n_summands_or_proba=mode, n_bits=_nb(g, tag),
+                                quantizer_type=str(g[f'{tag}_qtype']), quantizer=qz)
+        assert relerr(est, g[f'{tag}_est_{mtag}']) < TOL_FP64, (tag, mtag)
+    np.testing.assert_allclose(m.predict_proba(g[f'{tag}_r']), g[f'{tag}_proba'], rtol=1e-9, atol=1e-300)
+    assert np.array_equal(m.predict_proba_max(g[f'{tag}_r']), g[f'{tag}_labels'])
+
+
+# ----------------------------------------------------------------------------- estimates vs oracle, larger shapes
+
+def _case(K, N, B, snr, nb, qt, mean_scale, seed):
+    means, covs, w = orc.random_psd_gmm(K, N, seed=seed, mean_scale=mean_scale)
+    h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=seed + 1)
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    return means, covs, w, h, noise, qz, r
+
+
+@pytest.mark.parametrize('K,N,B,snr,nb,qt,ms', [
+    (16, 32, 500, 0, 1, 'uniform', 0.0),        # config 1 shape (N=32, K=16, 1-bit)
+    (64, 64, 300, 10, 1, 'uniform', 0.0),       # config 2 shape (N=64, K=64, 1-bit)
+    (64, 64, 200, -10, 1, 'uniform', 0.1),
+    (8, 64, 200, 30, 1, 'uniform', 0.0),
+    (12, 64, 200, 10, 2, 'uniform', 0.1),
+    (12, 48, 200, 10, 3, 'lloyd', 0.0),
+    (5, 20, 77, 5, 4, 'uniform', 0.2),          # ragged: N not a multiple of anything nice, B not a tile multiple
+])
+@pytest.mark.parametrize('precision', ['fp64', 'tc'])
+def test_gmm_vs_oracle(qce, K, N, B, snr, nb, qt, ms, precision):
+    from quantized_channel_estimation_b200 import _lib
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, qt, ms, seed=K + N)
+    m = qce.Gmm_nbit(n_components=K, covariance_type='full').set_parameters(means, covs, w)
+    m.precision = precision
+    tol = TOL_FP64 if precision == 'fp64' else TOL_TC
+    for mode in ('all', 1, 3, 0.95):
+        ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
+                                      quantizer=qz)
+        try:
+            est = m.estimate_from_y(torch.from_numpy(r).cuda(), snr, N, n_summands_or_proba=mode, n_bits=nb,
+                                    quantizer_type=qt, quantizer=qz)
+        except _lib.QceError as e:
+            if precision == 'tc' and e.status == _lib.ERR_UNSUPPORTED:
+                pytest.skip(f'tensor-core kernel does not cover this shape/mode: {e}')
+            raise
+        assert est.is_cuda and est.dtype == torch.complex128
+        est = est.cpu().numpy()
+        if mode == 'all' or precision == 'fp64':
+            assert relerr(est, ref) < tol, (mode, relerr(est, ref))
+        else:
+            # hard selections can flip for near-ties under FP32 log-likelihoods: compare per sample, allow a few flips
+            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert np.mean(per > 1e-4) < 0.02, (mode, np.sort(per)[-5:])
+    # NMSE within 0.01 dB of the oracle's (north_star)
+    ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+    est = m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+    d_db = 10 * np.log10(orc.mse(est, h) / orc.mse(ref, h))
+    assert abs(d_db) < 0.01
+
+
+def test_pipeline_matches_stepwise(qce):
+    """Fused observe->quantise->estimate->NMSE equals the three reference-API calls and the oracle."""
+    from quantized_channel_estimation_b200 import engine
+    K, N, B, snr = 16, 32, 3000, 5
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.0, seed=3)
+    m = qce.Gmm_nbit(n_components=K, covariance_type='full').set_parameters(means, covs, w)
+    model = m._prepared(np.eye(N, dtype=complex), snr, 1, 'uniform', None)
+    q = engine.Quantizer.get(1)
+    h64 = h.astype(np.complex64)
+    r64 = orc.get_observation_nbit(h64, snr, noise, None, 1)
+    ref = orc.gmm_estimate_from_y(means, covs, w, r64, snr, n_summands_or_proba='all', n_bits=1)
+    for prec in ('fp64', 'auto'):
+        est, acc = model.pipeline(q, torch.from_numpy(h64).cuda(), torch.from_numpy(noise).cuda(), 10 ** (-snr / 20), 'all',
+                                  prec, want_est=True)
+        acc = acc.cpu().numpy()
+        assert relerr(est.cpu().numpy(), ref) < (TOL_FP64 if prec == 'fp64' else TOL_TC)
+        assert acc[2] == B
+        np.testing.assert_allclose(acc[0] / (B * N), orc.mse(ref, h64.astype(complex)), rtol=1e-6)
+        np.testing.assert_allclose(acc[1], np.sum(np.abs(h64.astype(complex)) ** 2), rtol=1e-12)
+
+
+def test_linearity_and_batch_invariance_full_size(qce):
+    """Size-independent properties at the BASELINE shape (N=64, K=64, 1-bit, 2^17 pilots): estimates do not
+    depend on how the batch is tiled or ordered, and with a single component the estimator is linear in r."""
+    K, N, B, snr = 64, 64, 1 << 17, 10
+    means, covs, w = orc.random_psd_gmm(K, N, seed=0)
+    m = qce.Gmm_nbit(n_components=K, covariance_type='full').set_parameters(means, covs, w)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    bits = torch.randint(0, 2, (B, N, 2), generator=g, device='cuda', dtype=torch.int8)
+    r = torch.view_as_complex(((bits.double() * 2 - 1) / np.sqrt(2)).contiguous())
+    full = m.estimate_from_y(r, snr, N, n_summands_or_proba='all')
+    perm = torch.randperm(B, generator=g, device='cuda')
+    part = m.estimate_from_y(r[perm][:50001].contiguous(), snr, N, n_summands_or_proba='all')
+    assert torch.equal(part, full[perm][:50001])
+    # spot-check 64 rows of the full batch against the oracle
+    idx = np.arange(0, B, B // 64)
+    ref = orc.gmm_estimate_from_y(means, covs, w, r[idx].cpu().numpy(), snr, n_summands_or_proba='all', n_bits=1)
+    assert relerr(full[idx].cpu().numpy(), ref) < TOL_TC
+    m1 = qce.Gmm_nbit(n_components=1, covariance_type='full').set_parameters(means[:1], covs[:1], [1.0])
+    a = m1.estimate_from_y(r[:4096].contiguous(), snr, N, n_summands_or_proba='all')
+    b = m1.estimate_from_y((-r[:4096]).contiguous(), snr, N, n_summands_or_proba='all')
+    assert float((a + b).abs().max()) < 1e-5 * float(a.abs().max())
+
+
+def test_host_and_device_entry_points_agree(qce):
+    K, N, B, snr = 8, 32, 300000, 0         # > two staging chunks -> exercises the double-buffered host path
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.0, seed=9)
+    m = qce.Gmm_nbit(n_components=K, covariance_type='full').set_parameters(means, covs, w)
+    a = m.estimate_from_y(r, snr, N, n_summands_or_proba='all')
+    b = m.estimate_from_y(torch.from_numpy(r).cuda(), snr, N, n_summands_or_proba='all').cpu().numpy()
+    assert np.array_equal(a, b)
+    assert m.estimate_from_y(np.zeros((0, N), complex), snr, N, n_summands_or_proba='all').shape == (0, N)
