@@ -1,12 +1,562 @@
-// placeholder until the tcgen05 kernel lands
+// Tensor-core estimate kernel (QCE_PREC_TC): tcgen05.mma + TMEM accumulators + bulk-TMA operand staging.
+//
+// Maths (mode 'all', reference modules/gmm_cplx_bussgang.py:220-228 after _prepare_for_prediction):
+//     l_k = logc_k - |Linv_k r - zoff_k|^2,   h = sum_k softmax(l)_k (W_k r + hoff_k)
+// Formulation as real GEMMs.  A complex matrix-vector product is the real product with the 2x2-block
+// embedding E[2i+a][2j+b] = {Re, -Im; Im, Re}, vectors interleaved (re, im).  One sample tile is 128
+// pilots (the MMA M dimension, one TMEM lane per pilot); for component k the tensor core computes
+//     Z = R * E(Linv_k)^T   [128 x 2No]      H = R * E(W_k)^T   [128 x 2N]
+// with FP32 accumulators in TMEM.  Precision: the quantised pilots are small integers times a known
+// scale (1 bit: +-1; uniform b bit: odd integers), i.e. EXACT in FP16, so only the parameter operand is
+// split, P = P_hi + P_lo (two FP16 terms, ~22 significant bits after a per-matrix power-of-two scale),
+// and every GEMM is two kind::f16 passes accumulating into the same TMEM tile.
+//
+// CTA organisation (persistent, one CTA per SM, 384 threads):
+//   warp 0      bulk-TMA producer: streams the pre-formatted operand images of (Linv_hi, Linv_lo, W_hi, W_lo)
+//               of component k = 0..K-1 through a ring of shared-memory stages (cp.async.bulk + mbarrier tx)
+//   warp 1      MMA issuer (one elected thread): each staged image is used for BOTH resident sample tiles
+//               (256 pilots per CTA share one operand fetch), tcgen05.commit releases stages / publishes tiles
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue warpgroup of tile 0, warps 8-11 of tile 1: one thread per pilot; tcgen05.ld the
+//               whitened row -> |z|^2 -> l_k -> lazily rescaled online softmax -> FMA of the LMMSE row into
+//               128 register accumulators.  Per-component estimates never leave the SM.
+// The Z and H accumulators of the two tiles form a 4-deep ring: while the epilogue drains Z(k) the
+// tensor core produces H(k), then Z(k+1), ...
+#include <math.h>
+
 #include "qce_common.cuh"
+
 namespace qce {
-bool tc_supported(const qce_model*, int) { return false; }
-qce_status tc_pack_params(qce_model*, cudaStream_t) { return QCE_OK; }
-void tc_free(qce_model*) {}
-qce_status launch_dense_tc(const qce_model*, cudaStream_t, const double*, int64_t, int, int, double, double*, double*,
-                           const void*, int, double*) {
-    set_error("tensor-core kernel not built");
+
+constexpr int TILE_M = 128;
+constexpr int TILES = 2;
+constexpr int NUM_THREADS = 384;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct TcArgs {
+    const __half* image;       // [K][ Lhi | Llo | Whi | Wlo ] pre-formatted canonical K-major core-matrix images
+    const float* zscale;       // [K] 2^-e of the Linv image
+    const float* hscale;       // [K]
+    const float* zoff;         // [K][2No] fp32 (only if OFFS)
+    const float* hoff;         // [K][2N]
+    const double* logc;        // [K]
+    const double2* r;          // [B][No]
+    double2* h_est;            // [B][N] or null
+    const void* h_true;        // [B][N] c64/c128 or null
+    int h_true_c64;
+    double* acc;               // [3] or null
+    int64_t B;
+    int K, No, N;
+    double inv_data_scale;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 8000000000LL) {      // ~4 s: a protocol bug must not hang the GPU
+            printf("qce dense_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major, no-swizzle canonical layout: 8x16B core matrices; LBO = byte step between the two K-adjacent core
+// matrices of one MMA, SBO = byte step between M/N-adjacent core matrices (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;        // descriptor version 1 (Blackwell)
+    return d;                      // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n_cols) {
+    // c_format F32 (bit 4), a/b format F16 (0), a/b K-major (0), N>>3 at bit 17, M>>4 at bit 24
+    return (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int NZ, int NH>
+struct TcCfg {
+    static constexpr int KD = NZ;                                   // GEMM reduction length 2*n_obs
+    static constexpr int A_TILE_BYTES = TILE_M * KD * 2;
+    static constexpr int Z_BYTES = NZ * KD * 2, H_BYTES = NH * KD * 2;
+    static constexpr int STAGE_BYTES = Z_BYTES > H_BYTES ? Z_BYTES : H_BYTES;
+    static constexpr int CTRL_BYTES = 1024;
+    static constexpr int STAGES_FIT = (SMEM_LIMIT - TILES * A_TILE_BYTES - CTRL_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int SMEM_BYTES = TILES * A_TILE_BYTES + STAGES * STAGE_BYTES + CTRL_BYTES;
+    static constexpr int COMP_HALFS = 2 * NZ * KD + 2 * NH * KD;    // halfs per component image
+    static constexpr int TMEM_COLS_USED = TILES * (NZ + NH);
+    static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
+                                     : TMEM_COLS_USED <= 256 ? 256 : 512;
+    static_assert(STAGES >= 2, "operand ring needs at least two stages");
+    static_assert(TMEM_COLS_USED <= 512, "accumulators exceed TMEM");
+};
+
+// control block at the end of dynamic smem
+struct TcCtrl {
+    uint64_t full[8], empty[8];
+    uint64_t zfull[TILES], zempty[TILES], hfull[TILES], hempty[TILES];
+    uint64_t a_ready;
+    uint32_t tmem_base;
+    uint32_t pad;
+    unsigned char bad[TILES * TILE_M];
+};
+static_assert(sizeof(TcCtrl) <= 1024, "control block");
+
+template <int NCHZ, int NCHH, bool OFFS>
+__global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
+    constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
+    using Cfg = TcCfg<NZ, NH>;
+    constexpr int KD = Cfg::KD;
+    constexpr int S = Cfg::STAGES;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + TILES * Cfg::A_TILE_BYTES;
+    TcCtrl* ctrl = reinterpret_cast<TcCtrl*>(sB + S * Cfg::STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_pairs = (a.B + TILES * TILE_M - 1) / (TILES * TILE_M);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&ctrl->full[i]), 1); mbar_init(smem_u32(&ctrl->empty[i]), 1); }
+        for (int t = 0; t < TILES; ++t) {
+            mbar_init(smem_u32(&ctrl->zfull[t]), 1); mbar_init(smem_u32(&ctrl->hfull[t]), 1);
+            mbar_init(smem_u32(&ctrl->zempty[t]), TILE_M); mbar_init(smem_u32(&ctrl->hempty[t]), TILE_M);
+        }
+        mbar_init(smem_u32(&ctrl->a_ready), TILES * TILE_M);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < TILES * TILE_M) ctrl->bad[threadIdx.x] = 0;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctrl->tmem_base;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0 && lane == 0) {
+            // ===================== bulk-TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                for (int k = 0; k < a.K; ++k) {
+                    const __half* comp = a.image + (size_t)k * Cfg::COMP_HALFS;
+                    #pragma unroll
+                    for (int mtx = 0; mtx < 4; ++mtx) {
+                        const uint32_t bytes = (mtx < 2) ? Cfg::Z_BYTES : Cfg::H_BYTES;
+                        const __half* src = comp + (mtx < 2 ? mtx * NZ * KD : 2 * NZ * KD + (mtx - 2) * NH * KD);
+                        mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1);
+                        mbar_expect_tx(smem_u32(&ctrl->full[stage]), bytes);
+                        bulk_g2s(smem_u32(sB + stage * Cfg::STAGE_BYTES), src, bytes, smem_u32(&ctrl->full[stage]));
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===================== MMA issuer
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            uint32_t zph[TILES] = {0, 0}, hph[TILES] = {0, 0};    // parity of the *empty* barriers we wait on
+            constexpr uint32_t A_LBO = (TILE_M / 8) * 128, A_SBO = 128;
+            constexpr uint32_t IDESC_Z = make_idesc(NZ), IDESC_H = make_idesc(NH);
+            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                mbar_wait(smem_u32(&ctrl->a_ready), a_phase);
+                a_phase ^= 1;
+                tc_fence_after();
+                for (int k = 0; k < a.K; ++k) {
+                    #pragma unroll
+                    for (int mtx = 0; mtx < 4; ++mtx) {
+                        const bool isz = mtx < 2, lo = mtx & 1;
+                        const int ncols = isz ? NZ : NH;
+                        const uint32_t b_lbo = (ncols / 8) * 128, b_sbo = 128;
+                        mbar_wait(smem_u32(&ctrl->full[stage]), phase);
+                        tc_fence_after();
+                        const uint32_t b_base = smem_u32(sB + stage * Cfg::STAGE_BYTES);
+                        #pragma unroll
+                        for (int t = 0; t < TILES; ++t) {
+                            const uint32_t d = tmem_base + t * (NZ + NH) + (isz ? 0 : NZ);
+                            if (!lo) {   // first pass overwrites the accumulator: the epilogue must have drained it
+                                if (isz) { mbar_wait(smem_u32(&ctrl->zempty[t]), zph[t] ^ 1); zph[t] ^= 1; }
+                                else { mbar_wait(smem_u32(&ctrl->hempty[t]), hph[t] ^ 1); hph[t] ^= 1; }
+                                tc_fence_after();
+                            }
+                            const uint32_t a_base = smem_u32(sA + t * Cfg::A_TILE_BYTES);
+                            #pragma unroll
+                            for (int ks = 0; ks < KD / 16; ++ks) {
+                                const uint64_t ad = make_desc(a_base + ks * 2 * A_LBO, A_LBO, A_SBO);
+                                const uint64_t bd = make_desc(b_base + ks * 2 * b_lbo, b_lbo, b_sbo);
+                                umma_f16(d, ad, bd, isz ? IDESC_Z : IDESC_H, (lo || ks > 0) ? 1u : 0u);
+                            }
+                            if (lo) tc_commit(smem_u32(isz ? &ctrl->zfull[t] : &ctrl->hfull[t]));
+                        }
+                        tc_commit(smem_u32(&ctrl->empty[stage]));
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ===================== epilogue warpgroups: one thread per pilot
+        const int t = (warp - 4) >> 2;                 // tile within the pair
+        const int wq = warp & 3;                       // TMEM lane quadrant of this warp
+        const int wg_warp = (warp - 4) & 3;
+        const int row = wq * 32 + lane;
+        unsigned char* sAt = sA + t * Cfg::A_TILE_BYTES;
+        const uint32_t tz = tmem_base + ((uint32_t)(wq * 32) << 16) + t * (NZ + NH);
+        const uint32_t th = tz + NZ;
+        uint32_t zph = 0, hph = 0;
+        const int No = a.No, N = a.N;
+        double err = 0.0, pw = 0.0, cnt = 0.0;
+
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const int64_t tile_base = (pair * TILES + t) * TILE_M;
+            // ---- prologue: pilots -> exact FP16 integers in the canonical K-major core-matrix layout
+            {
+                constexpr int CORES = (TILE_M / 8) * (KD / 8);
+                #pragma unroll 8
+                for (int c = wg_warp; c < CORES; c += 4) {
+                    const int mb = c % (TILE_M / 8), kb = c / (TILE_M / 8);
+                    const int rr = mb * 8 + (lane & 7), j = kb * 4 + (lane >> 3);
+                    double2 v = make_double2(0.0, 0.0);
+                    if (tile_base + rr < a.B) v = __ldg(a.r + (tile_base + rr) * No + j);
+                    const double mr = v.x * a.inv_data_scale, mi = v.y * a.inv_data_scale;
+                    const double qr = rint(mr), qi = rint(mi);
+                    // off-grid or out-of-range data cannot be represented exactly: poison the row (NaN output)
+                    if (!(fabs(mr - qr) <= 1e-6 * fmax(1.0, fabs(qr)) && fabs(mi - qi) <= 1e-6 * fmax(1.0, fabs(qi)) &&
+                          fabs(qr) <= 2048.0 && fabs(qi) <= 2048.0))
+                        ctrl->bad[t * TILE_M + rr] = 1;
+                    const __half2 hv = __floats2half2_rn((float)qr, (float)qi);
+                    *reinterpret_cast<__half2*>(sAt + (kb * (TILE_M / 8) + mb) * 128 + (lane & 7) * 16 + (lane >> 3) * 4) = hv;
+                }
+                fence_proxy_async();
+                mbar_arrive(smem_u32(&ctrl->a_ready));
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+            }
+            const bool row_bad = ctrl->bad[t * TILE_M + row] != 0;
+
+            float acc[NH];
+            #pragma unroll
+            for (int j = 0; j < NH; ++j) acc[j] = 0.f;
+            double mref = 0.0;
+            float ssum = 0.f;
+
+            for (int k = 0; k < a.K; ++k) {
+                // ---- whitened residual -> quadratic form
+                mbar_wait(smem_u32(&ctrl->zfull[t]), zph);
+                zph ^= 1;
+                tc_fence_after();
+                const float zs = __ldg(a.zscale + k);
+                double q = 0.0;
+                #pragma unroll
+                for (int ch = 0; ch < NCHZ; ++ch) {
+                    float v[32];
+                    tmem_ld32(tz + ch * 32, v);
+                    tmem_ld_wait();
+                    #pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        float s0 = 0.f, s1 = 0.f;
+                        #pragma unroll
+                        for (int u = 0; u < 8; u += 2) {
+                            float z0 = v[g8 * 8 + u], z1 = v[g8 * 8 + u + 1];
+                            if (OFFS) {
+                                z0 = fmaf(z0, zs, -__ldg(a.zoff + (size_t)k * NZ + ch * 32 + g8 * 8 + u));
+                                z1 = fmaf(z1, zs, -__ldg(a.zoff + (size_t)k * NZ + ch * 32 + g8 * 8 + u + 1));
+                            }
+                            s0 = fmaf(z0, z0, s0);
+                            s1 = fmaf(z1, z1, s1);
+                        }
+                        q += (double)(s0 + s1);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(smem_u32(&ctrl->zempty[t]));
+                if (!OFFS) q *= (double)zs * (double)zs;
+                const double l = __ldg(a.logc + k) - q;
+                // ---- lazily rescaled online softmax (reference maximum moves only on jumps > 8)
+                float p;
+                if (k == 0) {
+                    mref = l; p = 1.f; ssum = 1.f;
+                } else {
+                    float df = (float)(l - mref);
+                    if (df > 8.f) {
+                        const float sc = __expf(-df);
+                        ssum *= sc;
+                        #pragma unroll
+                        for (int j = 0; j < NH; ++j) acc[j] *= sc;
+                        mref = l;
+                        df = 0.f;
+                    }
+                    p = __expf(df);
+                    ssum += p;
+                }
+                // ---- LMMSE row, weighted accumulation
+                mbar_wait(smem_u32(&ctrl->hfull[t]), hph);
+                hph ^= 1;
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, p > 1e-30f)) {
+                    const float ph = p * __ldg(a.hscale + k);
+                    #pragma unroll
+                    for (int ch = 0; ch < NCHH; ++ch) {
+                        float v[32];
+                        tmem_ld32(th + ch * 32, v);
+                        tmem_ld_wait();
+                        #pragma unroll
+                        for (int u = 0; u < 32; ++u) {
+                            acc[ch * 32 + u] = fmaf(ph, v[u], acc[ch * 32 + u]);
+                            if (OFFS) acc[ch * 32 + u] = fmaf(p, __ldg(a.hoff + (size_t)k * NH + ch * 32 + u), acc[ch * 32 + u]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(smem_u32(&ctrl->hempty[t]));
+            }
+
+            // ---- finalise: normalise, write the estimate row, NMSE accumulators
+            const int64_t g = tile_base + row;
+            if (g < a.B) {
+                const float invs = row_bad ? __int_as_float(0x7fc00000) : 1.f / ssum;
+                double2* out = a.h_est ? a.h_est + g * N : nullptr;
+                #pragma unroll
+                for (int j = 0; j < NH / 2; ++j) {
+                    const double2 e = make_double2((double)(acc[2 * j] * invs), (double)(acc[2 * j + 1] * invs));
+                    if (out) out[j] = e;
+                    if (a.acc && a.h_true) {
+                        double2 h;
+                        if (a.h_true_c64) {
+                            const float2 hf = reinterpret_cast<const float2*>(a.h_true)[g * N + j];
+                            h = make_double2((double)hf.x, (double)hf.y);
+                        } else {
+                            h = reinterpret_cast<const double2*>(a.h_true)[g * N + j];
+                        }
+                        const double dx = e.x - h.x, dy = e.y - h.y;
+                        err += dx * dx + dy * dy;
+                        pw += h.x * h.x + h.y * h.y;
+                    }
+                }
+                cnt += 1.0;
+            }
+            ctrl->bad[t * TILE_M + row] = 0;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");   // flags cleared before the next prologue sets them
+        }
+        if (a.acc) {
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                err += __shfl_xor_sync(0xffffffffu, err, off);
+                pw += __shfl_xor_sync(0xffffffffu, pw, off);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+            }
+            if (lane == 0 && cnt > 0.0) {
+                atomicAdd(a.acc + 0, err);
+                atomicAdd(a.acc + 1, pw);
+                atomicAdd(a.acc + 2, cnt);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ parameter packing
+// One block per (component, matrix): power-of-two scale to put the largest entry in [2^12, 2^13), then the FP16
+// hi/lo images of the real 2x2-block embedding in the canonical layout (core (nb, kb) at ((kb * ncols/8) + nb) * 128 B).
+__global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict__ Linv, const double2* __restrict__ W, int No, int N,
+                                                      double data_scale, __half* __restrict__ image, float* __restrict__ zscale,
+                                                      float* __restrict__ hscale) {
+    const int k = blockIdx.x >> 1, which = blockIdx.x & 1;
+    const int R = which ? N : No, C = No;
+    const double2* src = which ? W + (size_t)k * N * No : Linv + (size_t)k * No * No;
+    __shared__ double smax[256];
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < R * C; i += 256) {
+        const double2 v = src[i];
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+    smax[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + s]);
+        __syncthreads();
+    }
+    mx = smax[0] * data_scale;
+    int ex = 0;
+    if (mx > 0.0 && isfinite(mx)) frexp(mx, &ex);          // mx = f * 2^ex, f in [0.5, 1)
+    const int e = (mx > 0.0 && isfinite(mx)) ? 13 - ex : 0;
+    const double sc = ldexp(data_scale, e);
+    if (threadIdx.x == 0) (which ? hscale : zscale)[k] = (float)ldexp(1.0, -e);
+    const int ncols = 2 * R, kd = 2 * No;
+    const size_t comp_halfs = (size_t)2 * (2 * No) * kd + (size_t)2 * (2 * N) * kd;
+    __half* hi = image + (size_t)k * comp_halfs + (which ? (size_t)2 * (2 * No) * kd : 0);
+    __half* lo = hi + (size_t)ncols * kd;
+    const int nbs = ncols / 8;
+    for (int idx = threadIdx.x; idx < ncols * kd; idx += 256) {
+        const int core = idx >> 6, within = idx & 63;
+        const int nb = core % nbs, kb = core / nbs;
+        const int n = nb * 8 + (within >> 3), kk = kb * 8 + (within & 7);
+        const double2 v = src[(size_t)(n >> 1) * C + (kk >> 1)];
+        const int aa = n & 1, bb = kk & 1;
+        const double x = (aa == bb ? v.x : (aa ? v.y : -v.y)) * sc;
+        const __half h = __double2half(x);
+        hi[idx] = h;
+        lo[idx] = __double2half(x - (double)__half2float(h));
+    }
+}
+
+__global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const double2* __restrict__ hoff, const double* __restrict__ logc,
+                                     int K, int No, int N, float* __restrict__ zoff_f, float* __restrict__ hoff_f, int* __restrict__ nonzero) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int nz = 0;
+    if (i < K * No) { const double2 v = zoff[i]; zoff_f[2 * i] = (float)v.x; zoff_f[2 * i + 1] = (float)v.y; nz |= (v.x != 0.0 || v.y != 0.0); }
+    if (i < K * N) { const double2 v = hoff[i]; hoff_f[2 * i] = (float)v.x; hoff_f[2 * i + 1] = (float)v.y; nz |= (v.x != 0.0 || v.y != 0.0); }
+    if (nz) atomicOr(nonzero, 1);
+    (void)logc;
+}
+
+bool tc_supported(const qce_model* m, int mode) {
+    if (mode != QCE_MODE_ALL) return false;
+    if (m->n_obs % 16 || m->n_ant % 16 || m->n_obs > 64 || m->n_ant > 64) return false;
+    if (!(m->data_scale > 0.0)) return false;
+    return true;
+}
+
+void tc_free(qce_model* m) {
+    TcParams& p = m->tc;
+    cudaFree(p.image); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc);
+    p = TcParams();
+}
+
+qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
+    TcParams& p = m->tc;
+    const size_t K = m->n_comp, No = m->n_obs, N = m->n_ant;
+    const size_t comp_halfs = 2 * (2 * No) * (2 * No) + 2 * (2 * N) * (2 * No);
+    if (!p.image) {
+        p.image_bytes = K * comp_halfs * sizeof(__half);
+        QCE_CUDA_TRY(cudaMalloc(&p.image, p.image_bytes));
+        QCE_CUDA_TRY(cudaMalloc(&p.zoff, K * 2 * No * sizeof(float)));
+        QCE_CUDA_TRY(cudaMalloc(&p.hoff, K * 2 * N * sizeof(float)));
+        QCE_CUDA_TRY(cudaMalloc(&p.zscale, K * sizeof(float)));
+        QCE_CUDA_TRY(cudaMalloc(&p.hscale, K * sizeof(float)));
+        QCE_CUDA_TRY(cudaMalloc(&p.logc, sizeof(int)));          // reused as the "offsets non-zero" flag
+    }
+    int* flag = reinterpret_cast<int*>(p.logc);
+    QCE_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    tc_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+                                                     (__half*)p.image, p.zscale, p.hscale);
+    QCE_CHECK_LAUNCH("tc_pack_kernel");
+    const size_t nmax = K * (No > N ? No : N);
+    tc_pack_small_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, s>>>((const double2*)m->zoff, (const double2*)m->hoff, m->logc, (int)K,
+                                                                        (int)No, (int)N, p.zoff, p.hoff, flag);
+    QCE_CHECK_LAUNCH("tc_pack_small_kernel");
+    int h_flag = 0;
+    QCE_CUDA_TRY(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    QCE_CUDA_TRY(cudaStreamSynchronize(s));
+    p.passes = h_flag ? 3 : 2;     // here: 3 = "has offsets" marker, the MMA always runs two passes
+    p.ready = true;
+    return QCE_OK;
+}
+
+template <int NCHZ, int NCHH, bool OFFS>
+static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
+    using Cfg = TcCfg<32 * NCHZ, 32 * NCHH>;
+    static bool attr_set = false;
+    auto kern = dense_tc_kernel<NCHZ, NCHH, OFFS>;
+    if (!attr_set) {
+        QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n_pairs = (a.B + TILES * TILE_M - 1) / (TILES * TILE_M);
+    const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
+    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, s>>>(a);
+    QCE_CHECK_LAUNCH("dense_tc_kernel");
+    return QCE_OK;
+}
+
+template <int NCHZ, int NCHH>
+static qce_status launch_offs(const TcArgs& a, bool offs, cudaStream_t s) {
+    return offs ? launch_cfg<NCHZ, NCHH, true>(a, s) : launch_cfg<NCHZ, NCHH, false>(a, s);
+}
+
+qce_status launch_dense_tc(const qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
+                           double* h_est, double* logp_out, const void* h_true, int h_true_c64, double* acc) {
+    (void)n_top; (void)rho;
+    if (B == 0) return QCE_OK;
+    if (logp_out) { set_error("tensor-core kernel does not export log-probabilities"); return QCE_ERR_UNSUPPORTED; }
+    if (mode != QCE_MODE_ALL) { set_error("tensor-core kernel: mode %d not supported", mode); return QCE_ERR_UNSUPPORTED; }
+    const TcParams& p = m->tc;
+    TcArgs a;
+    a.image = (const __half*)p.image; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
+    a.logc = m->logc; a.r = (const double2*)r; a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
+    a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant; a.inv_data_scale = 1.0 / m->data_scale;
+    const bool offs = p.passes == 3;
+    const int cz = m->n_obs / 16, ch = m->n_ant / 16;
+#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) return launch_offs<Z, H>(a, offs, s);
+    QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
+#undef QCE_TC_CASE
+    set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant);
     return QCE_ERR_UNSUPPORTED;
 }
+
 }  // namespace qce
