@@ -52,12 +52,13 @@ struct qce_quantizer {
 struct TcParams {
     void* image = nullptr;      // packed FP16 hi/lo operand images, device
     size_t image_bytes = 0;
-    float* zoff = nullptr;      // [K][2*n_obs] scaled whitened offsets (fp32)
+    float* zoff = nullptr;      // [K][2*n_obs] whitened offsets (fp32)
     float* hoff = nullptr;      // [K][2*n_ant]
-    float* logc = nullptr;      // [K]
-    float* zscale = nullptr;    // [K] scale folded out of Linv_k images
+    float* zscale = nullptr;    // [K] power-of-two scale folded out of the Linv_k image
     float* hscale = nullptr;    // [K]
-    int passes = 0;             // 2 (exact data) or 3
+    int* flags = nullptr;       // device scratch: [0] offsets non-zero, [1] some Linv_k not lower triangular
+    bool has_offsets = false;
+    bool triangular = false;
     bool ready = false;
 };
 

@@ -12,16 +12,19 @@
 // and every GEMM is two kind::f16 passes accumulating into the same TMEM tile.
 //
 // CTA organisation (persistent, one CTA per SM, 384 threads):
-//   warp 0      bulk-TMA producer: streams the pre-formatted operand images of (Linv_hi, Linv_lo, W_hi, W_lo)
-//               of component k = 0..K-1 through a ring of shared-memory stages (cp.async.bulk + mbarrier tx)
-//   warp 1      MMA issuer (one elected thread): each staged image is used for BOTH resident sample tiles
-//               (256 pilots per CTA share one operand fetch), tcgen05.commit releases stages / publishes tiles
+//   warp 0      bulk-TMA producer: streams the pre-formatted operand image of component k = 0..K-1 -- the stacked
+//               matrix [E(Linv_k); E(W_k)] (so one MMA of N = 2No + 2N columns yields Z|H at once), hi then lo
+//               term, each in two K-halves -- through a ring of shared-memory stages (cp.async.bulk + mbarrier tx)
+//   warp 1      MMA issuer (one elected thread): each staged chunk is used for BOTH resident sample tiles
+//               (256 pilots per CTA share one operand fetch), tile-major so the tiles' accumulators complete half
+//               a component apart; Linv_k is lower triangular, so K-step ks only feeds columns >= 16 ks and the
+//               MMA is issued with the shrunken N; tcgen05.commit releases stages / publishes accumulators
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue warpgroup of tile 0, warps 8-11 of tile 1: one thread per pilot; tcgen05.ld the
 //               whitened row -> |z|^2 -> l_k -> lazily rescaled online softmax -> FMA of the LMMSE row into
 //               128 register accumulators.  Per-component estimates never leave the SM.
-// The Z and H accumulators of the two tiles form a 4-deep ring: while the epilogue drains Z(k) the
-// tensor core produces H(k), then Z(k+1), ...
+// The two tiles ping-pong: while the epilogue warpgroup of tile 0 drains Z|H(k), the tensor core produces
+// Z|H(k) of tile 1, and so on.
 #include <math.h>
 
 #include "qce_common.cuh"
@@ -48,6 +51,7 @@ struct TcArgs {
     int64_t B;
     int K, No, N;
     double inv_data_scale;
+    int tri;                   // Linv_k lower triangular (Cholesky whitening): skip the structurally zero columns
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -128,25 +132,27 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 template <int NZ, int NH>
 struct TcCfg {
     static constexpr int KD = NZ;                                   // GEMM reduction length 2*n_obs
+    static constexpr int NT = NZ + NH;                              // fused MMA N: Z columns then H columns
     static constexpr int A_TILE_BYTES = TILE_M * KD * 2;
-    static constexpr int Z_BYTES = NZ * KD * 2, H_BYTES = NH * KD * 2;
-    static constexpr int STAGE_BYTES = Z_BYTES > H_BYTES ? Z_BYTES : H_BYTES;
+    static constexpr int KSPS = KD / 32;                            // K-steps (of 16) per staged chunk = half the K range
+    static constexpr int STAGE_BYTES = NT * (KD / 2) * 2;           // one K-half of the stacked hi (or lo) image
     static constexpr int CTRL_BYTES = 1024;
     static constexpr int STAGES_FIT = (SMEM_LIMIT - TILES * A_TILE_BYTES - CTRL_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int SMEM_BYTES = TILES * A_TILE_BYTES + STAGES * STAGE_BYTES + CTRL_BYTES;
-    static constexpr int COMP_HALFS = 2 * NZ * KD + 2 * NH * KD;    // halfs per component image
-    static constexpr int TMEM_COLS_USED = TILES * (NZ + NH);
+    static constexpr int COMP_HALFS = 2 * NT * KD;                  // halfs per component image: hi then lo
+    static constexpr int TMEM_COLS_USED = TILES * NT;
     static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
                                      : TMEM_COLS_USED <= 256 ? 256 : 512;
-    static_assert(STAGES >= 2, "operand ring needs at least two stages");
+    static_assert(STAGES >= 5, "tile-major schedule keeps the 4 chunks of a component resident plus one prefetch");
+    static_assert(NT <= 256, "fused MMA N exceeds 256");
     static_assert(TMEM_COLS_USED <= 512, "accumulators exceed TMEM");
 };
 
 // control block at the end of dynamic smem
 struct TcCtrl {
     uint64_t full[8], empty[8];
-    uint64_t zfull[TILES], zempty[TILES], hfull[TILES], hempty[TILES];
+    uint64_t acc_full[TILES], acc_empty[TILES];
     uint64_t a_ready;
     uint32_t tmem_base;
     uint32_t pad;
@@ -171,8 +177,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     if (threadIdx.x == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&ctrl->full[i]), 1); mbar_init(smem_u32(&ctrl->empty[i]), 1); }
         for (int t = 0; t < TILES; ++t) {
-            mbar_init(smem_u32(&ctrl->zfull[t]), 1); mbar_init(smem_u32(&ctrl->hfull[t]), 1);
-            mbar_init(smem_u32(&ctrl->zempty[t]), TILE_M); mbar_init(smem_u32(&ctrl->hempty[t]), TILE_M);
+            mbar_init(smem_u32(&ctrl->acc_full[t]), 1);
+            mbar_init(smem_u32(&ctrl->acc_empty[t]), TILE_M);
         }
         mbar_init(smem_u32(&ctrl->a_ready), TILES * TILE_M);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -187,71 +193,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     tc_fence_after();
     const uint32_t tmem_base = ctrl->tmem_base;
 
+    // register budget: the CTA owns 384 x 168 registers; 128 x 56 + 256 x 224 = 64512 redistributes exactly that pool
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
-            // ===================== bulk-TMA producer
+            // ===================== bulk-TMA producer: 4 chunks per component (hi/K0, hi/K1, lo/K0, lo/K1)
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 for (int k = 0; k < a.K; ++k) {
-                    const __half* comp = a.image + (size_t)k * Cfg::COMP_HALFS;
+                    const unsigned char* comp = reinterpret_cast<const unsigned char*>(a.image + (size_t)k * Cfg::COMP_HALFS);
                     #pragma unroll
-                    for (int mtx = 0; mtx < 4; ++mtx) {
-                        const uint32_t bytes = (mtx < 2) ? Cfg::Z_BYTES : Cfg::H_BYTES;
-                        const __half* src = comp + (mtx < 2 ? mtx * NZ * KD : 2 * NZ * KD + (mtx - 2) * NH * KD);
+                    for (int q = 0; q < 4; ++q) {
                         mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1);
-                        mbar_expect_tx(smem_u32(&ctrl->full[stage]), bytes);
-                        bulk_g2s(smem_u32(sB + stage * Cfg::STAGE_BYTES), src, bytes, smem_u32(&ctrl->full[stage]));
+                        mbar_expect_tx(smem_u32(&ctrl->full[stage]), Cfg::STAGE_BYTES);
+                        bulk_g2s(smem_u32(sB + stage * Cfg::STAGE_BYTES), comp + (size_t)q * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES,
+                                 smem_u32(&ctrl->full[stage]));
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer
-            int stage = 0;
-            uint32_t phase = 0, a_phase = 0;
-            uint32_t zph[TILES] = {0, 0}, hph[TILES] = {0, 0};    // parity of the *empty* barriers we wait on
-            constexpr uint32_t A_LBO = (TILE_M / 8) * 128, A_SBO = 128;
-            constexpr uint32_t IDESC_Z = make_idesc(NZ), IDESC_H = make_idesc(NH);
+            constexpr int NT = Cfg::NT, KSPS = Cfg::KSPS;
+            constexpr uint32_t A_LBO = (TILE_M / 8) * 128, B_LBO = (NT / 8) * 128;      // SBO = 128 for both
+            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                      // SBO field | descriptor version 1
+            const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFF) | ((A_LBO >> 4) << 16);
+            const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFF) | ((B_LBO >> 4) << 16);
+            const uint32_t tri16 = a.tri ? 16u : 0u;
+            int stage0 = 0;                          // ring slot / parity of chunk 0 of the current component
+            uint32_t phase0 = 0, a_phase = 0;
+            uint32_t eph0 = 0, eph1 = 0;             // parity of acc_empty[t] waited on next
             for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 mbar_wait(smem_u32(&ctrl->a_ready), a_phase);
                 a_phase ^= 1;
                 tc_fence_after();
                 for (int k = 0; k < a.K; ++k) {
                     #pragma unroll
-                    for (int mtx = 0; mtx < 4; ++mtx) {
-                        const bool isz = mtx < 2, lo = mtx & 1;
-                        const int ncols = isz ? NZ : NH;
-                        const uint32_t b_lbo = (ncols / 8) * 128, b_sbo = 128;
-                        mbar_wait(smem_u32(&ctrl->full[stage]), phase);
+                    for (int t = 0; t < TILES; ++t) {
+                        // the first MMA overwrites the accumulator: the epilogue must have drained component k-1
+                        if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
+                        else { mbar_wait(smem_u32(&ctrl->acc_empty[1]), eph1 ^ 1); eph1 ^= 1; }
                         tc_fence_after();
-                        const uint32_t b_base = smem_u32(sB + stage * Cfg::STAGE_BYTES);
+                        const uint32_t d_tile = tmem_base + t * NT;
+                        const uint32_t a_lo_t = a_lo0 + t * (Cfg::A_TILE_BYTES >> 4);
+                        int stage = stage0;
+                        uint32_t phase = phase0;
                         #pragma unroll
-                        for (int t = 0; t < TILES; ++t) {
-                            const uint32_t d = tmem_base + t * (NZ + NH) + (isz ? 0 : NZ);
-                            if (!lo) {   // first pass overwrites the accumulator: the epilogue must have drained it
-                                if (isz) { mbar_wait(smem_u32(&ctrl->zempty[t]), zph[t] ^ 1); zph[t] ^= 1; }
-                                else { mbar_wait(smem_u32(&ctrl->hempty[t]), hph[t] ^ 1); hph[t] ^= 1; }
-                                tc_fence_after();
-                            }
-                            const uint32_t a_base = smem_u32(sA + t * Cfg::A_TILE_BYTES);
+                        for (int q = 0; q < 4; ++q) {
+                            if (t == 0) { mbar_wait(smem_u32(&ctrl->full[stage]), phase); tc_fence_after(); }
+                            const uint32_t b_lo_s = b_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
                             #pragma unroll
-                            for (int ks = 0; ks < KD / 16; ++ks) {
-                                const uint64_t ad = make_desc(a_base + ks * 2 * A_LBO, A_LBO, A_SBO);
-                                const uint64_t bd = make_desc(b_base + ks * 2 * b_lbo, b_lbo, b_sbo);
-                                umma_f16(d, ad, bd, isz ? IDESC_Z : IDESC_H, (lo || ks > 0) ? 1u : 0u);
+                            for (int s2 = 0; s2 < KSPS; ++s2) {
+                                const int ks = (q & 1) * KSPS + s2;                 // K-step within the full K range
+                                const uint32_t skip = tri16 * ks;                   // structurally zero leading columns
+                                const uint64_t ad = ((uint64_t)DESC_HI << 32) | (a_lo_t + ks * ((2 * A_LBO) >> 4));
+                                const uint64_t bd = ((uint64_t)DESC_HI << 32) | (b_lo_s + s2 * ((2 * B_LBO) >> 4) + (skip >> 3) * (128 >> 4));
+                                const uint32_t idesc = (1u << 4) | (((uint32_t)(NT - skip) >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+                                umma_f16(d_tile + skip, ad, bd, idesc, (q >= 2 || ks > 0) ? 1u : 0u);
                             }
-                            if (lo) tc_commit(smem_u32(isz ? &ctrl->zfull[t] : &ctrl->hfull[t]));
+                            if (t == TILES - 1) tc_commit(smem_u32(&ctrl->empty[stage]));
+                            if (++stage == S) { stage = 0; phase ^= 1; }
                         }
-                        tc_commit(smem_u32(&ctrl->empty[stage]));
-                        if (++stage == S) { stage = 0; phase ^= 1; }
+                        tc_commit(smem_u32(&ctrl->acc_full[t]));
+                        if (t == TILES - 1) { stage0 = stage; phase0 = phase; }
                     }
                 }
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================== epilogue warpgroups: one thread per pilot
         const int t = (warp - 4) >> 2;                 // tile within the pair
         const int wq = warp & 3;                       // TMEM lane quadrant of this warp
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         unsigned char* sAt = sA + t * Cfg::A_TILE_BYTES;
         const uint32_t tz = tmem_base + ((uint32_t)(wq * 32) << 16) + t * (NZ + NH);
         const uint32_t th = tz + NZ;
-        uint32_t zph = 0, hph = 0;
+        uint32_t fph = 0;
         const int No = a.No, N = a.N;
         double err = 0.0, pw = 0.0, cnt = 0.0;
 
@@ -298,8 +309,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
 
             for (int k = 0; k < a.K; ++k) {
                 // ---- whitened residual -> quadratic form
-                mbar_wait(smem_u32(&ctrl->zfull[t]), zph);
-                zph ^= 1;
+                mbar_wait(smem_u32(&ctrl->acc_full[t]), fph);
+                fph ^= 1;
                 tc_fence_after();
                 const float zs = __ldg(a.zscale + k);
                 double q = 0.0;
@@ -324,8 +335,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         q += (double)(s0 + s1);
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(smem_u32(&ctrl->zempty[t]));
                 if (!OFFS) q *= (double)zs * (double)zs;
                 const double l = __ldg(a.logc + k) - q;
                 // ---- lazily rescaled online softmax (reference maximum moves only on jumps > 8)
@@ -346,9 +355,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     ssum += p;
                 }
                 // ---- LMMSE row, weighted accumulation
-                mbar_wait(smem_u32(&ctrl->hfull[t]), hph);
-                hph ^= 1;
-                tc_fence_after();
                 if (__any_sync(0xffffffffu, p > 1e-30f)) {
                     const float ph = p * __ldg(a.hscale + k);
                     #pragma unroll
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(smem_u32(&ctrl->hempty[t]));
+                mbar_arrive(smem_u32(&ctrl->acc_empty[t]));
             }
 
             // ---- finalise: normalise, write the estimate row, NMSE accumulators
@@ -418,20 +424,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
 }
 
 // ------------------------------------------------------------------------------------------------ parameter packing
-// One block per (component, matrix): power-of-two scale to put the largest entry in [2^12, 2^13), then the FP16
-// hi/lo images of the real 2x2-block embedding in the canonical layout (core (nb, kb) at ((kb * ncols/8) + nb) * 128 B).
+// One block per (component, matrix).  Power-of-two scale putting the largest entry in [2^12, 2^13), then the FP16
+// hi/lo terms of the real 2x2-block embedding, written into the component's stacked image [E(Linv); E(W)]
+// ((2No + 2N) rows x 2No) in the canonical K-major core-matrix layout: core (nb, kb) at ((kb * NT/8) + nb) * 128 B,
+// hi image then lo image.  flags[1] is raised if some Linv_k is not lower triangular.
 __global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict__ Linv, const double2* __restrict__ W, int No, int N,
                                                       double data_scale, __half* __restrict__ image, float* __restrict__ zscale,
-                                                      float* __restrict__ hscale) {
+                                                      float* __restrict__ hscale, int* __restrict__ flags) {
     const int k = blockIdx.x >> 1, which = blockIdx.x & 1;
     const int R = which ? N : No, C = No;
     const double2* src = which ? W + (size_t)k * N * No : Linv + (size_t)k * No * No;
     __shared__ double smax[256];
     double mx = 0.0;
+    int upper = 0;
     for (int i = threadIdx.x; i < R * C; i += 256) {
         const double2 v = src[i];
         mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+        if (!which && (i % C) > (i / C) && (v.x != 0.0 || v.y != 0.0)) upper = 1;
     }
+    if (upper) atomicOr(flags + 1, 1);
     smax[threadIdx.x] = mx;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -444,11 +455,10 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict_
     const int e = (mx > 0.0 && isfinite(mx)) ? 13 - ex : 0;
     const double sc = ldexp(data_scale, e);
     if (threadIdx.x == 0) (which ? hscale : zscale)[k] = (float)ldexp(1.0, -e);
-    const int ncols = 2 * R, kd = 2 * No;
-    const size_t comp_halfs = (size_t)2 * (2 * No) * kd + (size_t)2 * (2 * N) * kd;
-    __half* hi = image + (size_t)k * comp_halfs + (which ? (size_t)2 * (2 * No) * kd : 0);
-    __half* lo = hi + (size_t)ncols * kd;
-    const int nbs = ncols / 8;
+    const int ncols = 2 * R, kd = 2 * No, nt = 2 * No + 2 * N;
+    __half* hi = image + (size_t)k * 2 * nt * kd;
+    __half* lo = hi + (size_t)nt * kd;
+    const int nbs = ncols / 8, nb0 = which ? (2 * No) / 8 : 0;
     for (int idx = threadIdx.x; idx < ncols * kd; idx += 256) {
         const int core = idx >> 6, within = idx & 63;
         const int nb = core % nbs, kb = core / nbs;
@@ -457,19 +467,19 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict_
         const int aa = n & 1, bb = kk & 1;
         const double x = (aa == bb ? v.x : (aa ? v.y : -v.y)) * sc;
         const __half h = __double2half(x);
-        hi[idx] = h;
-        lo[idx] = __double2half(x - (double)__half2float(h));
+        const size_t dst = ((size_t)kb * (nt / 8) + nb0 + nb) * 64 + within;
+        hi[dst] = h;
+        lo[dst] = __double2half(x - (double)__half2float(h));
     }
 }
 
-__global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const double2* __restrict__ hoff, const double* __restrict__ logc,
-                                     int K, int No, int N, float* __restrict__ zoff_f, float* __restrict__ hoff_f, int* __restrict__ nonzero) {
+__global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const double2* __restrict__ hoff, int K, int No, int N,
+                                     float* __restrict__ zoff_f, float* __restrict__ hoff_f, int* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int nz = 0;
     if (i < K * No) { const double2 v = zoff[i]; zoff_f[2 * i] = (float)v.x; zoff_f[2 * i + 1] = (float)v.y; nz |= (v.x != 0.0 || v.y != 0.0); }
     if (i < K * N) { const double2 v = hoff[i]; hoff_f[2 * i] = (float)v.x; hoff_f[2 * i + 1] = (float)v.y; nz |= (v.x != 0.0 || v.y != 0.0); }
-    if (nz) atomicOr(nonzero, 1);
-    (void)logc;
+    if (nz) atomicOr(flags, 1);
 }
 
 bool tc_supported(const qce_model* m, int mode) {
@@ -481,14 +491,14 @@ bool tc_supported(const qce_model* m, int mode) {
 
 void tc_free(qce_model* m) {
     TcParams& p = m->tc;
-    cudaFree(p.image); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc);
+    cudaFree(p.image); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.flags);
     p = TcParams();
 }
 
 qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     TcParams& p = m->tc;
     const size_t K = m->n_comp, No = m->n_obs, N = m->n_ant;
-    const size_t comp_halfs = 2 * (2 * No) * (2 * No) + 2 * (2 * N) * (2 * No);
+    const size_t comp_halfs = 2 * (2 * No + 2 * N) * (2 * No);
     if (!p.image) {
         p.image_bytes = K * comp_halfs * sizeof(__half);
         QCE_CUDA_TRY(cudaMalloc(&p.image, p.image_bytes));
@@ -496,21 +506,21 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
         QCE_CUDA_TRY(cudaMalloc(&p.hoff, K * 2 * N * sizeof(float)));
         QCE_CUDA_TRY(cudaMalloc(&p.zscale, K * sizeof(float)));
         QCE_CUDA_TRY(cudaMalloc(&p.hscale, K * sizeof(float)));
-        QCE_CUDA_TRY(cudaMalloc(&p.logc, sizeof(int)));          // reused as the "offsets non-zero" flag
+        QCE_CUDA_TRY(cudaMalloc(&p.flags, 2 * sizeof(int)));
     }
-    int* flag = reinterpret_cast<int*>(p.logc);
-    QCE_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    QCE_CUDA_TRY(cudaMemsetAsync(p.flags, 0, 2 * sizeof(int), s));
     tc_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
-                                                     (__half*)p.image, p.zscale, p.hscale);
+                                                     (__half*)p.image, p.zscale, p.hscale, p.flags);
     QCE_CHECK_LAUNCH("tc_pack_kernel");
     const size_t nmax = K * (No > N ? No : N);
-    tc_pack_small_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, s>>>((const double2*)m->zoff, (const double2*)m->hoff, m->logc, (int)K,
-                                                                        (int)No, (int)N, p.zoff, p.hoff, flag);
+    tc_pack_small_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, s>>>((const double2*)m->zoff, (const double2*)m->hoff, (int)K, (int)No,
+                                                                        (int)N, p.zoff, p.hoff, p.flags);
     QCE_CHECK_LAUNCH("tc_pack_small_kernel");
-    int h_flag = 0;
-    QCE_CUDA_TRY(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int h_flags[2] = {0, 0};
+    QCE_CUDA_TRY(cudaMemcpyAsync(h_flags, p.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
     QCE_CUDA_TRY(cudaStreamSynchronize(s));
-    p.passes = h_flag ? 3 : 2;     // here: 3 = "has offsets" marker, the MMA always runs two passes
+    p.has_offsets = h_flags[0] != 0;
+    p.triangular = h_flags[1] == 0;
     p.ready = true;
     return QCE_OK;
 }
@@ -550,7 +560,8 @@ qce_status launch_dense_tc(const qce_model* m, cudaStream_t s, const double* r, 
     a.image = (const __half*)p.image; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
     a.logc = m->logc; a.r = (const double2*)r; a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
     a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant; a.inv_data_scale = 1.0 / m->data_scale;
-    const bool offs = p.passes == 3;
+    a.tri = p.triangular ? 1 : 0;
+    const bool offs = p.has_offsets;
     const int cz = m->n_obs / 16, ch = m->n_ant / 16;
 #define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) return launch_offs<Z, H>(a, offs, s);
     QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
