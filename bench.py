@@ -229,25 +229,29 @@ def main():
 
     # --- roofline: the dense estimate kernel alone on resident quantised pilots
     pk = peaks()
+    import ctypes as C
+    lib = _lib.load()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     r = qce.get_observation_nbit(h, SNRS[4], n_bits=N_BITS, noise=noise)
-    out = None
+    out = torch.empty((B, N_ANT), dtype=torch.complex128, device=dev)
+    tc_used = args.precision in ('auto', 'tc') and lib.qce_format_pilots(models[4].handle, stream, C.c_void_p(r.data_ptr()), B) == 0
+    if tc_used:
+        def kernel_only():
+            _lib.check(lib.qce_estimate_formatted(models[4].handle, stream, B, C.c_void_p(out.data_ptr()), None, None))
+    else:
+        def kernel_only():
+            models[4].estimate(r, 'all', 'fp64')
     for _ in range(2):
-        out = models[4].estimate(r, 'all', args.precision)
+        kernel_only()
     torch.cuda.synchronize()
     reps = 5
     ev0.record()
     for _ in range(reps):
-        out = models[4].estimate(r, 'all', args.precision)
+        kernel_only()
     ev1.record()
     torch.cuda.synchronize()
     k_ms = ev0.elapsed_time(ev1) / reps
     achieved = FLOP_PER_EST * B / (k_ms * 1e-3) / 1e12
-    tc_used = False
-    try:
-        models[4].estimate(r[:256].contiguous(), 'all', 'tc')
-        tc_used = args.precision in ('auto', 'tc')
-    except Exception:
-        tc_used = False
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['burst'], 'unit': 'TFLOP/s', 'frac': achieved / pk['burst'],
                 'traffic': None, 'kernel': 'dense_tc_kernel' if tc_used else 'dense_fp64_kernel', 'kernel_ms': k_ms,
                 'peak_source': f"{pk['src']} bf16 burst (kernel timed alone)",
@@ -265,9 +269,7 @@ def main():
         r_np = r_host.numpy()
         gmm.estimate_from_y(r_np[:4096], SNRS[4], N_ANT, n_summands_or_proba='all', n_bits=N_BITS)
         from quantized_channel_estimation_b200.engine import parse_mode
-        import ctypes as C
         out_host = torch.empty((Be, N_ANT), dtype=torch.complex128).pin_memory()
-        lib = _lib.load()
         mode, n_top, rho = parse_mode('all')
         prec = _lib.PREC_TC if tc_used else _lib.PREC_FP64
 

@@ -31,6 +31,8 @@ _SIGS = {
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qce_pipeline': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double,
                                C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    'qce_format_pilots': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    'qce_estimate_formatted': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qce_estimate_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.c_void_p]),
 }

@@ -207,6 +207,28 @@ qce_status qce_pipeline(qce_model* m, const qce_quantizer* q, void* stream, cons
     if (m->n_obs != m->n_ant) { set_error("qce_pipeline: A = I requires n_obs == n_ant"); return QCE_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t N = m->n_ant;
+    if (!m->params_set) { set_error("qce_pipeline: model has no parameters"); return QCE_ERR_INVALID; }
+    {
+        qce_status stm = check_mode(mode, n_top, rho, m->n_comp);
+        if (stm) return stm;
+    }
+    if (precision == QCE_PREC_TC) {
+        if (!tc_supported(m, mode) || !m->tc.ready) {
+            set_error("tensor-core kernel does not support n_obs=%d n_ant=%d K=%d mode=%d", m->n_obs, m->n_ant, m->n_comp, mode);
+            return QCE_ERR_UNSUPPORTED;
+        }
+        // one formatter launch (observe + quantise + FP16 tiles) and one estimate launch per 2^22 pilots
+        const int64_t chunk = (int64_t)1 << 22;
+        const size_t hs = h_is_c64 ? 8 : 16;
+        for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+            const int64_t nb = (B - b0) < chunk ? (B - b0) : chunk;
+            const char* hp = (const char*)h + (size_t)b0 * N * hs;
+            qce_status st = launch_pipeline_tc(m, &q->t, s, hp, h_is_c64, (const double*)noise + (size_t)b0 * N * 2, noise_scale, nb, mode,
+                                               h_est ? (double*)h_est + (size_t)b0 * N * 2 : nullptr, acc);
+            if (st) return st;
+        }
+        return QCE_OK;
+    }
     // quantised pilots of one chunk live in a model-owned scratch buffer (grown on first use, then reused)
     const int64_t chunk_max = (int64_t)1 << 20;
     const int64_t cap = B < chunk_max ? B : chunk_max;
@@ -228,6 +250,18 @@ qce_status qce_pipeline(qce_model* m, const qce_quantizer* q, void* stream, cons
         if (st) return st;
     }
     return QCE_OK;
+}
+
+qce_status qce_format_pilots(qce_model* m, void* stream, const void* r, int64_t B) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && !r)) { set_error("qce_format_pilots: invalid argument"); return QCE_ERR_INVALID; }
+    if (!tc_supported(m, QCE_MODE_ALL) || !m->tc.ready) { set_error("qce_format_pilots: tensor-core path not available for this model"); return QCE_ERR_UNSUPPORTED; }
+    return tc_format(m, (cudaStream_t)stream, (const double*)r, B);
+}
+
+qce_status qce_estimate_formatted(qce_model* m, void* stream, int64_t B, void* h_est, const void* h_true, double* acc) {
+    if (!m || !m->params_set || B < 0) { set_error("qce_estimate_formatted: invalid argument"); return QCE_ERR_INVALID; }
+    if (!tc_supported(m, QCE_MODE_ALL) || !m->tc.ready) { set_error("qce_estimate_formatted: tensor-core path not available for this model"); return QCE_ERR_UNSUPPORTED; }
+    return tc_estimate_formatted(m, (cudaStream_t)stream, B, (double*)h_est, h_true, 0, acc);
 }
 
 qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,

@@ -56,6 +56,11 @@ struct TcParams {
     float* hoff = nullptr;      // [K][2*n_ant]
     float* zscale = nullptr;    // [K] power-of-two scale folded out of the Linv_k image
     float* hscale = nullptr;    // [K]
+    void* logc2 = nullptr;      // [K] float2: logc_k as an FP32 (hi, lo) pair
+    void* a_img = nullptr;      // scratch: pilot tiles as FP16 integers (grown on demand, outside the steady state)
+    void* bad = nullptr;        // scratch: per-row off-grid flags
+    int64_t tile_cap = 0;
+    int64_t formatted_rows = 0; // pilots currently held in a_img
     int* flags = nullptr;       // device scratch: [0] offsets non-zero, [1] some Linv_k not lower triangular
     bool has_offsets = false;
     bool triangular = false;
@@ -94,8 +99,13 @@ qce_status launch_dense_fp64_raw(const qce_model* m, cudaStream_t s, const doubl
 // qce_dense_tc.cu
 qce_status tc_pack_params(qce_model* m, cudaStream_t s);
 void tc_free(qce_model* m);
-qce_status launch_dense_tc(const qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top,
+qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top,
                            double rho, double* h_est, double* logp_out, const void* h_true, int h_true_c64,
                            double* acc);
+qce_status tc_format(qce_model* m, cudaStream_t s, const double* r, int64_t B);
+qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
+                                 double* acc);
+qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t s, const void* h, int h_is_c64,
+                              const double* noise, double noise_scale, int64_t B, int mode, double* h_est, double* acc);
 bool tc_supported(const qce_model* m, int mode);
 }  // namespace qce

@@ -26,6 +26,7 @@
 // The two tiles ping-pong: while the epilogue warpgroup of tile 0 drains Z|H(k), the tensor core produces
 // Z|H(k) of tile 1, and so on.
 #include <math.h>
+#include <stdlib.h>
 
 #include "qce_common.cuh"
 
@@ -42,15 +43,16 @@ struct TcArgs {
     const float* hscale;       // [K]
     const float* zoff;         // [K][2No] fp32 (only if OFFS)
     const float* hoff;         // [K][2N]
-    const double* logc;        // [K]
-    const double2* r;          // [B][No]
+    const float2* logc2;       // [K] logc_k as an unevaluated FP32 pair (hi, lo)
+    const __half* a_img;       // [n_tiles][128 x 2No] pilots as exact FP16 integers, canonical K-major core-matrix tiles
+    const unsigned char* bad;  // [n_tiles * 128] rows whose data was not on the quantiser grid (estimate -> NaN)
     double2* h_est;            // [B][N] or null
     const void* h_true;        // [B][N] c64/c128 or null
     int h_true_c64;
     double* acc;               // [3] or null
     int64_t B;
     int K, No, N;
-    double inv_data_scale;
+    long long* prof;           // optional per-role cycle counters of block 0 (QCE_TC_PROF=1), else null
     int tri;                   // Linv_k lower triangular (Cholesky whitening): skip the structurally zero columns
 };
 
@@ -153,10 +155,9 @@ struct TcCfg {
 struct TcCtrl {
     uint64_t full[8], empty[8];
     uint64_t acc_full[TILES], acc_empty[TILES];
-    uint64_t a_ready;
+    uint64_t a_full, a_free;
     uint32_t tmem_base;
     uint32_t pad;
-    unsigned char bad[TILES * TILE_M];
 };
 static_assert(sizeof(TcCtrl) <= 1024, "control block");
 
@@ -180,10 +181,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             mbar_init(smem_u32(&ctrl->acc_full[t]), 1);
             mbar_init(smem_u32(&ctrl->acc_empty[t]), TILE_M);
         }
-        mbar_init(smem_u32(&ctrl->a_ready), TILES * TILE_M);
+        mbar_init(smem_u32(&ctrl->a_full), 1);
+        mbar_init(smem_u32(&ctrl->a_free), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < TILES * TILE_M) ctrl->bad[threadIdx.x] = 0;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)), "r"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -213,6 +214,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     }
                 }
             }
+        } else if (warp == 3 && lane == 0) {
+            // ===================== pilot-tile producer: the two pre-formatted 128-pilot tiles of each pair, one bulk copy each
+            uint32_t fph = 0;
+            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                mbar_wait(smem_u32(&ctrl->a_free), fph ^ 1);      // all MMAs of the previous pair have read the tiles
+                fph ^= 1;
+                mbar_expect_tx(smem_u32(&ctrl->a_full), TILES * Cfg::A_TILE_BYTES);
+                #pragma unroll
+                for (int t = 0; t < TILES; ++t)
+                    bulk_g2s(smem_u32(sA + t * Cfg::A_TILE_BYTES),
+                             reinterpret_cast<const unsigned char*>(a.a_img) + (size_t)(pair * TILES + t) * Cfg::A_TILE_BYTES,
+                             Cfg::A_TILE_BYTES, smem_u32(&ctrl->a_full));
+            }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer
             constexpr int NT = Cfg::NT, KSPS = Cfg::KSPS;
@@ -224,24 +238,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             int stage0 = 0;                          // ring slot / parity of chunk 0 of the current component
             uint32_t phase0 = 0, a_phase = 0;
             uint32_t eph0 = 0, eph1 = 0;             // parity of acc_empty[t] waited on next
+            long long w_empty = 0, w_full = 0, w_a = 0, t_begin = clock64();
             for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                mbar_wait(smem_u32(&ctrl->a_ready), a_phase);
+                const long long ca = clock64();
+                mbar_wait(smem_u32(&ctrl->a_full), a_phase);
                 a_phase ^= 1;
                 tc_fence_after();
+                w_a += clock64() - ca;
                 for (int k = 0; k < a.K; ++k) {
                     #pragma unroll
                     for (int t = 0; t < TILES; ++t) {
                         // the first MMA overwrites the accumulator: the epilogue must have drained component k-1
+                        long long c0 = clock64();
                         if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
                         else { mbar_wait(smem_u32(&ctrl->acc_empty[1]), eph1 ^ 1); eph1 ^= 1; }
                         tc_fence_after();
+                        w_empty += clock64() - c0;
                         const uint32_t d_tile = tmem_base + t * NT;
                         const uint32_t a_lo_t = a_lo0 + t * (Cfg::A_TILE_BYTES >> 4);
                         int stage = stage0;
                         uint32_t phase = phase0;
                         #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            if (t == 0) { mbar_wait(smem_u32(&ctrl->full[stage]), phase); tc_fence_after(); }
+                            if (t == 0) { c0 = clock64(); mbar_wait(smem_u32(&ctrl->full[stage]), phase); tc_fence_after(); w_full += clock64() - c0; }
                             const uint32_t b_lo_s = b_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
                             #pragma unroll
                             for (int s2 = 0; s2 < KSPS; ++s2) {
@@ -259,66 +278,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         if (t == TILES - 1) { stage0 = stage; phase0 = phase; }
                     }
                 }
+                tc_commit(smem_u32(&ctrl->a_free));
             }
+            if (a.prof && blockIdx.x == 0) { a.prof[0] = clock64() - t_begin; a.prof[1] = w_empty; a.prof[2] = w_full; a.prof[3] = w_a; }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ===================== epilogue warpgroups: one thread per pilot
         const int t = (warp - 4) >> 2;                 // tile within the pair
         const int wq = warp & 3;                       // TMEM lane quadrant of this warp
-        const int wg_warp = (warp - 4) & 3;
         const int row = wq * 32 + lane;
-        unsigned char* sAt = sA + t * Cfg::A_TILE_BYTES;
         const uint32_t tz = tmem_base + ((uint32_t)(wq * 32) << 16) + t * (NZ + NH);
         const uint32_t th = tz + NZ;
         uint32_t fph = 0;
-        const int No = a.No, N = a.N;
+        const int N = a.N;
         double err = 0.0, pw = 0.0, cnt = 0.0;
+        long long w_acc = 0, c_z = 0, c_h = 0, c_pro = 0, c_ld = 0;
 
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const int64_t tile_base = (pair * TILES + t) * TILE_M;
-            // ---- prologue: pilots -> exact FP16 integers in the canonical K-major core-matrix layout
-            {
-                constexpr int CORES = (TILE_M / 8) * (KD / 8);
-                #pragma unroll 8
-                for (int c = wg_warp; c < CORES; c += 4) {
-                    const int mb = c % (TILE_M / 8), kb = c / (TILE_M / 8);
-                    const int rr = mb * 8 + (lane & 7), j = kb * 4 + (lane >> 3);
-                    double2 v = make_double2(0.0, 0.0);
-                    if (tile_base + rr < a.B) v = __ldg(a.r + (tile_base + rr) * No + j);
-                    const double mr = v.x * a.inv_data_scale, mi = v.y * a.inv_data_scale;
-                    const double qr = rint(mr), qi = rint(mi);
-                    // off-grid or out-of-range data cannot be represented exactly: poison the row (NaN output)
-                    if (!(fabs(mr - qr) <= 1e-6 * fmax(1.0, fabs(qr)) && fabs(mi - qi) <= 1e-6 * fmax(1.0, fabs(qi)) &&
-                          fabs(qr) <= 2048.0 && fabs(qi) <= 2048.0))
-                        ctrl->bad[t * TILE_M + rr] = 1;
-                    const __half2 hv = __floats2half2_rn((float)qr, (float)qi);
-                    *reinterpret_cast<__half2*>(sAt + (kb * (TILE_M / 8) + mb) * 128 + (lane & 7) * 16 + (lane >> 3) * 4) = hv;
-                }
-                fence_proxy_async();
-                mbar_arrive(smem_u32(&ctrl->a_ready));
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
-            }
-            const bool row_bad = ctrl->bad[t * TILE_M + row] != 0;
+            long long c0 = clock64();
+            bool row_bad = false;
+            if (tile_base + row < a.B) row_bad = __ldg(a.bad + tile_base + row) != 0;
+            c_pro += clock64() - c0;
 
             float acc[NH];
             #pragma unroll
             for (int j = 0; j < NH; ++j) acc[j] = 0.f;
-            double mref = 0.0;
+            float mref_hi = 0.f, mref_lo = 0.f;
             float ssum = 0.f;
 
+            float zs_n = __ldg(a.zscale), hs_n = __ldg(a.hscale);
+            float2 lc_n = __ldg(a.logc2);
             for (int k = 0; k < a.K; ++k) {
+                // per-component scalars were fetched one iteration ahead (their L2 latency would otherwise sit on the
+                // critical path between "accumulator ready" and "accumulator released")
+                const float zs = zs_n, hs = hs_n;
+                const float2 lc = lc_n;
+                if (k + 1 < a.K) { zs_n = __ldg(a.zscale + k + 1); hs_n = __ldg(a.hscale + k + 1); lc_n = __ldg(a.logc2 + k + 1); }
                 // ---- whitened residual -> quadratic form
+                c0 = clock64();
                 mbar_wait(smem_u32(&ctrl->acc_full[t]), fph);
                 fph ^= 1;
                 tc_fence_after();
-                const float zs = __ldg(a.zscale + k);
-                double q = 0.0;
+                long long c1 = clock64();
+                w_acc += c1 - c0;
+                float q_hi = 0.f, q_lo = 0.f;        // quadratic form as an unevaluated FP32 pair (TwoSum accumulation)
                 #pragma unroll
                 for (int ch = 0; ch < NCHZ; ++ch) {
                     float v[32];
+                    long long cl = clock64();
                     tmem_ld32(tz + ch * 32, v);
                     tmem_ld_wait();
+                    c_ld += clock64() - cl;
                     #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
                         float s0 = 0.f, s1 = 0.f;
@@ -332,31 +344,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                             s0 = fmaf(z0, z0, s0);
                             s1 = fmaf(z1, z1, s1);
                         }
-                        q += (double)(s0 + s1);
+                        {   // q += s0 + s1 without losing the rounding error (Knuth TwoSum, FP32 only)
+                            const float g = s0 + s1;
+                            const float tt = q_hi + g;
+                            const float bp = tt - q_hi;
+                            q_lo += (q_hi - (tt - bp)) + (g - bp);
+                            q_hi = tt;
+                        }
                     }
                 }
-                if (!OFFS) q *= (double)zs * (double)zs;
-                const double l = __ldg(a.logc + k) - q;
+                if (!OFFS) { const float zs2 = zs * zs; q_hi *= zs2; q_lo *= zs2; }   // power of two: exact
+                // l = logc - q as a pair: hi part plus the exact rounding error of the subtraction
+                const float l_hi = lc.x - q_hi;
+                const float bq = l_hi - lc.x;
+                const float l_lo = ((lc.x - (l_hi - bq)) + (-q_hi - bq)) + (lc.y - q_lo);
                 // ---- lazily rescaled online softmax (reference maximum moves only on jumps > 8)
                 float p;
                 if (k == 0) {
-                    mref = l; p = 1.f; ssum = 1.f;
+                    mref_hi = l_hi; mref_lo = l_lo; p = 1.f; ssum = 1.f;
                 } else {
-                    float df = (float)(l - mref);
+                    float df = (l_hi - mref_hi) + (l_lo - mref_lo);
                     if (df > 8.f) {
                         const float sc = __expf(-df);
                         ssum *= sc;
                         #pragma unroll
                         for (int j = 0; j < NH; ++j) acc[j] *= sc;
-                        mref = l;
+                        mref_hi = l_hi; mref_lo = l_lo;
                         df = 0.f;
                     }
                     p = __expf(df);
                     ssum += p;
                 }
+                long long c2 = clock64();
+                c_z += c2 - c1;
                 // ---- LMMSE row, weighted accumulation
                 if (__any_sync(0xffffffffu, p > 1e-30f)) {
-                    const float ph = p * __ldg(a.hscale + k);
+                    const float ph = p * hs;
                     #pragma unroll
                     for (int ch = 0; ch < NCHH; ++ch) {
                         float v[32];
@@ -371,6 +394,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 }
                 tc_fence_before();
                 mbar_arrive(smem_u32(&ctrl->acc_empty[t]));
+                c_h += clock64() - c2;
             }
 
             // ---- finalise: normalise, write the estimate row, NMSE accumulators
@@ -397,8 +421,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 }
                 cnt += 1.0;
             }
-            ctrl->bad[t * TILE_M + row] = 0;
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");   // flags cleared before the next prologue sets them
+        }
+        if (a.prof && blockIdx.x == 0 && lane == 0 && wq == 0) {
+            a.prof[4 + t * 4 + 0] = w_acc; a.prof[4 + t * 4 + 1] = c_z; a.prof[4 + t * 4 + 2] = c_h; a.prof[4 + t * 4 + 3] = c_pro; a.prof[12 + t] = c_ld;
         }
         if (a.acc) {
             #pragma unroll
@@ -473,13 +498,98 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict_
     }
 }
 
-__global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const double2* __restrict__ hoff, int K, int No, int N,
-                                     float* __restrict__ zoff_f, float* __restrict__ hoff_f, int* __restrict__ flags) {
+__global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const double2* __restrict__ hoff, const double* __restrict__ logc,
+                                     int K, int No, int N, float* __restrict__ zoff_f, float* __restrict__ hoff_f,
+                                     float2* __restrict__ logc2, int* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int nz = 0;
+    if (i < K) { const double l = logc[i]; const float hi = (float)l; logc2[i] = make_float2(hi, (float)(l - (double)hi)); }
     if (i < K * No) { const double2 v = zoff[i]; zoff_f[2 * i] = (float)v.x; zoff_f[2 * i + 1] = (float)v.y; nz |= (v.x != 0.0 || v.y != 0.0); }
     if (i < K * N) { const double2 v = hoff[i]; hoff_f[2 * i] = (float)v.x; hoff_f[2 * i + 1] = (float)v.y; nz |= (v.x != 0.0 || v.y != 0.0); }
     if (nz) atomicOr(flags, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ pilot tiles
+// HBM-bound formatter: pilots -> exact FP16 integers m = r / data_scale, written as 128-pilot tiles in the canonical
+// K-major core-matrix layout the MMA A-descriptor expects (core (mb, kb) at ((kb * 16) + mb) * 128 B), so that the
+// estimate kernel stages a tile with ONE contiguous bulk copy.  One CTA per (tile, 8-row block): its 8 warps sweep the
+// K cores, i.e. the CTA reads 8 full pilot rows (coalesced 64 B segments) and every warp writes one 128 B core matrix.
+// OBSERVE = true fuses get_observation_nbit + quant (modules/utils.py:241-251, :189-203) in front: y = h + s*n with
+// two roundings, then the same sign / digitize decisions as quantize_kernel (bit-exact), then the level's grid index.
+template <bool OBSERVE, bool H_C64>
+__global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__ src, const double2* __restrict__ noise, double noise_scale,
+                                                        QuantTables qt, int64_t B, int No, double inv_data_scale,
+                                                        __half* __restrict__ img, unsigned char* __restrict__ bad) {
+    extern __shared__ double s_tab[];              // thr[n_thr] then labels[n_thr + 1] (OBSERVE, b > 1)
+    __shared__ int s_bad[8];
+    const int KD = 2 * No, kbs = KD / 8;
+    const int64_t tile = blockIdx.x / (TILE_M / 8);
+    const int mb = blockIdx.x % (TILE_M / 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (OBSERVE && qt.n_bits > 1) {
+        for (int i = threadIdx.x; i < 2 * qt.n_thr + 1; i += blockDim.x) s_tab[i] = (i < qt.n_thr) ? qt.thr[i] : qt.labels[i - qt.n_thr];
+    }
+    if (threadIdx.x < 8) s_bad[threadIdx.x] = 0;
+    __syncthreads();
+    const int rr = mb * 8 + (lane & 7);
+    const int64_t g = tile * TILE_M + rr;
+    const float inv = (float)inv_data_scale;
+    __half* tile_img = img + (size_t)tile * TILE_M * KD;
+    int my_bad = 0;
+    for (int kb = warp; kb < kbs; kb += 8) {
+        const int j = kb * 4 + (lane >> 3);
+        double2 v = make_double2(0.0, 0.0);
+        if (g < B) {
+            if (OBSERVE) {
+                double2 h;
+                if (H_C64) { const float2 hf = reinterpret_cast<const float2*>(src)[g * No + j]; h = make_double2((double)hf.x, (double)hf.y); }
+                else h = reinterpret_cast<const double2*>(src)[g * No + j];
+                const double2 w = noise[g * No + j];
+                const double yx = __dadd_rn(h.x, __dmul_rn(noise_scale, w.x)), yy = __dadd_rn(h.y, __dmul_rn(noise_scale, w.y));
+                if (qt.n_bits == 1) {        // value on the grid is sign(y) (x 1/sqrt(2) = data_scale)
+                    v.x = (yx > 0.0) ? 1.0 : ((yx < 0.0) ? -1.0 : ((yx == 0.0) ? 0.0 : yx));
+                    v.y = (yy > 0.0) ? 1.0 : ((yy < 0.0) ? -1.0 : ((yy == 0.0) ? 0.0 : yy));
+                } else {
+                    const double* thr = s_tab;
+                    const double* lab = s_tab + qt.n_thr;
+                    int ir = qt.n_thr, ii = qt.n_thr;
+                    if (yx == yx) { int lo = 0, hi = qt.n_thr; while (lo < hi) { int mid = (lo + hi) >> 1; if (thr[mid] <= yx) lo = mid + 1; else hi = mid; } ir = lo; }
+                    if (yy == yy) { int lo = 0, hi = qt.n_thr; while (lo < hi) { int mid = (lo + hi) >> 1; if (thr[mid] <= yy) lo = mid + 1; else hi = mid; } ii = lo; }
+                    v.x = lab[ir] * inv_data_scale;
+                    v.y = lab[ii] * inv_data_scale;
+                }
+            } else {
+                v = __ldg(reinterpret_cast<const double2*>(src) + g * No + j);
+                v.x *= inv_data_scale;
+                v.y *= inv_data_scale;
+            }
+        }
+        const float mr = (float)v.x, mi = (float)v.y;
+        const float qr = rintf(mr), qi = rintf(mi);
+        // off-grid / out-of-range / NaN data cannot be represented exactly: flag the row (its estimate becomes NaN)
+        if (!(fabsf(mr - qr) <= 1e-4f * fmaxf(1.f, fabsf(qr)) && fabsf(mi - qi) <= 1e-4f * fmaxf(1.f, fabsf(qi)) &&
+              fabsf(qr) <= 2048.f && fabsf(qi) <= 2048.f))
+            my_bad = 1;
+        *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img) + (size_t)(kb * (TILE_M / 8) + mb) * 128 + (lane & 7) * 16 +
+                                    (lane >> 3) * 4) = __floats2half2_rn(qr, qi);
+        (void)inv;
+    }
+    if (my_bad) s_bad[lane & 7] = 1;
+    __syncthreads();
+    if (threadIdx.x < 8) bad[tile * TILE_M + mb * 8 + threadIdx.x] = (unsigned char)s_bad[threadIdx.x];
+}
+
+static qce_status tc_ensure_tiles(qce_model* m, int64_t rows) {
+    TcParams& p = m->tc;
+    const int64_t tiles = (rows + TILE_M - 1) / TILE_M + 1;        // +1: the last pair may touch one tile past the end
+    if (tiles <= p.tile_cap) return QCE_OK;
+    if (p.a_img) { QCE_CUDA_TRY(cudaFree(p.a_img)); QCE_CUDA_TRY(cudaFree(p.bad)); p.a_img = nullptr; p.bad = nullptr; p.tile_cap = 0; }
+    QCE_CUDA_TRY(cudaMalloc(&p.a_img, (size_t)tiles * TILE_M * 2 * m->n_obs * sizeof(__half)));
+    QCE_CUDA_TRY(cudaMalloc(&p.bad, (size_t)tiles * TILE_M));
+    QCE_CUDA_TRY(cudaMemset(p.a_img, 0, (size_t)tiles * TILE_M * 2 * m->n_obs * sizeof(__half)));
+    QCE_CUDA_TRY(cudaMemset(p.bad, 0, (size_t)tiles * TILE_M));
+    p.tile_cap = tiles;
+    return QCE_OK;
 }
 
 bool tc_supported(const qce_model* m, int mode) {
@@ -491,7 +601,7 @@ bool tc_supported(const qce_model* m, int mode) {
 
 void tc_free(qce_model* m) {
     TcParams& p = m->tc;
-    cudaFree(p.image); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.flags);
+    cudaFree(p.image); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc2); cudaFree(p.flags); cudaFree(p.a_img); cudaFree(p.bad);
     p = TcParams();
 }
 
@@ -506,6 +616,7 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
         QCE_CUDA_TRY(cudaMalloc(&p.hoff, K * 2 * N * sizeof(float)));
         QCE_CUDA_TRY(cudaMalloc(&p.zscale, K * sizeof(float)));
         QCE_CUDA_TRY(cudaMalloc(&p.hscale, K * sizeof(float)));
+        QCE_CUDA_TRY(cudaMalloc(&p.logc2, K * sizeof(float2)));
         QCE_CUDA_TRY(cudaMalloc(&p.flags, 2 * sizeof(int)));
     }
     QCE_CUDA_TRY(cudaMemsetAsync(p.flags, 0, 2 * sizeof(int), s));
@@ -513,8 +624,8 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
                                                      (__half*)p.image, p.zscale, p.hscale, p.flags);
     QCE_CHECK_LAUNCH("tc_pack_kernel");
     const size_t nmax = K * (No > N ? No : N);
-    tc_pack_small_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, s>>>((const double2*)m->zoff, (const double2*)m->hoff, (int)K, (int)No,
-                                                                        (int)N, p.zoff, p.hoff, p.flags);
+    tc_pack_small_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, s>>>((const double2*)m->zoff, (const double2*)m->hoff, m->logc, (int)K, (int)No,
+                                                                        (int)N, p.zoff, p.hoff, (float2*)p.logc2, p.flags);
     QCE_CHECK_LAUNCH("tc_pack_small_kernel");
     int h_flags[2] = {0, 0};
     QCE_CUDA_TRY(cudaMemcpyAsync(h_flags, p.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
@@ -549,25 +660,93 @@ static qce_status launch_offs(const TcArgs& a, bool offs, cudaStream_t s) {
     return offs ? launch_cfg<NCHZ, NCHH, true>(a, s) : launch_cfg<NCHZ, NCHH, false>(a, s);
 }
 
-qce_status launch_dense_tc(const qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
+static qce_status tc_run(const qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc) {
+    const TcParams& p = m->tc;
+    TcArgs a;
+    a.image = (const __half*)p.image; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
+    a.logc2 = (const float2*)p.logc2; a.a_img = (const __half*)p.a_img; a.bad = (const unsigned char*)p.bad;
+    a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
+    a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant;
+    a.tri = p.triangular ? 1 : 0;
+    static long long* prof = nullptr;
+    static const bool want_prof = getenv("QCE_TC_PROF") != nullptr;
+    if (want_prof && !prof) cudaMallocManaged(&prof, 16 * sizeof(long long));
+    a.prof = want_prof ? prof : nullptr;
+    const bool offs = p.has_offsets;
+    const int cz = m->n_obs / 16, ch = m->n_ant / 16;
+    qce_status st = QCE_ERR_UNSUPPORTED;
+    bool hit = false;
+#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, s); hit = true; }
+    QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
+#undef QCE_TC_CASE
+    if (!hit) {
+        set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant);
+        return QCE_ERR_UNSUPPORTED;
+    }
+    if (want_prof && st == QCE_OK) {
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "[qce tc prof] B=%lld K=%d | mma: total %lld wait_acc_empty %lld wait_full %lld wait_a %lld | epi t0: wait %lld z %lld h %lld pro %lld | epi t1: wait %lld z %lld h %lld pro %lld | zld t0 %lld t1 %lld\n",
+                (long long)B, a.K, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10], prof[11], prof[12], prof[13]);
+    }
+    return st;
+}
+
+static bool tc_instantiated(const qce_model* m) {
+    const int cz = m->n_obs / 16, ch = m->n_ant / 16;
+    return (cz == ch && cz >= 1 && cz <= 4) || (cz == 4 && ch == 2) || (cz == 2 && ch == 1);
+}
+
+qce_status tc_format(qce_model* m, cudaStream_t s, const double* r, int64_t B) {
+    if (!tc_instantiated(m)) { set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant); return QCE_ERR_UNSUPPORTED; }
+    qce_status st = tc_ensure_tiles(m, B);
+    if (st) return st;
+    const int64_t tiles = (B + TILE_M - 1) / TILE_M;
+    QuantTables none{};
+    tc_format_kernel<false, false><<<(unsigned)(tiles * (TILE_M / 8)), 256, 0, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->data_scale,
+                                                                                  (__half*)m->tc.a_img, (unsigned char*)m->tc.bad);
+    QCE_CHECK_LAUNCH("tc_format_kernel");
+    m->tc.formatted_rows = B;
+    return QCE_OK;
+}
+
+qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc) {
+    if (B > m->tc.formatted_rows) { set_error("qce_estimate_formatted: only %lld pilots are formatted", (long long)m->tc.formatted_rows); return QCE_ERR_INVALID; }
+    if (B == 0) return QCE_OK;
+    return tc_run(m, s, B, h_est, h_true, h_true_c64, acc);
+}
+
+// pilots given as complex128 values (estimate_from_y): format, then estimate
+qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
                            double* h_est, double* logp_out, const void* h_true, int h_true_c64, double* acc) {
     (void)n_top; (void)rho;
     if (B == 0) return QCE_OK;
     if (logp_out) { set_error("tensor-core kernel does not export log-probabilities"); return QCE_ERR_UNSUPPORTED; }
     if (mode != QCE_MODE_ALL) { set_error("tensor-core kernel: mode %d not supported", mode); return QCE_ERR_UNSUPPORTED; }
-    const TcParams& p = m->tc;
-    TcArgs a;
-    a.image = (const __half*)p.image; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
-    a.logc = m->logc; a.r = (const double2*)r; a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
-    a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant; a.inv_data_scale = 1.0 / m->data_scale;
-    a.tri = p.triangular ? 1 : 0;
-    const bool offs = p.has_offsets;
-    const int cz = m->n_obs / 16, ch = m->n_ant / 16;
-#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) return launch_offs<Z, H>(a, offs, s);
-    QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
-#undef QCE_TC_CASE
-    set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant);
-    return QCE_ERR_UNSUPPORTED;
+    qce_status st = tc_format(m, s, r, B);
+    if (st) return st;
+    return tc_run(m, s, B, h_est, h_true, h_true_c64, acc);
+}
+
+// fused Monte-Carlo step: observe (A = I) -> quantise -> estimate -> NMSE accumulators; the quantised pilots never exist in HBM
+// other than as the FP16 tile image
+qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t s, const void* h, int h_is_c64, const double* noise,
+                              double noise_scale, int64_t B, int mode, double* h_est, double* acc) {
+    if (B == 0) return QCE_OK;
+    if (mode != QCE_MODE_ALL || !tc_instantiated(m)) { set_error("tensor-core pipeline: shape/mode not supported"); return QCE_ERR_UNSUPPORTED; }
+    qce_status st = tc_ensure_tiles(m, B);
+    if (st) return st;
+    const int64_t tiles = (B + TILE_M - 1) / TILE_M;
+    const size_t smem = (qt->n_bits > 1) ? (size_t)(2 * qt->n_thr + 1) * sizeof(double) : 0;
+    const unsigned grid = (unsigned)(tiles * (TILE_M / 8));
+    if (h_is_c64)
+        tc_format_kernel<true, true><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, 1.0 / m->data_scale,
+                                                            (__half*)m->tc.a_img, (unsigned char*)m->tc.bad);
+    else
+        tc_format_kernel<true, false><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, 1.0 / m->data_scale,
+                                                             (__half*)m->tc.a_img, (unsigned char*)m->tc.bad);
+    QCE_CHECK_LAUNCH("tc_format_kernel(observe)");
+    m->tc.formatted_rows = B;
+    return tc_run(m, s, B, h_est, h, h_is_c64, acc);
 }
 
 }  // namespace qce
