@@ -32,6 +32,7 @@ BATCH = 1 << 20
 METRIC = 'Bussgang-GMM estimates/sec (M=64,K=64,1-bit)'
 UNIT = 'estimates/s'
 FLOP_PER_EST = 16 * N_COMP * N_ANT * N_ANT
+WORKLOAD = f"Bussgang-GMM 'full' 1-bit N={N_ANT} K={N_COMP} mode=all, SNR sweep -10..30 dB (BASELINE configs[1])"
 
 
 def peaks():
@@ -106,6 +107,15 @@ def cpu_port_rate(means, covs, w, n_obs, snr=10, seed=123):
     return n_obs / dt, dt, float(orc.mse(est, h))
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -118,6 +128,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    use_all_host_threads()
     means, covs, w = make_params()
     sample = 4096
     for _ in range(args.warmup):
@@ -131,7 +142,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'c128', 'data': 'synthetic',
-            'config': {'workload': f'Bussgang-GMM full 1-bit N={N_ANT} K={N_COMP}, SNR sweep -10..30 dB', 'batch_per_step': sample},
+            'config': {'workload': WORKLOAD, 'batch_per_step': sample, 'note': 'bounded sample of the same workload on the host cores'},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': f'{sample} observations per step (numpy oracle, batched over samples), {os.cpu_count()} host cpus'},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -296,6 +307,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
         n_cpu = 8192
         cpu_port_rate(means, covs, w, 256)
         rate, dt, _ = cpu_port_rate(means, covs, w, n_cpu)
@@ -307,7 +319,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f16x2-split/f32-acc' if tc_used else 'f64', 'data': 'synthetic',
-                'config': {'workload': f"Bussgang-GMM 'full' 1-bit N={N_ANT} K={N_COMP} mode=all, SNR sweep -10..30 dB (BASELINE configs[1])",
+                'config': {'workload': WORKLOAD,
                            'batch_per_gpu_per_step': B, 'global_batch': world * B, 'parallelism': f'dp{world}',
                            'l2': 'inputs larger than L2 (h 512 MiB c64 + noise 1 GiB c128 per step), no flush needed',
                            'params': 'random-PSD GMM seed 0 (SURVEY 8d P-rand)'},

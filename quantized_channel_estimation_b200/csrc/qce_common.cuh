@@ -52,6 +52,8 @@ struct qce_quantizer {
 struct TcParams {
     void* image = nullptr;      // packed FP16 hi/lo operand images, device
     size_t image_bytes = 0;
+    void* image2 = nullptr;     // per-CTA half images of the SM-pair (cta_group::2) kernel
+    size_t image2_bytes = 0;
     float* zoff = nullptr;      // [K][2*n_obs] whitened offsets (fp32)
     float* hoff = nullptr;      // [K][2*n_ant]
     float* zscale = nullptr;    // [K] power-of-two scale folded out of the Linv_k image

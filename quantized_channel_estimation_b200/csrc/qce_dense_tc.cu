@@ -23,6 +23,11 @@
 //   warps 4-7   epilogue warpgroup of tile 0, warps 8-11 of tile 1: one thread per pilot; tcgen05.ld the
 //               whitened row -> |z|^2 -> l_k -> lazily rescaled online softmax -> FMA of the LMMSE row into
 //               128 register accumulators.  Per-component estimates never leave the SM.
+// CG = 2 (default): two CTAs of a cluster form an SM pair; the leader issues tcgen05.mma.cta_group::2 with M = 256 (each
+// CTA's 128-pilot tile in its own TMEM) and each CTA stages only HALF of every operand chunk (its N'/2 rows), which
+// halves the shared-memory operand traffic per SM -- the measured limit of cta_group::1 SS-mode MMAs (172 clk for
+// M128 x N256 x K16 instead of 128) -- and the L2->smem traffic.  Cross-CTA signalling: multicast tcgen05.commit for
+// "stage free" / "accumulator ready", remote mbarrier arrives (mapa) for "peer chunk landed" / "accumulator drained".
 // The two tiles ping-pong: while the epilogue warpgroup of tile 0 drains Z|H(k), the tensor core produces
 // Z|H(k) of tile 1, and so on.
 #include <math.h>
@@ -32,13 +37,22 @@
 
 namespace qce {
 
+// per-role cycle counters (QCE_TC_PROF=1 prints them) cost issue slots in the single-thread MMA loop: compile them in only
+// with -DQCE_TC_PROFILE
+#ifdef QCE_TC_PROFILE
+#define QCE_CLK() clock64()
+#else
+#define QCE_CLK() 0LL
+#endif
+
 constexpr int TILE_M = 128;
 constexpr int TILES = 2;
 constexpr int NUM_THREADS = 384;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct TcArgs {
-    const __half* image;       // [K][ Lhi | Llo | Whi | Wlo ] pre-formatted canonical K-major core-matrix images
+    const __half* image;       // CG=1: [K][hi | lo] stacked [E(Linv); E(W)] images, canonical K-major core-matrix order
+    const unsigned char* image2;  // CG=2: [K][rank][hi K0 | hi K1 | lo K0 | lo K1] per-CTA half images (see tc2_pack_kernel)
     const float* zscale;       // [K] 2^-e of the Linv image
     const float* hscale;       // [K]
     const float* zoff;         // [K][2No] fp32 (only if OFFS)
@@ -86,6 +100,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+    // default semantics (release at CTA scope, like cutlass::arch::ClusterBarrier::arrive): a cluster-scope release costs a
+    // full fence + L1 invalidate per arrival; the data handed over here lives in TMEM / async-proxy smem, not in generic memory
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -96,12 +126,36 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// one lane of a converged warp (the warp runs the issuing loop with uniform control flow so that descriptors stay in
+// uniform registers; only the tcgen05 instructions themselves are predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {      // cta_group::2: arrive on the barrier at this offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// shared-memory matrix descriptors are passed as (low word, common high word): the low word is a 32-bit base plus an
+// immediate in the issuing loop, the high word (SBO | version) is a constant
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accum) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum) : "memory");
 }
 // K-major, no-swizzle canonical layout: 8x16B core matrices; LBO = byte step between the two K-adjacent core
 // matrices of one MMA, SBO = byte step between M/N-adjacent core matrices (cute::UMMA::SmemDescriptor bit layout)
@@ -131,22 +185,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int NZ, int NH>
+// CG=2 per-CTA operand images.  K-step ks (16 reduction elements) needs the stacked rows [skip, NT), skip = 16 ks for a
+// triangular Linv (else 0): N' = NT - skip rows, of which rank 0 holds the first N'/2 and rank 1 the rest.  A chunk is the
+// concatenation over the K-steps of one K-half of the sub-blocks [2 k-cores][N'/16 n-cores][128 B].
+__host__ __device__ constexpr int tc2_nprime(int nt, int tri16, int ks) { return nt - tri16 * ks; }
+__host__ __device__ constexpr int tc2_sub_off(int nt, int tri16, int ksps, int half, int s2) {     // byte offset of sub-block s2 in its chunk
+    return 16 * (s2 * nt - tri16 * (s2 * half * ksps + s2 * (s2 - 1) / 2));
+}
+__host__ __device__ constexpr int tc2_chunk_bytes(int nt, int tri16, int ksps, int half) { return tc2_sub_off(nt, tri16, ksps, half, ksps); }
+__host__ __device__ constexpr int tc2_rank_comp_bytes(int nt, int tri16, int ksps) {
+    return 2 * (tc2_chunk_bytes(nt, tri16, ksps, 0) + tc2_chunk_bytes(nt, tri16, ksps, 1));
+}
+
+template <int NZ, int NH, int CG>
 struct TcCfg {
     static constexpr int KD = NZ;                                   // GEMM reduction length 2*n_obs
     static constexpr int NT = NZ + NH;                              // fused MMA N: Z columns then H columns
     static constexpr int A_TILE_BYTES = TILE_M * KD * 2;
     static constexpr int KSPS = KD / 32;                            // K-steps (of 16) per staged chunk = half the K range
-    static constexpr int STAGE_BYTES = NT * (KD / 2) * 2;           // one K-half of the stacked hi (or lo) image
+    // CG=1: a chunk is one K-half of the stacked hi (or lo) image, 4 chunks per component.
+    // CG=2: a chunk is this CTA's share of the whole hi (or lo) image (triangular layout), 2 chunks per component.
+    static constexpr int NCHUNK = (CG == 2) ? 2 : 4;
+    static constexpr int CB0 = tc2_chunk_bytes(NT, 16, KSPS, 0), CB1 = tc2_chunk_bytes(NT, 16, KSPS, 1);
+    static constexpr int STAGE_BYTES = (CG == 2) ? (CB0 + CB1) : NT * (KD / 2) * 2;
     static constexpr int CTRL_BYTES = 1024;
     static constexpr int STAGES_FIT = (SMEM_LIMIT - TILES * A_TILE_BYTES - CTRL_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int SMEM_BYTES = TILES * A_TILE_BYTES + STAGES * STAGE_BYTES + CTRL_BYTES;
-    static constexpr int COMP_HALFS = 2 * NT * KD;                  // halfs per component image: hi then lo
+    static constexpr int COMP_HALFS = 2 * NT * KD;                  // CG=1: halfs per component image: hi then lo
     static constexpr int TMEM_COLS_USED = TILES * NT;
     static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
                                      : TMEM_COLS_USED <= 256 ? 256 : 512;
-    static_assert(STAGES >= 5, "tile-major schedule keeps the 4 chunks of a component resident plus one prefetch");
+    static_assert(STAGES >= NCHUNK + 1, "tile-major schedule keeps the chunks of a component resident plus one prefetch");
+    static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
     static_assert(NT <= 256, "fused MMA N exceeds 256");
     static_assert(TMEM_COLS_USED <= 512, "accumulators exceed TMEM");
 };
@@ -161,10 +232,10 @@ struct TcCtrl {
 };
 static_assert(sizeof(TcCtrl) <= 1024, "control block");
 
-template <int NCHZ, int NCHH, bool OFFS>
+template <int NCHZ, int NCHH, bool OFFS, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
-    using Cfg = TcCfg<NZ, NH>;
+    using Cfg = TcCfg<NZ, NH, CG>;
     constexpr int KD = Cfg::KD;
     constexpr int S = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -173,24 +244,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     TcCtrl* ctrl = reinterpret_cast<TcCtrl*>(sB + S * Cfg::STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_pairs = (a.B + TILES * TILE_M - 1) / (TILES * TILE_M);
+    // work unit: CG * TILES tiles (256 pilots per CTA); the cluster (CG CTAs) walks the units round-robin
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int64_t n_units = (a.B + CG * TILES * TILE_M - 1) / (CG * TILES * TILE_M);
+    const int64_t unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
+    // the SM-pair variant is only launched for triangular Linv (the common, Cholesky case): its offsets are compile-time
+    const int tri16 = (CG == 2) ? 16 : (a.tri ? 16 : 0);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&ctrl->full[i]), 1); mbar_init(smem_u32(&ctrl->empty[i]), 1); }
+        // CG=2: the leader's "full" barriers also collect one remote arrival from the peer CTA ("my half has landed too")
+        const uint32_t full_count = (CG == 2 && rank == 0) ? 2 : 1;
+        for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&ctrl->full[i]), full_count); mbar_init(smem_u32(&ctrl->empty[i]), 1); }
         for (int t = 0; t < TILES; ++t) {
             mbar_init(smem_u32(&ctrl->acc_full[t]), 1);
-            mbar_init(smem_u32(&ctrl->acc_empty[t]), TILE_M);
+            mbar_init(smem_u32(&ctrl->acc_empty[t]), 4 * CG);       // one arrival per epilogue warp (of both CTAs)
         }
-        mbar_init(smem_u32(&ctrl->a_full), 1);
+        mbar_init(smem_u32(&ctrl->a_full), full_count);
         mbar_init(smem_u32(&ctrl->a_free), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)), "r"(Cfg::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)), "r"(Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)), "r"(Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // barriers initialised in BOTH CTAs before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = ctrl->tmem_base;
 
@@ -198,14 +281,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
-            // ===================== bulk-TMA producer: 4 chunks per component (hi/K0, hi/K1, lo/K0, lo/K1)
+            // ===================== bulk-TMA producer: NCHUNK chunks per component through the ring
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            constexpr size_t COMP_BYTES = (CG == 2) ? (size_t)2 * Cfg::STAGE_BYTES : (size_t)Cfg::COMP_HALFS * 2;
+            const unsigned char* img = (CG == 2) ? a.image2 + (size_t)rank * COMP_BYTES : reinterpret_cast<const unsigned char*>(a.image);
+            constexpr size_t COMP_STRIDE = COMP_BYTES * CG;      // CG=2: [k][rank]
+            for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
                 for (int k = 0; k < a.K; ++k) {
-                    const unsigned char* comp = reinterpret_cast<const unsigned char*>(a.image + (size_t)k * Cfg::COMP_HALFS);
+                    const unsigned char* comp = img + (size_t)k * COMP_STRIDE;
                     #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < Cfg::NCHUNK; ++q) {
                         mbar_wait(smem_u32(&ctrl->empty[stage]), phase ^ 1);
                         mbar_expect_tx(smem_u32(&ctrl->full[stage]), Cfg::STAGE_BYTES);
                         bulk_g2s(smem_u32(sB + stage * Cfg::STAGE_BYTES), comp + (size_t)q * Cfg::STAGE_BYTES, Cfg::STAGE_BYTES,
@@ -215,72 +301,114 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 }
             }
         } else if (warp == 3 && lane == 0) {
-            // ===================== pilot-tile producer: the two pre-formatted 128-pilot tiles of each pair, one bulk copy each
+            // ===================== pilot-tile producer: the two pre-formatted 128-pilot tiles of each unit, one bulk copy each
             uint32_t fph = 0;
-            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                mbar_wait(smem_u32(&ctrl->a_free), fph ^ 1);      // all MMAs of the previous pair have read the tiles
+            for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+                mbar_wait(smem_u32(&ctrl->a_free), fph ^ 1);      // all MMAs of the previous unit have read the tiles
                 fph ^= 1;
                 mbar_expect_tx(smem_u32(&ctrl->a_full), TILES * Cfg::A_TILE_BYTES);
                 #pragma unroll
                 for (int t = 0; t < TILES; ++t)
                     bulk_g2s(smem_u32(sA + t * Cfg::A_TILE_BYTES),
-                             reinterpret_cast<const unsigned char*>(a.a_img) + (size_t)(pair * TILES + t) * Cfg::A_TILE_BYTES,
+                             reinterpret_cast<const unsigned char*>(a.a_img) + (size_t)((unit * CG + rank) * TILES + t) * Cfg::A_TILE_BYTES,
                              Cfg::A_TILE_BYTES, smem_u32(&ctrl->a_full));
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===================== MMA issuer
+        } else if (warp == 1 && rank == 0) {
+            // ===================== MMA issuer (leader CTA).  The whole warp runs the loop (uniform control flow keeps the
+            // descriptors in uniform registers); one elected lane issues.  Every instruction between two MMAs is exposed
+            // latency, so descriptors are 32-bit base + compile-time immediate and barrier waits are kept to
+            // NCHUNK + TILES per component.
+            const bool elected = elect_one();
             constexpr int NT = Cfg::NT, KSPS = Cfg::KSPS;
-            constexpr uint32_t A_LBO = (TILE_M / 8) * 128, B_LBO = (NT / 8) * 128;      // SBO = 128 for both
+            constexpr uint32_t A_LBO = (TILE_M / 8) * 128;                              // SBO = 128 for both operands
             constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                      // SBO field | descriptor version 1
+            constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)((CG * TILE_M) >> 4) << 24);
             const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFF) | ((A_LBO >> 4) << 16);
-            const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFF) | ((B_LBO >> 4) << 16);
-            const uint32_t tri16 = a.tri ? 16u : 0u;
+            const uint32_t b_addr0 = (smem_u32(sB) >> 4) & 0x3FFF;
             int stage0 = 0;                          // ring slot / parity of chunk 0 of the current component
             uint32_t phase0 = 0, a_phase = 0;
             uint32_t eph0 = 0, eph1 = 0;             // parity of acc_empty[t] waited on next
-            long long w_empty = 0, w_full = 0, w_a = 0, t_begin = clock64();
-            for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                const long long ca = clock64();
+            long long w_empty = 0, w_full = 0, w_a = 0, t_begin = QCE_CLK();
+            for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+                const long long ca = QCE_CLK();
                 mbar_wait(smem_u32(&ctrl->a_full), a_phase);
                 a_phase ^= 1;
                 tc_fence_after();
-                w_a += clock64() - ca;
+                w_a += QCE_CLK() - ca;
                 for (int k = 0; k < a.K; ++k) {
                     #pragma unroll
                     for (int t = 0; t < TILES; ++t) {
                         // the first MMA overwrites the accumulator: the epilogue must have drained component k-1
-                        long long c0 = clock64();
+                        long long c0 = QCE_CLK();
                         if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
                         else { mbar_wait(smem_u32(&ctrl->acc_empty[1]), eph1 ^ 1); eph1 ^= 1; }
                         tc_fence_after();
-                        w_empty += clock64() - c0;
+                        w_empty += QCE_CLK() - c0;
                         const uint32_t d_tile = tmem_base + t * NT;
                         const uint32_t a_lo_t = a_lo0 + t * (Cfg::A_TILE_BYTES >> 4);
                         int stage = stage0;
                         uint32_t phase = phase0;
                         #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (t == 0) { c0 = clock64(); mbar_wait(smem_u32(&ctrl->full[stage]), phase); tc_fence_after(); w_full += clock64() - c0; }
-                            const uint32_t b_lo_s = b_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
-                            #pragma unroll
-                            for (int s2 = 0; s2 < KSPS; ++s2) {
-                                const int ks = (q & 1) * KSPS + s2;                 // K-step within the full K range
-                                const uint32_t skip = tri16 * ks;                   // structurally zero leading columns
-                                const uint64_t ad = ((uint64_t)DESC_HI << 32) | (a_lo_t + ks * ((2 * A_LBO) >> 4));
-                                const uint64_t bd = ((uint64_t)DESC_HI << 32) | (b_lo_s + s2 * ((2 * B_LBO) >> 4) + (skip >> 3) * (128 >> 4));
-                                const uint32_t idesc = (1u << 4) | (((uint32_t)(NT - skip) >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-                                umma_f16(d_tile + skip, ad, bd, idesc, (q >= 2 || ks > 0) ? 1u : 0u);
+                        for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                            if (t == 0) {
+                                c0 = QCE_CLK();
+                                mbar_wait(smem_u32(&ctrl->full[stage]), phase);
+                                tc_fence_after();
+                                w_full += QCE_CLK() - c0;
                             }
-                            if (t == TILES - 1) tc_commit(smem_u32(&ctrl->empty[stage]));
+                            const uint32_t b_addr_s = b_addr0 + stage * (Cfg::STAGE_BYTES >> 4);
+                            constexpr int KS_PER_CHUNK = (CG == 2) ? 2 * KSPS : KSPS;
+                            #pragma unroll
+                            for (int s2 = 0; s2 < KS_PER_CHUNK; ++s2) {
+                                const int ks = (CG == 2) ? s2 : (q & 1) * KSPS + s2;           // K-step within the full K range
+                                const bool lo_pass = (CG == 2) ? (q == 1) : (q >= 2);
+                                const uint32_t skip = (uint32_t)(tri16 * ks);                   // structurally zero leading columns
+                                const uint32_t np = NT - skip;                                  // N' of this MMA
+                                const uint32_t a_lo = a_lo_t + ks * ((2 * A_LBO) >> 4);
+                                uint32_t b_lo;
+                                if (CG == 2) {  // per-CTA half image: sub-block of N'/2 rows, LBO = (N'/16) cores * 128 B (all immediates)
+                                    const int half = ks / KSPS, sb = ks % KSPS;
+                                    const int off = (half ? Cfg::CB0 : 0) + tc2_sub_off(NT, 16, KSPS, half, sb);
+                                    b_lo = (b_addr_s + (uint32_t)(off >> 4)) | ((np >> 1) << 16);
+                                } else {        // full stacked image: skip the leading row blocks
+                                    b_lo = (b_addr_s + s2 * (((2 * NT / 8) * 128) >> 4) + (skip >> 3) * (128 >> 4)) | ((((NT / 8) * 128) >> 4) << 16);
+                                }
+                                const uint32_t idesc = IDESC0 | ((np >> 3) << 17);
+                                const uint32_t accum = (lo_pass || ks > 0) ? 1u : 0u;
+                                if (elected) {
+                                    if (CG == 2) umma2_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
+                                    else umma_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
+                                }
+                            }
+                            if (t == TILES - 1 && elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->empty[stage])); else tc_commit(smem_u32(&ctrl->empty[stage])); }
                             if (++stage == S) { stage = 0; phase ^= 1; }
                         }
-                        tc_commit(smem_u32(&ctrl->acc_full[t]));
+                        if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->acc_full[t])); else tc_commit(smem_u32(&ctrl->acc_full[t])); }
+                        __syncwarp();
                         if (t == TILES - 1) { stage0 = stage; phase0 = phase; }
                     }
                 }
-                tc_commit(smem_u32(&ctrl->a_free));
+                if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->a_free)); else tc_commit(smem_u32(&ctrl->a_free)); }
+                __syncwarp();
             }
-            if (a.prof && blockIdx.x == 0) { a.prof[0] = clock64() - t_begin; a.prof[1] = w_empty; a.prof[2] = w_full; a.prof[3] = w_a; }
+            if (a.prof && blockIdx.x == 0 && elected) { a.prof[0] = QCE_CLK() - t_begin; a.prof[1] = w_empty; a.prof[2] = w_full; a.prof[3] = w_a; }
+        } else if (CG == 2 && warp == 1 && lane == 0 && rank == 1) {
+            // ===================== relay (peer CTA): when this CTA's tiles / chunk have landed, arrive on the LEADER's barrier
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+                mbar_wait(smem_u32(&ctrl->a_full), a_phase);
+                a_phase ^= 1;
+                mbar_arrive_cluster(smem_u32(&ctrl->a_full), 0);
+                for (int k = 0; k < a.K; ++k) {
+                    #pragma unroll
+                    for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                        mbar_wait(smem_u32(&ctrl->full[stage]), phase);
+                        mbar_arrive_cluster(smem_u32(&ctrl->full[stage]), 0);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
@@ -295,12 +423,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         double err = 0.0, pw = 0.0, cnt = 0.0;
         long long w_acc = 0, c_z = 0, c_h = 0, c_pro = 0, c_ld = 0;
 
-        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-            const int64_t tile_base = (pair * TILES + t) * TILE_M;
-            long long c0 = clock64();
+        for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+            const int64_t tile_base = ((unit * CG + rank) * TILES + t) * TILE_M;
+            long long c0 = QCE_CLK();
             bool row_bad = false;
             if (tile_base + row < a.B) row_bad = __ldg(a.bad + tile_base + row) != 0;
-            c_pro += clock64() - c0;
+            c_pro += QCE_CLK() - c0;
 
             float acc[NH];
             #pragma unroll
@@ -317,20 +445,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 const float2 lc = lc_n;
                 if (k + 1 < a.K) { zs_n = __ldg(a.zscale + k + 1); hs_n = __ldg(a.hscale + k + 1); lc_n = __ldg(a.logc2 + k + 1); }
                 // ---- whitened residual -> quadratic form
-                c0 = clock64();
+                c0 = QCE_CLK();
                 mbar_wait(smem_u32(&ctrl->acc_full[t]), fph);
                 fph ^= 1;
                 tc_fence_after();
-                long long c1 = clock64();
+                long long c1 = QCE_CLK();
                 w_acc += c1 - c0;
                 float q_hi = 0.f, q_lo = 0.f;        // quadratic form as an unevaluated FP32 pair (TwoSum accumulation)
                 #pragma unroll
                 for (int ch = 0; ch < NCHZ; ++ch) {
                     float v[32];
-                    long long cl = clock64();
+                    long long cl = QCE_CLK();
                     tmem_ld32(tz + ch * 32, v);
                     tmem_ld_wait();
-                    c_ld += clock64() - cl;
+                    c_ld += QCE_CLK() - cl;
                     #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
                         float s0 = 0.f, s1 = 0.f;
@@ -375,7 +503,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     p = __expf(df);
                     ssum += p;
                 }
-                long long c2 = clock64();
+                long long c2 = QCE_CLK();
                 c_z += c2 - c1;
                 // ---- LMMSE row, weighted accumulation
                 if (__any_sync(0xffffffffu, p > 1e-30f)) {
@@ -393,8 +521,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(smem_u32(&ctrl->acc_empty[t]));
-                c_h += clock64() - c2;
+                __syncwarp();
+                if (lane == 0) {        // one arrival per warp on the LEADER's barrier
+                    if (CG == 2) mbar_arrive_cluster(smem_u32(&ctrl->acc_empty[t]), 0); else mbar_arrive(smem_u32(&ctrl->acc_empty[t]));
+                }
+                c_h += QCE_CLK() - c2;
             }
 
             // ---- finalise: normalise, write the estimate row, NMSE accumulators
@@ -440,11 +571,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         }
     }
 
+    __syncwarp();                                                // single-lane roles rejoin their warp before the block-wide barriers
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // the peer's smem / TMEM stay valid until every MMA has retired
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -495,6 +628,40 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict_
         const size_t dst = ((size_t)kb * (nt / 8) + nb0 + nb) * 64 + within;
         hi[dst] = h;
         lo[dst] = __double2half(x - (double)__half2float(h));
+    }
+}
+
+// CG=2 operand images (layout: see tc2_nprime / tc2_sub_off).  One block per (component, rank); the power-of-two scales
+// were fixed by tc_pack_kernel.
+__global__ void __launch_bounds__(256) tc2_pack_kernel(const double2* __restrict__ Linv, const double2* __restrict__ W, int No, int N,
+                                                       double data_scale, const float* __restrict__ zscale, const float* __restrict__ hscale,
+                                                       int tri16, unsigned char* __restrict__ image2) {
+    const int k = blockIdx.x >> 1, rank = blockIdx.x & 1;
+    const int kd = 2 * No, nz = 2 * No, nt = 2 * No + 2 * N, ksps = kd / 32;
+    const double scz = data_scale / (double)zscale[k], sch = data_scale / (double)hscale[k];
+    const int cb0 = tc2_chunk_bytes(nt, tri16, ksps, 0), cb1 = tc2_chunk_bytes(nt, tri16, ksps, 1);
+    unsigned char* base = image2 + ((size_t)k * 2 + rank) * (size_t)(2 * (cb0 + cb1));
+    for (int half = 0; half < 2; ++half) {
+        for (int s2 = 0; s2 < ksps; ++s2) {
+            const int ks = half * ksps + s2;
+            const int np = tc2_nprime(nt, tri16, ks), rows = np / 2;
+            const int n0 = tri16 * ks + rank * rows;                       // first stacked row held by this rank
+            __half* hi = reinterpret_cast<__half*>(base + (half ? cb0 : 0) + tc2_sub_off(nt, tri16, ksps, half, s2));
+            __half* lo = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(hi) + (cb0 + cb1));
+            for (int idx = threadIdx.x; idx < rows * 16; idx += 256) {
+                const int core = idx >> 6, within = idx & 63;              // core = kc * (rows/8) + nb
+                const int nb = core % (rows / 8), kc = core / (rows / 8);
+                const int n = n0 + nb * 8 + (within >> 3), kk = ks * 16 + kc * 8 + (within & 7);
+                const bool isz = n < nz;
+                const int rrow = isz ? n : n - nz;
+                const double2 v = isz ? Linv[((size_t)k * No + (rrow >> 1)) * No + (kk >> 1)] : W[((size_t)k * N + (rrow >> 1)) * No + (kk >> 1)];
+                const int aa = rrow & 1, bb = kk & 1;
+                const double x = (aa == bb ? v.x : (aa ? v.y : -v.y)) * (isz ? scz : sch);
+                const __half h = __double2half(x);
+                hi[idx] = h;
+                lo[idx] = __double2half(x - (double)__half2float(h));
+            }
+        }
     }
 }
 
@@ -581,7 +748,7 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
 
 static qce_status tc_ensure_tiles(qce_model* m, int64_t rows) {
     TcParams& p = m->tc;
-    const int64_t tiles = (rows + TILE_M - 1) / TILE_M + 1;        // +1: the last pair may touch one tile past the end
+    const int64_t tiles = (rows + TILE_M - 1) / TILE_M + 4;        // the last work unit (up to 4 tiles) may reach past the end
     if (tiles <= p.tile_cap) return QCE_OK;
     if (p.a_img) { QCE_CUDA_TRY(cudaFree(p.a_img)); QCE_CUDA_TRY(cudaFree(p.bad)); p.a_img = nullptr; p.bad = nullptr; p.tile_cap = 0; }
     QCE_CUDA_TRY(cudaMalloc(&p.a_img, (size_t)tiles * TILE_M * 2 * m->n_obs * sizeof(__half)));
@@ -601,7 +768,7 @@ bool tc_supported(const qce_model* m, int mode) {
 
 void tc_free(qce_model* m) {
     TcParams& p = m->tc;
-    cudaFree(p.image); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc2); cudaFree(p.flags); cudaFree(p.a_img); cudaFree(p.bad);
+    cudaFree(p.image); cudaFree(p.image2); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc2); cudaFree(p.flags); cudaFree(p.a_img); cudaFree(p.bad);
     p = TcParams();
 }
 
@@ -632,15 +799,25 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     QCE_CUDA_TRY(cudaStreamSynchronize(s));
     p.has_offsets = h_flags[0] != 0;
     p.triangular = h_flags[1] == 0;
+    {   // per-CTA half images of the SM-pair kernel (their layout depends on the triangular flag)
+        const int nt = (int)(2 * No + 2 * N), ksps = (int)(2 * No) / 32, tri16 = p.triangular ? 16 : 0;
+        const size_t bytes = K * 2 * (size_t)tc2_rank_comp_bytes(nt, tri16, ksps);
+        if (p.image2 && bytes > p.image2_bytes) { QCE_CUDA_TRY(cudaFree(p.image2)); p.image2 = nullptr; }
+        if (!p.image2) { QCE_CUDA_TRY(cudaMalloc(&p.image2, bytes)); p.image2_bytes = bytes; }
+        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+                                                          p.zscale, p.hscale, tri16, (unsigned char*)p.image2);
+        QCE_CHECK_LAUNCH("tc2_pack_kernel");
+        QCE_CUDA_TRY(cudaStreamSynchronize(s));
+    }
     p.ready = true;
     return QCE_OK;
 }
 
-template <int NCHZ, int NCHH, bool OFFS>
+template <int NCHZ, int NCHH, bool OFFS, int CG>
 static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
-    using Cfg = TcCfg<32 * NCHZ, 32 * NCHH>;
+    using Cfg = TcCfg<32 * NCHZ, 32 * NCHH, CG>;
     static bool attr_set = false;
-    auto kern = dense_tc_kernel<NCHZ, NCHH, OFFS>;
+    auto kern = dense_tc_kernel<NCHZ, NCHH, OFFS, CG>;
     if (!attr_set) {
         QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
@@ -648,22 +825,36 @@ static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t n_pairs = (a.B + TILES * TILE_M - 1) / (TILES * TILE_M);
-    const unsigned grid = (unsigned)(n_pairs < sms ? n_pairs : sms);
-    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, s>>>(a);
+    const int64_t n_units = (a.B + CG * TILES * TILE_M - 1) / (CG * TILES * TILE_M);
+    const int64_t max_clusters = sms / CG;
+    const unsigned grid = (unsigned)((n_units < max_clusters ? n_units : max_clusters) * CG);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QCE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
     QCE_CHECK_LAUNCH("dense_tc_kernel");
     return QCE_OK;
 }
 
 template <int NCHZ, int NCHH>
-static qce_status launch_offs(const TcArgs& a, bool offs, cudaStream_t s) {
-    return offs ? launch_cfg<NCHZ, NCHH, true>(a, s) : launch_cfg<NCHZ, NCHH, false>(a, s);
+static qce_status launch_offs(const TcArgs& a, bool offs, int cg, cudaStream_t s) {
+    if (cg == 2) return offs ? launch_cfg<NCHZ, NCHH, true, 2>(a, s) : launch_cfg<NCHZ, NCHH, false, 2>(a, s);
+    return offs ? launch_cfg<NCHZ, NCHH, true, 1>(a, s) : launch_cfg<NCHZ, NCHH, false, 1>(a, s);
 }
 
 static qce_status tc_run(const qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc) {
     const TcParams& p = m->tc;
     TcArgs a;
-    a.image = (const __half*)p.image; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
+    a.image = (const __half*)p.image; a.image2 = (const unsigned char*)p.image2; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
     a.logc2 = (const float2*)p.logc2; a.a_img = (const __half*)p.a_img; a.bad = (const unsigned char*)p.bad;
     a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
     a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant;
@@ -674,9 +865,12 @@ static qce_status tc_run(const qce_model* m, cudaStream_t s, int64_t B, double* 
     a.prof = want_prof ? prof : nullptr;
     const bool offs = p.has_offsets;
     const int cz = m->n_obs / 16, ch = m->n_ant / 16;
+    // QCE_TC_CG=1 selects the single-CTA (cta_group::1) variant; default is the SM-pair variant
+    static const int cg_env = (getenv("QCE_TC_CG") && atoi(getenv("QCE_TC_CG")) == 1) ? 1 : 2;
+    const int cg = p.triangular ? cg_env : 1;
     qce_status st = QCE_ERR_UNSUPPORTED;
     bool hit = false;
-#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, s); hit = true; }
+#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, cg, s); hit = true; }
     QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
 #undef QCE_TC_CASE
     if (!hit) {
