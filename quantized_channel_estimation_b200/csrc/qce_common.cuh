@@ -59,10 +59,6 @@ struct TcParams {
     float* zscale = nullptr;    // [K] power-of-two scale folded out of the Linv_k image
     float* hscale = nullptr;    // [K]
     void* logc2 = nullptr;      // [K] float2: logc_k as an FP32 (hi, lo) pair
-    void* a_img = nullptr;      // scratch: pilot tiles as FP16 integers (grown on demand, outside the steady state)
-    void* bad = nullptr;        // scratch: per-row off-grid flags
-    int64_t tile_cap = 0;
-    int64_t formatted_rows = 0; // pilots currently held in a_img
     int* flags = nullptr;       // device scratch: [0] offsets non-zero, [1] some Linv_k not lower triangular
     bool has_offsets = false;
     bool triangular = false;

@@ -33,6 +33,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+
 #include "qce_common.cuh"
 
 namespace qce {
@@ -430,9 +433,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             if (tile_base + row < a.B) row_bad = __ldg(a.bad + tile_base + row) != 0;
             c_pro += QCE_CLK() - c0;
 
-            float acc[NH];
+            float2 acc[NH / 2];                        // the estimate row, (re, im) pairs: packed FFMA2 arithmetic
             #pragma unroll
-            for (int j = 0; j < NH; ++j) acc[j] = 0.f;
+            for (int j = 0; j < NH / 2; ++j) acc[j] = make_float2(0.f, 0.f);
             float mref_hi = 0.f, mref_lo = 0.f;
             float ssum = 0.f;
 
@@ -452,34 +455,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 long long c1 = QCE_CLK();
                 w_acc += c1 - c0;
                 float q_hi = 0.f, q_lo = 0.f;        // quadratic form as an unevaluated FP32 pair (TwoSum accumulation)
+                // TMEM loads are double-buffered: chunk ch+1 (and finally the first H chunk) is in flight while chunk ch is
+                // reduced, so their latency stays off the accumulator-release critical path
+                float va[32], vb[32];
+                tmem_ld32(tz, va);
+                tmem_ld_wait();
                 #pragma unroll
                 for (int ch = 0; ch < NCHZ; ++ch) {
-                    float v[32];
-                    long long cl = QCE_CLK();
-                    tmem_ld32(tz + ch * 32, v);
-                    tmem_ld_wait();
-                    c_ld += QCE_CLK() - cl;
+                    float (&v)[32] = (ch & 1) ? vb : va;
+                    float (&vn)[32] = (ch & 1) ? va : vb;
+                    if (ch + 1 < NCHZ) tmem_ld32(tz + (ch + 1) * 32, vn); else tmem_ld32(th, vn);
                     #pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        float s0 = 0.f, s1 = 0.f;
+                    for (int g16 = 0; g16 < 2; ++g16) {
+                        float2 s0 = make_float2(0.f, 0.f), s1 = s0;
                         #pragma unroll
                         for (int u = 0; u < 8; u += 2) {
-                            float z0 = v[g8 * 8 + u], z1 = v[g8 * 8 + u + 1];
+                            float2 z0 = make_float2(v[g16 * 16 + 2 * u], v[g16 * 16 + 2 * u + 1]);
+                            float2 z1 = make_float2(v[g16 * 16 + 2 * u + 2], v[g16 * 16 + 2 * u + 3]);
                             if (OFFS) {
-                                z0 = fmaf(z0, zs, -__ldg(a.zoff + (size_t)k * NZ + ch * 32 + g8 * 8 + u));
-                                z1 = fmaf(z1, zs, -__ldg(a.zoff + (size_t)k * NZ + ch * 32 + g8 * 8 + u + 1));
+                                const float2* zo = reinterpret_cast<const float2*>(a.zoff + (size_t)k * NZ + ch * 32 + g16 * 16 + 2 * u);
+                                const float2 o0 = __ldg(zo), o1 = __ldg(zo + 1);
+                                z0 = __ffma2_rn(z0, make_float2(zs, zs), make_float2(-o0.x, -o0.y));
+                                z1 = __ffma2_rn(z1, make_float2(zs, zs), make_float2(-o1.x, -o1.y));
                             }
-                            s0 = fmaf(z0, z0, s0);
-                            s1 = fmaf(z1, z1, s1);
+                            s0 = __ffma2_rn(z0, z0, s0);
+                            s1 = __ffma2_rn(z1, z1, s1);
                         }
-                        {   // q += s0 + s1 without losing the rounding error (Knuth TwoSum, FP32 only)
-                            const float g = s0 + s1;
+                        {   // q += (16 squares) without losing the rounding error (Knuth TwoSum, FP32 only)
+                            const float g = (s0.x + s0.y) + (s1.x + s1.y);
                             const float tt = q_hi + g;
                             const float bp = tt - q_hi;
                             q_lo += (q_hi - (tt - bp)) + (g - bp);
                             q_hi = tt;
                         }
                     }
+                    tmem_ld_wait();
                 }
                 if (!OFFS) { const float zs2 = zs * zs; q_hi *= zs2; q_lo *= zs2; }   // power of two: exact
                 // l = logc - q as a pair: hi part plus the exact rounding error of the subtraction
@@ -496,7 +506,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         const float sc = __expf(-df);
                         ssum *= sc;
                         #pragma unroll
-                        for (int j = 0; j < NH; ++j) acc[j] *= sc;
+                        for (int j = 0; j < NH / 2; ++j) acc[j] = __fmul2_rn(acc[j], make_float2(sc, sc));
                         mref_hi = l_hi; mref_lo = l_lo;
                         df = 0.f;
                     }
@@ -505,19 +515,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 }
                 long long c2 = QCE_CLK();
                 c_z += c2 - c1;
-                // ---- LMMSE row, weighted accumulation
-                if (__any_sync(0xffffffffu, p > 1e-30f)) {
-                    const float ph = p * hs;
+                // ---- LMMSE row, weighted accumulation (the first H chunk is already in registers)
+                {
+                    const bool any = __any_sync(0xffffffffu, p > 1e-30f);
+                    const float2 ph = make_float2(p * hs, p * hs);
                     #pragma unroll
                     for (int ch = 0; ch < NCHH; ++ch) {
-                        float v[32];
-                        tmem_ld32(th + ch * 32, v);
-                        tmem_ld_wait();
-                        #pragma unroll
-                        for (int u = 0; u < 32; ++u) {
-                            acc[ch * 32 + u] = fmaf(ph, v[u], acc[ch * 32 + u]);
-                            if (OFFS) acc[ch * 32 + u] = fmaf(p, __ldg(a.hoff + (size_t)k * NH + ch * 32 + u), acc[ch * 32 + u]);
+                        float (&v)[32] = ((NCHZ + ch) & 1) ? vb : va;
+                        float (&vn)[32] = ((NCHZ + ch) & 1) ? va : vb;
+                        if (ch + 1 < NCHH && any) tmem_ld32(th + (ch + 1) * 32, vn);
+                        if (any) {
+                            #pragma unroll
+                            for (int u = 0; u < 16; ++u) {
+                                acc[ch * 16 + u] = __ffma2_rn(ph, make_float2(v[2 * u], v[2 * u + 1]), acc[ch * 16 + u]);
+                                if (OFFS) {
+                                    const float2 ho = __ldg(reinterpret_cast<const float2*>(a.hoff + (size_t)k * NH + ch * 32 + 2 * u));
+                                    acc[ch * 16 + u] = __ffma2_rn(make_float2(p, p), ho, acc[ch * 16 + u]);
+                                }
+                            }
                         }
+                        tmem_ld_wait();
                     }
                 }
                 tc_fence_before();
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 double2* out = a.h_est ? a.h_est + g * N : nullptr;
                 #pragma unroll
                 for (int j = 0; j < NH / 2; ++j) {
-                    const double2 e = make_double2((double)(acc[2 * j] * invs), (double)(acc[2 * j + 1] * invs));
+                    const double2 e = make_double2((double)(acc[j].x * invs), (double)(acc[j].y * invs));
                     if (out) out[j] = e;
                     if (a.acc && a.h_true) {
                         double2 h;
@@ -746,16 +763,38 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
     if (threadIdx.x < 8) bad[tile * TILE_M + mb * 8 + threadIdx.x] = (unsigned char)s_bad[threadIdx.x];
 }
 
-static qce_status tc_ensure_tiles(qce_model* m, int64_t rows) {
-    TcParams& p = m->tc;
-    const int64_t tiles = (rows + TILE_M - 1) / TILE_M + 4;        // the last work unit (up to 4 tiles) may reach past the end
-    if (tiles <= p.tile_cap) return QCE_OK;
-    if (p.a_img) { QCE_CUDA_TRY(cudaFree(p.a_img)); QCE_CUDA_TRY(cudaFree(p.bad)); p.a_img = nullptr; p.bad = nullptr; p.tile_cap = 0; }
-    QCE_CUDA_TRY(cudaMalloc(&p.a_img, (size_t)tiles * TILE_M * 2 * m->n_obs * sizeof(__half)));
-    QCE_CUDA_TRY(cudaMalloc(&p.bad, (size_t)tiles * TILE_M));
-    QCE_CUDA_TRY(cudaMemset(p.a_img, 0, (size_t)tiles * TILE_M * 2 * m->n_obs * sizeof(__half)));
-    QCE_CUDA_TRY(cudaMemset(p.bad, 0, (size_t)tiles * TILE_M));
-    p.tile_cap = tiles;
+// Pilot-tile scratch: one buffer set per CUDA stream (calls on different streams may be in flight concurrently, e.g. the
+// double-buffered host path), shared by all models, grown on demand outside the steady state.
+struct TileScratch {
+    void* img = nullptr;
+    void* bad = nullptr;
+    size_t img_bytes = 0, bad_bytes = 0;
+    const qce_model* owner = nullptr;      // model whose pilots are currently formatted here
+    int64_t rows = 0;
+};
+static std::mutex g_scratch_mu;
+static std::map<cudaStream_t, TileScratch> g_scratch;
+
+static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, TileScratch** out) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    TileScratch& t = g_scratch[s];
+    const size_t tiles = (size_t)((rows + TILE_M - 1) / TILE_M + 4);   // the last work unit (up to 4 tiles) may reach past the end
+    const size_t need_img = tiles * TILE_M * 2 * (size_t)m->n_obs * sizeof(__half), need_bad = tiles * TILE_M;
+    if (need_img > t.img_bytes) {
+        if (t.img) QCE_CUDA_TRY(cudaFree(t.img));
+        t.img = nullptr; t.img_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t.img, need_img));
+        QCE_CUDA_TRY(cudaMemset(t.img, 0, need_img));
+        t.img_bytes = need_img;
+    }
+    if (need_bad > t.bad_bytes) {
+        if (t.bad) QCE_CUDA_TRY(cudaFree(t.bad));
+        t.bad = nullptr; t.bad_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t.bad, need_bad));
+        QCE_CUDA_TRY(cudaMemset(t.bad, 0, need_bad));
+        t.bad_bytes = need_bad;
+    }
+    *out = &t;
     return QCE_OK;
 }
 
@@ -768,7 +807,7 @@ bool tc_supported(const qce_model* m, int mode) {
 
 void tc_free(qce_model* m) {
     TcParams& p = m->tc;
-    cudaFree(p.image); cudaFree(p.image2); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc2); cudaFree(p.flags); cudaFree(p.a_img); cudaFree(p.bad);
+    cudaFree(p.image); cudaFree(p.image2); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc2); cudaFree(p.flags);
     p = TcParams();
 }
 
@@ -851,11 +890,12 @@ static qce_status launch_offs(const TcArgs& a, bool offs, int cg, cudaStream_t s
     return offs ? launch_cfg<NCHZ, NCHH, true, 1>(a, s) : launch_cfg<NCHZ, NCHH, false, 1>(a, s);
 }
 
-static qce_status tc_run(const qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc) {
+static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
+                         double* acc) {
     const TcParams& p = m->tc;
     TcArgs a;
     a.image = (const __half*)p.image; a.image2 = (const unsigned char*)p.image2; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
-    a.logc2 = (const float2*)p.logc2; a.a_img = (const __half*)p.a_img; a.bad = (const unsigned char*)p.bad;
+    a.logc2 = (const float2*)p.logc2; a.a_img = (const __half*)ts->img; a.bad = (const unsigned char*)ts->bad;
     a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
     a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant;
     a.tri = p.triangular ? 1 : 0;
@@ -890,23 +930,39 @@ static bool tc_instantiated(const qce_model* m) {
     return (cz == ch && cz >= 1 && cz <= 4) || (cz == 4 && ch == 2) || (cz == 2 && ch == 1);
 }
 
-qce_status tc_format(qce_model* m, cudaStream_t s, const double* r, int64_t B) {
+static qce_status tc_format_into(qce_model* m, cudaStream_t s, const double* r, int64_t B, TileScratch** out) {
     if (!tc_instantiated(m)) { set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant); return QCE_ERR_UNSUPPORTED; }
-    qce_status st = tc_ensure_tiles(m, B);
+    TileScratch* ts = nullptr;
+    qce_status st = tc_scratch(m, s, B, &ts);
     if (st) return st;
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
     QuantTables none{};
     tc_format_kernel<false, false><<<(unsigned)(tiles * (TILE_M / 8)), 256, 0, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->data_scale,
-                                                                                  (__half*)m->tc.a_img, (unsigned char*)m->tc.bad);
+                                                                                  (__half*)ts->img, (unsigned char*)ts->bad);
     QCE_CHECK_LAUNCH("tc_format_kernel");
-    m->tc.formatted_rows = B;
+    ts->owner = m; ts->rows = B;
+    *out = ts;
     return QCE_OK;
 }
 
+qce_status tc_format(qce_model* m, cudaStream_t s, const double* r, int64_t B) {
+    TileScratch* ts = nullptr;
+    return tc_format_into(m, s, r, B, &ts);
+}
+
 qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc) {
-    if (B > m->tc.formatted_rows) { set_error("qce_estimate_formatted: only %lld pilots are formatted", (long long)m->tc.formatted_rows); return QCE_ERR_INVALID; }
+    TileScratch* ts = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        auto it = g_scratch.find(s);
+        if (it != g_scratch.end()) ts = &it->second;
+    }
+    if (!ts || ts->owner != m || B > ts->rows) {
+        set_error("qce_estimate_formatted: no pilots of this model are formatted on this stream (or fewer than %lld)", (long long)B);
+        return QCE_ERR_INVALID;
+    }
     if (B == 0) return QCE_OK;
-    return tc_run(m, s, B, h_est, h_true, h_true_c64, acc);
+    return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
 }
 
 // pilots given as complex128 values (estimate_from_y): format, then estimate
@@ -916,9 +972,10 @@ qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_
     if (B == 0) return QCE_OK;
     if (logp_out) { set_error("tensor-core kernel does not export log-probabilities"); return QCE_ERR_UNSUPPORTED; }
     if (mode != QCE_MODE_ALL) { set_error("tensor-core kernel: mode %d not supported", mode); return QCE_ERR_UNSUPPORTED; }
-    qce_status st = tc_format(m, s, r, B);
+    TileScratch* ts = nullptr;
+    qce_status st = tc_format_into(m, s, r, B, &ts);
     if (st) return st;
-    return tc_run(m, s, B, h_est, h_true, h_true_c64, acc);
+    return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
 }
 
 // fused Monte-Carlo step: observe (A = I) -> quantise -> estimate -> NMSE accumulators; the quantised pilots never exist in HBM
@@ -927,20 +984,21 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
                               double noise_scale, int64_t B, int mode, double* h_est, double* acc) {
     if (B == 0) return QCE_OK;
     if (mode != QCE_MODE_ALL || !tc_instantiated(m)) { set_error("tensor-core pipeline: shape/mode not supported"); return QCE_ERR_UNSUPPORTED; }
-    qce_status st = tc_ensure_tiles(m, B);
+    TileScratch* ts = nullptr;
+    qce_status st = tc_scratch(m, s, B, &ts);
     if (st) return st;
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
     const size_t smem = (qt->n_bits > 1) ? (size_t)(2 * qt->n_thr + 1) * sizeof(double) : 0;
     const unsigned grid = (unsigned)(tiles * (TILE_M / 8));
     if (h_is_c64)
         tc_format_kernel<true, true><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, 1.0 / m->data_scale,
-                                                            (__half*)m->tc.a_img, (unsigned char*)m->tc.bad);
+                                                            (__half*)ts->img, (unsigned char*)ts->bad);
     else
         tc_format_kernel<true, false><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, 1.0 / m->data_scale,
-                                                             (__half*)m->tc.a_img, (unsigned char*)m->tc.bad);
+                                                             (__half*)ts->img, (unsigned char*)ts->bad);
     QCE_CHECK_LAUNCH("tc_format_kernel(observe)");
-    m->tc.formatted_rows = B;
-    return tc_run(m, s, B, h_est, h, h_is_c64, acc);
+    ts->owner = m; ts->rows = B;
+    return tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
 }
 
 }  // namespace qce
