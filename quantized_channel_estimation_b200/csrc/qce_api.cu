@@ -223,7 +223,7 @@ qce_status qce_pipeline(qce_model* m, const qce_quantizer* q, void* stream, cons
         for (int64_t b0 = 0; b0 < B; b0 += chunk) {
             const int64_t nb = (B - b0) < chunk ? (B - b0) : chunk;
             const char* hp = (const char*)h + (size_t)b0 * N * hs;
-            qce_status st = launch_pipeline_tc(m, &q->t, s, hp, h_is_c64, (const double*)noise + (size_t)b0 * N * 2, noise_scale, nb, mode,
+            qce_status st = launch_pipeline_tc(m, &q->t, s, hp, h_is_c64, (const double*)noise + (size_t)b0 * N * 2, noise_scale, nb, mode, n_top, rho,
                                                h_est ? (double*)h_est + (size_t)b0 * N * 2 : nullptr, acc);
             if (st) return st;
         }

@@ -104,6 +104,7 @@ qce_status tc_format(qce_model* m, cudaStream_t s, const double* r, int64_t B);
 qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
                                  double* acc);
 qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t s, const void* h, int h_is_c64,
-                              const double* noise, double noise_scale, int64_t B, int mode, double* h_est, double* acc);
+                              const double* noise, double noise_scale, int64_t B, int mode, int n_top, double rho, double* h_est,
+                              double* acc);
 bool tc_supported(const qce_model* m, int mode);
 }  // namespace qce

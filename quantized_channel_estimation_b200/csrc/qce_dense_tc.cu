@@ -64,6 +64,8 @@ struct TcArgs {
     const __half* a_img;       // [n_tiles][128 x 2No] pilots as exact FP16 integers, canonical K-major core-matrix tiles
     const unsigned char* bad;  // [n_tiles * 128] rows whose data was not on the quantiser grid (estimate -> NaN)
     double2* h_est;            // [B][N] or null
+    float2* lp_out;            // EPI=1: [B][K] weighted log-probabilities as FP32 (hi, lo) pairs
+    const float* w_in;         // EPI=2: [B][K] combination weights
     const void* h_true;        // [B][N] c64/c128 or null
     int h_true_c64;
     double* acc;               // [3] or null
@@ -235,7 +237,9 @@ struct TcCtrl {
 };
 static_assert(sizeof(TcCtrl) <= 1024, "control block");
 
-template <int NCHZ, int NCHH, bool OFFS, int CG>
+// EPI selects the epilogue: 0 = fused 'all' estimate (online softmax), 1 = export the weighted log-probabilities l_k only,
+// 2 = combine with given per-pilot weights (the top-1 / top-n / cumulative-probability modes run 1 -> select -> 2)
+template <int NCHZ, int NCHH, bool OFFS, int CG, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
     using Cfg = TcCfg<NZ, NH, CG>;
@@ -441,12 +445,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
 
             float zs_n = __ldg(a.zscale), hs_n = __ldg(a.hscale);
             float2 lc_n = __ldg(a.logc2);
+            const int64_t grow = (tile_base + row < a.B) ? tile_base + row : 0;     // rows past the end read row 0, never write
+            float w_n = (EPI == 2) ? __ldg(a.w_in + grow * a.K) : 0.f;
             for (int k = 0; k < a.K; ++k) {
                 // per-component scalars were fetched one iteration ahead (their L2 latency would otherwise sit on the
                 // critical path between "accumulator ready" and "accumulator released")
                 const float zs = zs_n, hs = hs_n;
                 const float2 lc = lc_n;
-                if (k + 1 < a.K) { zs_n = __ldg(a.zscale + k + 1); hs_n = __ldg(a.hscale + k + 1); lc_n = __ldg(a.logc2 + k + 1); }
+                const float w_k = w_n;
+                if (k + 1 < a.K) {
+                    zs_n = __ldg(a.zscale + k + 1); hs_n = __ldg(a.hscale + k + 1); lc_n = __ldg(a.logc2 + k + 1);
+                    if (EPI == 2) w_n = __ldg(a.w_in + grow * a.K + k + 1);
+                }
                 // ---- whitened residual -> quadratic form
                 c0 = QCE_CLK();
                 mbar_wait(smem_u32(&ctrl->acc_full[t]), fph);
@@ -454,17 +464,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 tc_fence_after();
                 long long c1 = QCE_CLK();
                 w_acc += c1 - c0;
+                float va[32], vb[32];
+                float p;
+                if (EPI != 2) {
                 float q_hi = 0.f, q_lo = 0.f;        // quadratic form as an unevaluated FP32 pair (TwoSum accumulation)
                 // TMEM loads are double-buffered: chunk ch+1 (and finally the first H chunk) is in flight while chunk ch is
                 // reduced, so their latency stays off the accumulator-release critical path
-                float va[32], vb[32];
                 tmem_ld32(tz, va);
                 tmem_ld_wait();
                 #pragma unroll
                 for (int ch = 0; ch < NCHZ; ++ch) {
                     float (&v)[32] = (ch & 1) ? vb : va;
                     float (&vn)[32] = (ch & 1) ? va : vb;
-                    if (ch + 1 < NCHZ) tmem_ld32(tz + (ch + 1) * 32, vn); else tmem_ld32(th, vn);
+                    if (ch + 1 < NCHZ) tmem_ld32(tz + (ch + 1) * 32, vn); else if (EPI == 0) tmem_ld32(th, vn);
                     #pragma unroll
                     for (int g16 = 0; g16 < 2; ++g16) {
                         float2 s0 = make_float2(0.f, 0.f), s1 = s0;
@@ -496,8 +508,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 const float l_hi = lc.x - q_hi;
                 const float bq = l_hi - lc.x;
                 const float l_lo = ((lc.x - (l_hi - bq)) + (-q_hi - bq)) + (lc.y - q_lo);
+                if (EPI == 1) {
+                    if (tile_base + row < a.B) a.lp_out[(tile_base + row) * a.K + k] = make_float2(l_hi, l_lo);
+                    p = 0.f;
+                } else {
                 // ---- lazily rescaled online softmax (reference maximum moves only on jumps > 8)
-                float p;
                 if (k == 0) {
                     mref_hi = l_hi; mref_lo = l_lo; p = 1.f; ssum = 1.f;
                 } else {
@@ -513,11 +528,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     p = __expf(df);
                     ssum += p;
                 }
+                }
+                } else {
+                    p = w_k;                         // given weight; the first H chunk has to be fetched here
+                    if (__any_sync(0xffffffffu, p != 0.f)) { tmem_ld32(th, (NCHZ & 1) ? vb : va); tmem_ld_wait(); }
+                }
                 long long c2 = QCE_CLK();
                 c_z += c2 - c1;
                 // ---- LMMSE row, weighted accumulation (the first H chunk is already in registers)
-                {
-                    const bool any = __any_sync(0xffffffffu, p > 1e-30f);
+                if (EPI != 1) {
+                    const bool any = __any_sync(0xffffffffu, (EPI == 2) ? (p != 0.f) : (p > 1e-30f));
                     const float2 ph = make_float2(p * hs, p * hs);
                     #pragma unroll
                     for (int ch = 0; ch < NCHH; ++ch) {
@@ -547,8 +567,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
 
             // ---- finalise: normalise, write the estimate row, NMSE accumulators
             const int64_t g = tile_base + row;
-            if (g < a.B) {
-                const float invs = row_bad ? __int_as_float(0x7fc00000) : 1.f / ssum;
+            if (EPI != 1 && g < a.B) {
+                const float invs = row_bad ? __int_as_float(0x7fc00000) : (EPI == 2 ? 1.f : 1.f / ssum);
                 double2* out = a.h_est ? a.h_est + g * N : nullptr;
                 #pragma unroll
                 for (int j = 0; j < NH / 2; ++j) {
@@ -763,12 +783,97 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
     if (threadIdx.x < 8) bad[tile * TILE_M + mb * 8 + threadIdx.x] = (unsigned char)s_bad[threadIdx.x];
 }
 
+// ------------------------------------------------------------------------------------------------ mode selection
+// One warp per pilot: weighted log-probabilities (FP32 pairs from the EPI=1 pass) -> combination weights per mode, with
+// the reference's semantics (gmm:197-242 / mofa:125-158): softmax responsibilities; top-1 = argmax of l (MFA flag: argmax
+// of exp(l), i.e. label 0 when everything underflows); top-n / cumulative-rho = descending selection, renormalised.
+// K <= 1024 (32 values per lane).  Also exports l as float64 when asked.
+__global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho,
+                                                        int flags, float* __restrict__ w_out, double* __restrict__ logp_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    constexpr int PER = 32;
+    double l[PER];
+    const int per = (K + 31) / 32;
+    double mx = -INFINITY;
+    int amax = 0;
+    #pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        l[i] = -INFINITY;
+        if (i < per) {
+            const int k = i * 32 + lane;
+            if (k < K) {
+                const float2 v = lp2[b * K + k];
+                l[i] = (double)v.x + (double)v.y;
+                if (logp_out) logp_out[b * K + k] = l[i];
+                if (l[i] > mx) { mx = l[i]; amax = k; }
+            }
+        }
+    }
+    // warp argmax (first index among equal maxima, like np.argmax)
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double om = __shfl_xor_sync(0xffffffffu, mx, off);
+        const int oa = __shfl_xor_sync(0xffffffffu, amax, off);
+        if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+    }
+    if (!w_out) return;
+    if (mode == QCE_MODE_TOP1) {
+        if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
+        #pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = (k == amax) ? 1.f : 0.f; }
+        return;
+    }
+    double sum = 0.0;
+    #pragma unroll
+    for (int i = 0; i < PER; ++i) if (i < per && i * 32 + lane < K) sum += exp(l[i] - mx);
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const double lse = mx + log(sum);
+    #pragma unroll
+    for (int i = 0; i < PER; ++i) l[i] = (i < per && i * 32 + lane < K) ? exp(l[i] - lse) : -1.0;     // responsibilities; -1 = no entry
+    if (mode == QCE_MODE_ALL) {
+        #pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = (float)l[i]; }
+        return;
+    }
+    // descending selection; selected entries are flagged by a set bit in `sel`
+    const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
+    unsigned sel = 0;
+    double cum = 0.0;
+    for (int it = 0; it < limit; ++it) {
+        double bv = -1.0;
+        int bk = 0x7fffffff;
+        #pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (i < per && !((sel >> i) & 1u) && l[i] > bv) { bv = l[i]; bk = i * 32 + lane; }
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+            if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+        }
+        if (bv < 0.0) break;
+        if ((bk & 31) == lane) sel |= 1u << (bk >> 5);
+        cum += bv;
+        if (mode == QCE_MODE_CUMPROB && cum >= rho) break;      // searchsorted(cumsum, rho) + 1 entries (gmm:234)
+    }
+    #pragma unroll
+    for (int i = 0; i < PER; ++i)
+        if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = ((sel >> i) & 1u) ? (float)(l[i] / cum) : 0.f; }
+}
+
 // Pilot-tile scratch: one buffer set per CUDA stream (calls on different streams may be in flight concurrently, e.g. the
 // double-buffered host path), shared by all models, grown on demand outside the steady state.
 struct TileScratch {
     void* img = nullptr;
     void* bad = nullptr;
-    size_t img_bytes = 0, bad_bytes = 0;
+    void* lp2 = nullptr;                   // [rows][K] float2 log-probabilities (modes other than fused 'all')
+    void* wts = nullptr;                   // [rows][K] float weights
+    size_t img_bytes = 0, bad_bytes = 0, lp2_bytes = 0, wts_bytes = 0;
     const qce_model* owner = nullptr;      // model whose pilots are currently formatted here
     int64_t rows = 0;
 };
@@ -798,8 +903,27 @@ static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, T
     return QCE_OK;
 }
 
+static qce_status tc_scratch_aux(TileScratch* t, size_t rows, size_t K) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    const size_t need_lp = rows * K * sizeof(float2), need_w = rows * K * sizeof(float);
+    if (need_lp > t->lp2_bytes) {
+        if (t->lp2) QCE_CUDA_TRY(cudaFree(t->lp2));
+        t->lp2 = nullptr; t->lp2_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t->lp2, need_lp));
+        t->lp2_bytes = need_lp;
+    }
+    if (need_w > t->wts_bytes) {
+        if (t->wts) QCE_CUDA_TRY(cudaFree(t->wts));
+        t->wts = nullptr; t->wts_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t->wts, need_w));
+        t->wts_bytes = need_w;
+    }
+    return QCE_OK;
+}
+
 bool tc_supported(const qce_model* m, int mode) {
-    if (mode != QCE_MODE_ALL) return false;
+    // the modes other than the fused 'all' need the SM-pair variant (triangular whitening factor)
+    if (mode != QCE_MODE_ALL && m->tc.ready && !m->tc.triangular) return false;
     if (m->n_obs % 16 || m->n_ant % 16 || m->n_obs > 64 || m->n_ant > 64) return false;
     if (!(m->data_scale > 0.0)) return false;
     return true;
@@ -852,11 +976,11 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     return QCE_OK;
 }
 
-template <int NCHZ, int NCHH, bool OFFS, int CG>
+template <int NCHZ, int NCHH, bool OFFS, int CG, int EPI>
 static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
     using Cfg = TcCfg<32 * NCHZ, 32 * NCHH, CG>;
     static bool attr_set = false;
-    auto kern = dense_tc_kernel<NCHZ, NCHH, OFFS, CG>;
+    auto kern = dense_tc_kernel<NCHZ, NCHH, OFFS, CG, EPI>;
     if (!attr_set) {
         QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
@@ -885,18 +1009,24 @@ static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
 }
 
 template <int NCHZ, int NCHH>
-static qce_status launch_offs(const TcArgs& a, bool offs, int cg, cudaStream_t s) {
-    if (cg == 2) return offs ? launch_cfg<NCHZ, NCHH, true, 2>(a, s) : launch_cfg<NCHZ, NCHH, false, 2>(a, s);
-    return offs ? launch_cfg<NCHZ, NCHH, true, 1>(a, s) : launch_cfg<NCHZ, NCHH, false, 1>(a, s);
+static qce_status launch_offs(const TcArgs& a, bool offs, int cg, int epi, cudaStream_t s) {
+    if (cg == 2) {
+        if (epi == 1) return offs ? launch_cfg<NCHZ, NCHH, true, 2, 1>(a, s) : launch_cfg<NCHZ, NCHH, false, 2, 1>(a, s);
+        if (epi == 2) return offs ? launch_cfg<NCHZ, NCHH, true, 2, 2>(a, s) : launch_cfg<NCHZ, NCHH, false, 2, 2>(a, s);
+        return offs ? launch_cfg<NCHZ, NCHH, true, 2, 0>(a, s) : launch_cfg<NCHZ, NCHH, false, 2, 0>(a, s);
+    }
+    if (epi != 0) { set_error("tensor-core kernel: the single-CTA variant only implements the fused 'all' epilogue"); return QCE_ERR_UNSUPPORTED; }
+    return offs ? launch_cfg<NCHZ, NCHH, true, 1, 0>(a, s) : launch_cfg<NCHZ, NCHH, false, 1, 0>(a, s);
 }
 
 static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
-                         double* acc) {
+                         double* acc, int epi = 0) {
     const TcParams& p = m->tc;
     TcArgs a;
     a.image = (const __half*)p.image; a.image2 = (const unsigned char*)p.image2; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
     a.logc2 = (const float2*)p.logc2; a.a_img = (const __half*)ts->img; a.bad = (const unsigned char*)ts->bad;
     a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
+    a.lp_out = (float2*)ts->lp2; a.w_in = (const float*)ts->wts;
     a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant;
     a.tri = p.triangular ? 1 : 0;
     static long long* prof = nullptr;
@@ -910,7 +1040,7 @@ static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t
     const int cg = p.triangular ? cg_env : 1;
     qce_status st = QCE_ERR_UNSUPPORTED;
     bool hit = false;
-#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, cg, s); hit = true; }
+#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, cg, epi, s); hit = true; }
     QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
 #undef QCE_TC_CASE
     if (!hit) {
@@ -965,25 +1095,39 @@ qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double
     return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
 }
 
+// the general path: log-probabilities -> per-mode weights -> weighted combination (three launches)
+static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, int64_t B, int mode, int n_top, double rho, double* h_est,
+                               double* logp_out, const void* h_true, int h_true_c64, double* acc) {
+    if (m->n_comp > 1024) { set_error("tensor-core mode selection supports K <= 1024"); return QCE_ERR_UNSUPPORTED; }
+    qce_status st = tc_scratch_aux(ts, (size_t)B, (size_t)m->n_comp);
+    if (st) return st;
+    st = tc_run(m, ts, s, B, nullptr, nullptr, 0, nullptr, 1);
+    if (st) return st;
+    const bool want_est = h_est || acc;
+    tc_select_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags,
+                                                             want_est ? (float*)ts->wts : nullptr, logp_out);
+    QCE_CHECK_LAUNCH("tc_select_kernel");
+    if (!want_est) return QCE_OK;
+    return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc, 2);
+}
+
 // pilots given as complex128 values (estimate_from_y): format, then estimate
 qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
                            double* h_est, double* logp_out, const void* h_true, int h_true_c64, double* acc) {
-    (void)n_top; (void)rho;
     if (B == 0) return QCE_OK;
-    if (logp_out) { set_error("tensor-core kernel does not export log-probabilities"); return QCE_ERR_UNSUPPORTED; }
-    if (mode != QCE_MODE_ALL) { set_error("tensor-core kernel: mode %d not supported", mode); return QCE_ERR_UNSUPPORTED; }
     TileScratch* ts = nullptr;
     qce_status st = tc_format_into(m, s, r, B, &ts);
     if (st) return st;
-    return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
+    if (mode == QCE_MODE_ALL && !logp_out) return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
+    return tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
 }
 
 // fused Monte-Carlo step: observe (A = I) -> quantise -> estimate -> NMSE accumulators; the quantised pilots never exist in HBM
 // other than as the FP16 tile image
 qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t s, const void* h, int h_is_c64, const double* noise,
-                              double noise_scale, int64_t B, int mode, double* h_est, double* acc) {
+                              double noise_scale, int64_t B, int mode, int n_top, double rho, double* h_est, double* acc) {
     if (B == 0) return QCE_OK;
-    if (mode != QCE_MODE_ALL || !tc_instantiated(m)) { set_error("tensor-core pipeline: shape/mode not supported"); return QCE_ERR_UNSUPPORTED; }
+    if (!tc_instantiated(m)) { set_error("tensor-core pipeline: shape not supported"); return QCE_ERR_UNSUPPORTED; }
     TileScratch* ts = nullptr;
     qce_status st = tc_scratch(m, s, B, &ts);
     if (st) return st;
@@ -998,7 +1142,8 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
                                                              (__half*)ts->img, (unsigned char*)ts->bad);
     QCE_CHECK_LAUNCH("tc_format_kernel(observe)");
     ts->owner = m; ts->rows = B;
-    return tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
+    if (mode == QCE_MODE_ALL) return tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
+    return tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);
 }
 
 }  // namespace qce
