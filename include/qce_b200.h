@@ -62,6 +62,7 @@ enum {
 
 typedef struct qce_model qce_model;
 typedef struct qce_quantizer qce_quantizer;
+typedef struct qce_circ_model qce_circ_model;
 
 int qce_abi_version(void);
 const char* qce_last_error_string(void);
@@ -142,6 +143,18 @@ qce_status qce_pipeline(qce_model* m, const qce_quantizer* q, void* stream, cons
 qce_status qce_format_pilots(qce_model* m, void* stream, const void* r_dev, int64_t B);
 qce_status qce_estimate_formatted(qce_model* m, void* stream, int64_t B, void* h_est_dev, const void* h_true_dev,
                                   double* acc_dev);
+
+/* ---- circulant / block-circulant covariances (new algorithm; the reference only has the dense path, into which it
+ * converts every covariance type, gmm:110-136).  C_h,k = F^H diag(c_k) F with F = F_n1 (x) F_n2 unitary (n1 = 1: plain
+ * circulant), A = I, zero means.  Host-precomputed per (snr, bits): inv_lambda_t [N][K] = 1 / eigenvalues of C_r,k
+ * (transposed), gain [K][N] = b_k c_k / lambda_k, logc [K] = ln w_k - N ln(pi) - sum_i ln lambda_k,i; all device f64.
+ * qce_circ_estimate has the semantics of qce_estimate (complex128 arithmetic, all four modes). */
+qce_status qce_circ_model_create(int n1, int n2, int n_comp, int flags, qce_circ_model** out);
+void qce_circ_model_destroy(qce_circ_model* m);
+qce_status qce_circ_model_set_params(qce_circ_model* m, void* stream, const double* inv_lambda_t_dev, const double* gain_dev,
+                                     const double* logc_dev);
+qce_status qce_circ_estimate(qce_circ_model* m, void* stream, const void* r_dev, int64_t B, int mode, int n_top, double rho,
+                             void* h_est_dev, double* logp_out_dev, const void* h_true_dev, double* acc_dev);
 
 /* Host-buffer form of qce_estimate: r_host c128 [B][n_obs] -> h_est_host c128 [B][n_ant].  Copies are
  * chunked through pinned staging buffers owned by the model and overlapped with the kernels on the

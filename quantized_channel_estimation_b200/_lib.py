@@ -33,6 +33,11 @@ _SIGS = {
                                C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     'qce_format_pilots': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     'qce_estimate_formatted': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'qce_circ_model_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    'qce_circ_model_destroy': (None, [C.c_void_p]),
+    'qce_circ_model_set_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'qce_circ_estimate': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     'qce_estimate_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.c_void_p]),
 }

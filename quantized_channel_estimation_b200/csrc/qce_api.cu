@@ -252,6 +252,46 @@ qce_status qce_pipeline(qce_model* m, const qce_quantizer* q, void* stream, cons
     return QCE_OK;
 }
 
+qce_status qce_circ_model_create(int n1, int n2, int n_comp, int flags, qce_circ_model** out) {
+    if (!out || n1 < 1 || n2 < 1 || n_comp < 1 || n1 > 256 || n2 > 256 || n_comp > 4096) { set_error("qce_circ_model_create: invalid shape"); return QCE_ERR_INVALID; }
+    qce_status st = require_device();
+    if (st) return st;
+    qce_circ_model* m = new qce_circ_model();
+    m->n1 = n1; m->n2 = n2; m->n_ant = n1 * n2; m->n_comp = n_comp; m->flags = flags;
+    const size_t N = m->n_ant, K = n_comp;
+    cudaError_t e = cudaMalloc(&m->inv_lambda_t, N * K * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&m->gain, N * K * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&m->logc, K * 8);
+    if (e != cudaSuccess) { set_error("qce_circ_model_create: %s", cudaGetErrorString(e)); qce_circ_model_destroy(m); return QCE_ERR_CUDA; }
+    *out = m;
+    return QCE_OK;
+}
+
+void qce_circ_model_destroy(qce_circ_model* m) {
+    if (!m) return;
+    cudaFree(m->inv_lambda_t); cudaFree(m->gain); cudaFree(m->logc);
+    delete m;
+}
+
+qce_status qce_circ_model_set_params(qce_circ_model* m, void* stream, const double* inv_lambda_t, const double* gain, const double* logc) {
+    if (!m || !inv_lambda_t || !gain || !logc) { set_error("qce_circ_model_set_params: invalid argument"); return QCE_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = m->n_ant, K = m->n_comp;
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->inv_lambda_t, inv_lambda_t, N * K * 8, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->gain, gain, N * K * 8, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->logc, logc, K * 8, cudaMemcpyDeviceToDevice, s));
+    m->params_set = true;
+    return QCE_OK;
+}
+
+qce_status qce_circ_estimate(qce_circ_model* m, void* stream, const void* r, int64_t B, int mode, int n_top, double rho, void* h_est,
+                             double* logp_out, const void* h_true, double* acc) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && !r)) { set_error("qce_circ_estimate: invalid argument"); return QCE_ERR_INVALID; }
+    qce_status st = check_mode(mode, n_top, rho, m->n_comp);
+    if (st) return st;
+    return launch_circ(m, (cudaStream_t)stream, (const double*)r, B, mode, n_top, rho, (double*)h_est, logp_out, (const double*)h_true, acc);
+}
+
 qce_status qce_format_pilots(qce_model* m, void* stream, const void* r, int64_t B) {
     if (!m || !m->params_set || B < 0 || (B > 0 && !r)) { set_error("qce_format_pilots: invalid argument"); return QCE_ERR_INVALID; }
     if (!tc_supported(m, QCE_MODE_ALL) || !m->tc.ready) { set_error("qce_format_pilots: tensor-core path not available for this model"); return QCE_ERR_UNSUPPORTED; }

@@ -65,6 +65,14 @@ struct TcParams {
     bool ready = false;
 };
 
+struct qce_circ_model {
+    int n1, n2, n_ant, n_comp, flags;
+    double* inv_lambda_t = nullptr;   // [N][K]  1 / eigenvalues of C_r,k, transposed for coalesced access
+    double* gain = nullptr;           // [K][N]  b_k c_k / lambda_k
+    double* logc = nullptr;           // [K]
+    bool params_set = false;
+};
+
 struct qce_model {
     int n_obs, n_ant, n_comp, flags;
     // fp64 parameter copies (device)
@@ -80,6 +88,45 @@ struct qce_model {
     void* pipe_r = nullptr;
     int64_t pipe_cap = 0;
 };
+
+#ifdef __CUDACC__
+namespace qce {
+// Per-sample weights from weighted log-probabilities, in place (lp[k] -> w[k]).
+__device__ inline void weights_from_logp(double* lp, int K, int mode, int n_top, double rho, int flags) {
+    double mx = lp[0];
+    int amax = 0;
+    for (int k = 1; k < K; ++k)
+        if (lp[k] > mx) { mx = lp[k]; amax = k; }
+    if (mode == QCE_MODE_TOP1) {
+        // gmm:349 argmax of the weighted log-prob; mofa:359-366 argmax of exp(.) -> 0 when all underflow
+        if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
+        for (int k = 0; k < K; ++k) lp[k] = (k == amax) ? 1.0 : 0.0;
+        return;
+    }
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) sum += exp(lp[k] - mx);
+    const double lse = mx + log(sum);               // scipy.special.logsumexp (gmm:652) / _log_sum (mofa:394-400)
+    for (int k = 0; k < K; ++k) lp[k] = exp(lp[k] - lse);
+    if (mode == QCE_MODE_ALL) return;
+    // descending selection (np.argsort(p)[::-1], gmm:210 / :233); selected entries are marked by the sign bit
+    const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
+    double cum = 0.0;
+    for (int it = 0; it < limit; ++it) {
+        int best = -1;
+        double bv = -1.0;
+        for (int k = 0; k < K; ++k)
+            if (!signbit(lp[k]) && lp[k] > bv) { bv = lp[k]; best = k; }
+        if (best < 0) break;
+        lp[best] = -bv;
+        cum += bv;
+        // searchsorted(cumsum, rho) + 1 (gmm:234): stop after the first prefix with cumsum >= rho
+        if (mode == QCE_MODE_CUMPROB && cum >= rho) break;
+    }
+    for (int k = 0; k < K; ++k) lp[k] = signbit(lp[k]) ? (-lp[k]) / cum : 0.0;
+}
+
+}  // namespace qce
+#endif
 
 namespace qce {
 // qce_quantize.cu
@@ -107,4 +154,7 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
                               const double* noise, double noise_scale, int64_t B, int mode, int n_top, double rho, double* h_est,
                               double* acc);
 bool tc_supported(const qce_model* m, int mode);
+// qce_circ.cu
+qce_status launch_circ(const qce_circ_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
+                       double* h_est, double* logp_out, const double* h_true, double* acc);
 }  // namespace qce

@@ -38,40 +38,6 @@ __device__ __forceinline__ void cfma(double2& acc, const double2 a, const double
     acc.y = fma(a.y, b.x, acc.y);
 }
 
-// Per-sample weights from weighted log-probabilities, in place (lp[k] -> w[k]).
-__device__ void weights_from_logp(double* lp, int K, int mode, int n_top, double rho, int flags) {
-    double mx = lp[0];
-    int amax = 0;
-    for (int k = 1; k < K; ++k)
-        if (lp[k] > mx) { mx = lp[k]; amax = k; }
-    if (mode == QCE_MODE_TOP1) {
-        // gmm:349 argmax of the weighted log-prob; mofa:359-366 argmax of exp(.) -> 0 when all underflow
-        if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
-        for (int k = 0; k < K; ++k) lp[k] = (k == amax) ? 1.0 : 0.0;
-        return;
-    }
-    double sum = 0.0;
-    for (int k = 0; k < K; ++k) sum += exp(lp[k] - mx);
-    const double lse = mx + log(sum);               // scipy.special.logsumexp (gmm:652) / _log_sum (mofa:394-400)
-    for (int k = 0; k < K; ++k) lp[k] = exp(lp[k] - lse);
-    if (mode == QCE_MODE_ALL) return;
-    // descending selection (np.argsort(p)[::-1], gmm:210 / :233); selected entries are marked by the sign bit
-    const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
-    double cum = 0.0;
-    for (int it = 0; it < limit; ++it) {
-        int best = -1;
-        double bv = -1.0;
-        for (int k = 0; k < K; ++k)
-            if (!signbit(lp[k]) && lp[k] > bv) { bv = lp[k]; best = k; }
-        if (best < 0) break;
-        lp[best] = -bv;
-        cum += bv;
-        // searchsorted(cumsum, rho) + 1 (gmm:234): stop after the first prefix with cumsum >= rho
-        if (mode == QCE_MODE_CUMPROB && cum >= rho) break;
-    }
-    for (int k = 0; k < K; ++k) lp[k] = signbit(lp[k]) ? (-lp[k]) / cum : 0.0;
-}
-
 template <int TS>
 __global__ void __launch_bounds__(256) dense_fp64_kernel(Fp64Args a) {
     constexpr int SP = TS / 2;          // sample pairs

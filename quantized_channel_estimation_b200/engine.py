@@ -208,3 +208,53 @@ class DenseModel:
                                                                    _ptr(noise), float(noise_scale), B, mode, n_top, rho, p,
                                                                    _ptr(h_est), _ptr(acc)))
         return (h_est, acc) if want_est else acc
+
+
+class CircModel:
+    """Circulant / block-circulant parameter set on the GPU (qce_circ_model); zero means, A = I."""
+
+    def __init__(self, prep, flags=0):
+        lib = _lib.require_device()
+        self.n_obs = self.n_ant = int(prep['n_ant'])
+        self.n_comp = int(prep['n_comp'])
+        self.handle = C.c_void_p()
+        _lib.check(lib.qce_circ_model_create(int(prep['n1']), int(prep['n2']), self.n_comp, int(flags), C.byref(self.handle)))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        t = {k: prep[k].to(dev).contiguous() for k in ('inv_lambda_t', 'gain', 'logc')}
+        _lib.check(lib.qce_circ_model_set_params(self.handle, _stream(), _ptr(t['inv_lambda_t']), _ptr(t['gain']), _ptr(t['logc'])))
+        torch.cuda.current_stream().synchronize()
+        self.device = dev
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None) and self.handle.value:
+                _lib.load().qce_circ_model_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def estimate(self, r, n_summands_or_proba='all', precision='auto', want_logp=False, h_true=None):
+        mode, n_top, rho = parse_mode(n_summands_or_proba)
+        r = _as_c128_cuda(r, 'y')
+        if r.dim() != 2 or r.shape[1] != self.n_obs:
+            raise ValueError(f'y must be [B, {self.n_obs}]')
+        B = r.shape[0]
+        h_est = torch.empty((B, self.n_ant), dtype=torch.complex128, device=r.device)
+        logp = torch.empty((B, self.n_comp), dtype=torch.float64, device=r.device) if want_logp else None
+        acc = None
+        if h_true is not None:
+            h_true = _as_c128_cuda(h_true, 'h_true')
+            acc = torch.zeros(3, dtype=torch.float64, device=r.device)
+        with torch.cuda.device(r.device):
+            _lib.check(_lib.load().qce_circ_estimate(self.handle, _stream(), _ptr(r), B, mode, n_top, rho, _ptr(h_est), _ptr(logp),
+                                                     _ptr(h_true), _ptr(acc)))
+        out = (h_est,)
+        if want_logp:
+            out += (logp,)
+        if h_true is not None:
+            out += (acc,)
+        return out if len(out) > 1 else h_est
+
+    def estimate_host(self, r, n_summands_or_proba='all', precision='auto'):
+        rt = torch.from_numpy(np.ascontiguousarray(np.asarray(r, dtype=np.complex128))).to(self.device)
+        return self.estimate(rt, n_summands_or_proba).cpu().numpy()

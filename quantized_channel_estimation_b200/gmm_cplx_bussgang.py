@@ -61,6 +61,8 @@ class Gmm_nbit:
         self.params = dict()
         self.F2 = None
         self.precision = 'auto'            # 'auto' | 'tc' | 'fp64' (arithmetic of the estimate kernel)
+        self.blocks = None                 # (n1, n2) when every covariance is F^H diag(c) F with F = F_n1 (x) F_n2
+        self.use_structure = True          # use the DFT-domain kernel when blocks is set, A = I and the means vanish
         self._cache = _PreparedCache()
 
     # ------------------------------------------------------------------ construction helpers
@@ -71,10 +73,16 @@ class Gmm_nbit:
         new.set_parameters(obj.means_cplx, obj.covs_cplx, obj.gm.weights_, zero_mean=obj.params.get('zero_mean', False))
         return new
 
-    def set_parameters(self, means, covs, weights, zero_mean=False):
+    def set_parameters(self, means, covs, weights, zero_mean=False, detect_structure=True):
+        """Install fitted parameters.  ``detect_structure``: test whether the covariances are (block-)circulant
+        (the reference fits those types in the DFT domain and then densifies them, gmm:104-136) and, if so, remember
+        the DFT-domain eigenvalues so that ``estimate_from_y`` can use the structured kernel."""
         self.means_cplx = np.array(means, dtype=complex)
         self.covs_cplx = np.array(covs, dtype=complex)
         self.gm.weights_ = np.array(weights, dtype=float)
+        self.blocks, self.fft_covs = (None, None)
+        if detect_structure and self.covs_cplx.shape[-1] <= 1024:
+            self.blocks, self.fft_covs = precompute.detect_blocks(self.covs_cplx)
         self.gm.n_components = self.means_cplx.shape[0]
         self.gm.covariance_type = 'full'       # every type is dense after fit (gmm:110-153)
         self.params['zero_mean'] = bool(zero_mean)
@@ -91,7 +99,46 @@ class Gmm_nbit:
                                   'Gmm_nbit.from_reference(obj) or set_parameters(means, covs, weights)')
 
     # ------------------------------------------------------------------ inference
+    def set_circulant_parameters(self, c, weights, blocks):
+        """Zero-mean (block-)circulant mixture from its DFT-domain eigenvalues ``c [K, N]``: ``C_k = F^H diag(c_k) F``,
+        ``F = F_n1 (x) F_n2``, ``blocks = (n1, n2)`` (``(1, N)``: circulant).  The dense covariances are materialised too
+        (reference behaviour) unless N > 1024."""
+        c = np.asarray(c, dtype=float)
+        K, N = c.shape
+        assert blocks[0] * blocks[1] == N
+        self.means_cplx = np.zeros((K, N), dtype=complex)
+        if N <= 1024:
+            F = precompute.dft_matrix(*blocks)
+            self.covs_cplx = np.einsum('ji,kj,jl->kil', F.conj(), c, F)
+        else:
+            self.covs_cplx = None
+        self.gm.weights_ = np.array(weights, dtype=float)
+        self.gm.n_components = K
+        self.gm.covariance_type = 'full'
+        self.params['zero_mean'] = True
+        self.blocks, self.fft_covs = tuple(blocks), c.copy()
+        self._cache.clear()
+        return self
+
+    def _structured(self, A):
+        if not (self.use_structure and self.blocks is not None and self.fft_covs is not None):
+            return False
+        A = np.asarray(A)
+        N = self.fft_covs.shape[1]
+        return A.shape == (N, N) and np.array_equal(A, np.eye(N)) and not np.any(self.means_cplx)
+
     def _prepared(self, A, snr_dB, n_bits, quantizer_type, quantizer):
+        if self._structured(A):
+            nb = 'inf' if (n_bits == 'inf' or n_bits == np.inf) else int(n_bits)
+            tables = _table_key(quantizer) if (nb != 1 and nb != 'inf' and quantizer_type == 'lloyd') else None
+            key = ('circ', float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, self.blocks,
+                   id(self.fft_covs), id(self.gm.weights_))
+
+            def make_circ():
+                prep = precompute.prepare_circulant(self.fft_covs, self.gm.weights_, self.blocks, snr_dB,
+                                                    np.inf if nb == 'inf' else nb, quantizer_type, quantizer)
+                return engine.CircModel(prep, flags=0)
+            return self._cache.get(key, make_circ)
         if self.means_cplx is None or self.covs_cplx is None or self.gm.weights_ is None:
             raise RuntimeError('Gmm_nbit: model is not fitted (means_cplx / covs_cplx / gm.weights_ missing)')
         if self.gm.covariance_type != 'full':

@@ -103,3 +103,60 @@ def prepare(means, covs, weights, A, snr_dB, n_bits=1, quantizer_type='uniform',
     return dict(Linv=Linv.contiguous(), W=W.contiguous(), zoff=zoff.contiguous(), hoff=hoff.contiguous(),
                 logc=logc.contiguous(), data_scale=data_scale_for(snr_dB, n_bits, quantizer_type),
                 m_r=m_r, C_r=Cr, b=b, n_obs=No, n_ant=N, n_comp=K)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# circulant / block-circulant covariances: everything is diagonal in the (2-D) DFT basis
+# --------------------------------------------------------------------------------------------------------------
+
+def dft_matrix(n1, n2):
+    """Unitary ``F = F_n1 (x) F_n2`` (reference gmm:105, :123-125)."""
+    F1 = np.fft.fft(np.eye(n1)) / np.sqrt(n1)
+    F2 = np.fft.fft(np.eye(n2)) / np.sqrt(n2)
+    return np.kron(F1, F2)
+
+
+def detect_blocks(covs, tol=1e-9):
+    """Return ``(n1, n2), c [K,N]`` if every ``covs[k] = F^H diag(c_k) F`` for some factorisation ``N = n1 n2``
+    (plain circulant = ``(1, N)`` is tried first), else ``(None, None)``."""
+    covs = np.asarray(covs)
+    N = covs.shape[-1]
+    scale = np.linalg.norm(covs)
+    cands = [(1, N)] + [(a, N // a) for a in range(2, N) if N % a == 0]
+    for n1, n2 in cands:
+        F = dft_matrix(n1, n2)
+        D = F @ covs @ F.conj().T
+        off = D - np.stack([np.diag(np.diag(d)) for d in D])
+        if np.linalg.norm(off) <= tol * scale:
+            return (n1, n2), np.real(np.diagonal(D, axis1=1, axis2=2)).copy()
+    return None, None
+
+
+def prepare_circulant(c, weights, blocks, snr_dB, n_bits=1, quantizer_type='uniform', quantizer=None, device=None):
+    """DFT-domain parameter blocks for ``C_h,k = F^H diag(c_k) F``, ``A = I``, zero means (SURVEY.md section 2.1,
+    "structured covariances"): ``inv_lambda_t [N,K]``, ``gain [K,N]``, ``logc [K]`` as float64 torch tensors."""
+    if device is None:
+        device = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
+    n1, n2 = blocks
+    c = np.asarray(c, dtype=float)
+    K, N = c.shape
+    sigma2 = 10 ** (-snr_dB / 10)
+    cy = c + sigma2                                           # eigenvalues of C_y
+    d = cy.mean(axis=1)                                       # its constant diagonal
+    b = bussgang_gain(d[:, None], snr_dB, n_bits, quantizer_type, quantizer)[:, 0]     # scalar gain per component
+    if n_bits == 1:
+        col0 = np.fft.ifft2(cy.reshape(K, n1, n2), axes=(1, 2))          # first column of C_y (times 1: F e_0 = 1/sqrt(N))
+        rho = col0 / d[:, None, None]
+        cr0 = 2 / np.pi * (np.arcsin(np.clip(rho.real, -1.0, 1.0)) + 1j * np.arcsin(np.clip(rho.imag, -1.0, 1.0)))
+        lam = np.real(np.fft.fft2(cr0, axes=(1, 2))).reshape(K, N)       # eigenvalues of the (block-)circulant C_r
+    elif _is_inf(n_bits):
+        lam = cy
+    else:
+        beta = np.clip(b, 0, 1)
+        lam = beta[:, None] ** 2 * cy + (1 - beta[:, None] ** 2) * d[:, None]
+    if not np.all(lam > 0):
+        raise ValueError(NOT_PD_MSG)
+    gain = b[:, None] * c / lam
+    logc = np.log(np.asarray(weights, dtype=float)) - N * math.log(math.pi) - np.log(lam).sum(axis=1)
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=device)
+    return dict(inv_lambda_t=t((1 / lam).T), gain=t(gain), logc=t(logc), n1=n1, n2=n2, n_ant=N, n_comp=K)

@@ -230,3 +230,44 @@ def test_host_and_device_entry_points_agree(qce):
     b = m.estimate_from_y(torch.from_numpy(r).cuda(), snr, N, n_summands_or_proba='all').cpu().numpy()
     assert np.array_equal(a, b)
     assert m.estimate_from_y(np.zeros((0, N), complex), snr, N, n_summands_or_proba='all').shape == (0, N)
+
+
+# ----------------------------------------------------------------------------- circulant / block-circulant kernel
+
+@pytest.mark.parametrize('n1,n2,K,nb,qt,tol', [
+    (1, 64, 8, 1, 'uniform', 1e-7),          # plain circulant, 1 bit (arcsine-law diagonal: the reference's C_r diag is 1 - O(1e-8))
+    (8, 8, 16, 1, 'uniform', 1e-7),
+    (16, 16, 12, 3, 'lloyd', 1e-10),         # config 3 shape: 256 antennas, 16x16 blocks, 3-bit Lloyd-Max
+    (4, 8, 6, 2, 'uniform', 1e-10),
+    (3, 5, 4, 2, 'uniform', 1e-10),          # odd sizes
+])
+def test_circulant_kernel_vs_dense_oracle(qce, n1, n2, K, nb, qt, tol):
+    """The DFT-domain kernel (new algorithm) against the oracle's DENSE path, which is what the reference computes
+    for circulant / block-circulant models after it densifies them (gmm:104-136)."""
+    N, B, snr = n1 * n2, 150, 8
+    c, covs, w, F = orc.circulant_gmm(K, n1, n2, seed=n1 + n2)
+    h, noise, _ = orc.sample_gmm_channels(np.zeros((K, N), complex), covs, w, B, seed=5)
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
+    m.set_parameters(np.zeros((K, N)), covs, w, zero_mean=True)           # structure is detected from the dense covariances
+    assert m.blocks is not None and m.blocks[0] * m.blocks[1] == N
+    np.testing.assert_allclose(m.fft_covs, c, rtol=1e-8, atol=1e-12)
+    from quantized_channel_estimation_b200.engine import CircModel
+    assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), CircModel)
+    for mode in ('all', 1, 3, 0.9):
+        ref = orc.gmm_estimate_from_y(np.zeros((K, N)), covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
+                                      quantizer=qz)
+        est = m.estimate_from_y(r, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz)
+        if mode == 'all' or tol < 1e-8:
+            assert relerr(est, ref) < tol, (mode, relerr(est, ref))
+        else:   # 1-bit: near-ties of the hard selections may flip under the 1e-8 arcsine-diagonal difference
+            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert np.mean(per > 1e-6) < 0.02
+    # and the structured path agrees with our own dense kernels
+    m.use_structure = False
+    m._cache.clear()
+    dense = m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+    m.use_structure = True
+    m._cache.clear()
+    assert relerr(m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz), dense) < max(tol, 1e-5)
