@@ -263,11 +263,15 @@ def main():
     torch.cuda.synchronize()
     k_ms = ev0.elapsed_time(ev1) / reps
     achieved = FLOP_PER_EST * B / (k_ms * 1e-3) / 1e12
+    # DRAM traffic of one 2^20-pilot launch of the dominant kernel from the committed ncu --set full capture
+    # (profiles/r01_tc_v5_ncu_summary.txt: dram read 280.5 MB + write 1108.9 MB; algorithmic: 268 MB tiles + 1074 MB estimates)
+    traffic = 1.389e9 * (B / float(1 << 20)) if tc_used else None
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['burst'], 'unit': 'TFLOP/s', 'frac': achieved / pk['burst'],
-                'traffic': None, 'kernel': 'dense_tc_kernel' if tc_used else 'dense_fp64_kernel', 'kernel_ms': k_ms,
+                'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'kernel': 'dense_tc_kernel' if tc_used else 'dense_fp64_kernel', 'kernel_ms': k_ms,
                 'peak_source': f"{pk['src']} bf16 burst (kernel timed alone)",
                 'algorithmic_flop_per_estimate': FLOP_PER_EST,
-                'note': ('FP16 hi/lo split: 2 tensor passes per algorithmic flop' if tc_used else
+                'tensor_passes': 2 if tc_used else None,
+                'note': ('FP16 hi/lo split: 2 tensor passes per algorithmic flop; cta_group::2 MMAs' if tc_used else
                          'complex128 SIMT kernel: bounded by the FP64 pipe (~40 TFLOP/s), not the tensor pipe')}
     del r, out
 
