@@ -63,6 +63,7 @@ enum {
 typedef struct qce_model qce_model;
 typedef struct qce_quantizer qce_quantizer;
 typedef struct qce_circ_model qce_circ_model;
+typedef struct qce_mfa_model qce_mfa_model;
 
 int qce_abi_version(void);
 const char* qce_last_error_string(void);
@@ -155,6 +156,21 @@ qce_status qce_circ_model_set_params(qce_circ_model* m, void* stream, const doub
                                      const double* logc_dev);
 qce_status qce_circ_estimate(qce_circ_model* m, void* stream, const void* r_dev, int64_t B, int mode, int n_top, double rho,
                              void* h_est_dev, double* logp_out_dev, const void* h_true_dev, double* acc_dev);
+
+/* ---- mixture of factor analysers in Woodbury form (A = I, n_bits > 1 or infinite resolution): C_r,k = U U^H + Delta_k is
+ * never formed (the reference builds it densely and pinvh's it, mofa:199-207).  Host-precomputed per (snr, bits), all
+ * device arrays: inv_delta [K][N] f64 = 1/Delta; evec [K][N] f64 = psi b / Delta; D c128 [K][2M][N] (rows 0..M-1: V1,
+ * rows M..2M-1: T = L_S^-1 U^H Delta^-1); Y c128 [K][N][2M] = [Lambda | -(e .* U) L_S^-H]; m_r c128 [K][N];
+ * mu c128 [K][N]; logc [K] = ln amps_k - N ln(pi) - sum ln Delta - ln det S.  Per pilot:
+ *   x = r - m_r,k;  l_k = logc_k - (sum_i |x_i|^2 inv_delta_i - |T x|^2);  h_k = mu_k + e .* x + Y [V1 x; T x].
+ * qce_mfa_estimate has the semantics of qce_estimate (complex128 arithmetic, all four modes, flags as qce_model_create). */
+qce_status qce_mfa_model_create(int n_ant, int latent_dim, int n_comp, int flags, qce_mfa_model** out);
+void qce_mfa_model_destroy(qce_mfa_model* m);
+qce_status qce_mfa_model_set_params(qce_mfa_model* m, void* stream, const double* inv_delta_dev, const double* evec_dev,
+                                    const double* D_dev, const double* Y_dev, const double* m_r_dev, const double* mu_dev,
+                                    const double* logc_dev);
+qce_status qce_mfa_estimate(qce_mfa_model* m, void* stream, const void* r_dev, int64_t B, int mode, int n_top, double rho,
+                            void* h_est_dev, double* logp_out_dev, const void* h_true_dev, double* acc_dev);
 
 /* Host-buffer form of qce_estimate: r_host c128 [B][n_obs] -> h_est_host c128 [B][n_ant].  Copies are
  * chunked through pinned staging buffers owned by the model and overlapped with the kernels on the

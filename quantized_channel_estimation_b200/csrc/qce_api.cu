@@ -292,6 +292,55 @@ qce_status qce_circ_estimate(qce_circ_model* m, void* stream, const void* r, int
     return launch_circ(m, (cudaStream_t)stream, (const double*)r, B, mode, n_top, rho, (double*)h_est, logp_out, (const double*)h_true, acc);
 }
 
+qce_status qce_mfa_model_create(int n_ant, int latent, int n_comp, int flags, qce_mfa_model** out) {
+    if (!out || n_ant < 1 || latent < 1 || n_comp < 1) { set_error("qce_mfa_model_create: invalid shape"); return QCE_ERR_INVALID; }
+    qce_status st = require_device();
+    if (st) return st;
+    qce_mfa_model* m = new qce_mfa_model();
+    m->n_ant = n_ant; m->latent = latent; m->n_comp = n_comp; m->flags = flags;
+    const size_t N = n_ant, M2 = 2 * (size_t)latent, K = n_comp;
+    cudaError_t e = cudaMalloc(&m->inv_delta, K * N * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&m->evec, K * N * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&m->D, K * M2 * N * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->Y, K * N * M2 * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->m_r, K * N * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->mu, K * N * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->logc, K * 8);
+    if (e != cudaSuccess) { set_error("qce_mfa_model_create: %s", cudaGetErrorString(e)); qce_mfa_model_destroy(m); return QCE_ERR_CUDA; }
+    *out = m;
+    return QCE_OK;
+}
+
+void qce_mfa_model_destroy(qce_mfa_model* m) {
+    if (!m) return;
+    cudaFree(m->inv_delta); cudaFree(m->evec); cudaFree(m->D); cudaFree(m->Y); cudaFree(m->m_r); cudaFree(m->mu); cudaFree(m->logc);
+    delete m;
+}
+
+qce_status qce_mfa_model_set_params(qce_mfa_model* m, void* stream, const double* inv_delta, const double* evec, const double* D,
+                                    const double* Y, const double* m_r, const double* mu, const double* logc) {
+    if (!m || !inv_delta || !evec || !D || !Y || !m_r || !mu || !logc) { set_error("qce_mfa_model_set_params: invalid argument"); return QCE_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = m->n_ant, M2 = 2 * (size_t)m->latent, K = m->n_comp;
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->inv_delta, inv_delta, K * N * 8, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->evec, evec, K * N * 8, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->D, D, K * M2 * N * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->Y, Y, K * N * M2 * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->m_r, m_r, K * N * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->mu, mu, K * N * 16, cudaMemcpyDeviceToDevice, s));
+    QCE_CUDA_TRY(cudaMemcpyAsync(m->logc, logc, K * 8, cudaMemcpyDeviceToDevice, s));
+    m->params_set = true;
+    return QCE_OK;
+}
+
+qce_status qce_mfa_estimate(qce_mfa_model* m, void* stream, const void* r, int64_t B, int mode, int n_top, double rho, void* h_est,
+                            double* logp_out, const void* h_true, double* acc) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && !r)) { set_error("qce_mfa_estimate: invalid argument"); return QCE_ERR_INVALID; }
+    qce_status st = check_mode(mode, n_top, rho, m->n_comp);
+    if (st) return st;
+    return launch_mfa(m, (cudaStream_t)stream, (const double*)r, B, mode, n_top, rho, (double*)h_est, logp_out, (const double*)h_true, acc);
+}
+
 qce_status qce_format_pilots(qce_model* m, void* stream, const void* r, int64_t B) {
     if (!m || !m->params_set || B < 0 || (B > 0 && !r)) { set_error("qce_format_pilots: invalid argument"); return QCE_ERR_INVALID; }
     if (!tc_supported(m, QCE_MODE_ALL) || !m->tc.ready) { set_error("qce_format_pilots: tensor-core path not available for this model"); return QCE_ERR_UNSUPPORTED; }

@@ -73,6 +73,18 @@ struct qce_circ_model {
     bool params_set = false;
 };
 
+struct qce_mfa_model {
+    int n_ant, latent, n_comp, flags;
+    double* inv_delta = nullptr;      // [K][N]
+    double* evec = nullptr;           // [K][N]
+    double* D = nullptr;              // c128 [K][2M][N]
+    double* Y = nullptr;              // c128 [K][N][2M]
+    double* m_r = nullptr;            // c128 [K][N]
+    double* mu = nullptr;             // c128 [K][N]
+    double* logc = nullptr;           // [K]
+    bool params_set = false;
+};
+
 struct qce_model {
     int n_obs, n_ant, n_comp, flags;
     // fp64 parameter copies (device)
@@ -154,6 +166,9 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
                               const double* noise, double noise_scale, int64_t B, int mode, int n_top, double rho, double* h_est,
                               double* acc);
 bool tc_supported(const qce_model* m, int mode);
+// qce_mfa.cu
+qce_status launch_mfa(const qce_mfa_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
+                      double* h_est, double* logp_out, const double* h_true, double* acc);
 // qce_circ.cu
 qce_status launch_circ(const qce_circ_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
                        double* h_est, double* logp_out, const double* h_true, double* acc);

@@ -246,8 +246,8 @@ class CircModel:
             h_true = _as_c128_cuda(h_true, 'h_true')
             acc = torch.zeros(3, dtype=torch.float64, device=r.device)
         with torch.cuda.device(r.device):
-            _lib.check(_lib.load().qce_circ_estimate(self.handle, _stream(), _ptr(r), B, mode, n_top, rho, _ptr(h_est), _ptr(logp),
-                                                     _ptr(h_true), _ptr(acc)))
+            _lib.check(self._estimate_fn()(self.handle, _stream(), _ptr(r), B, mode, n_top, rho, _ptr(h_est), _ptr(logp),
+                                           _ptr(h_true), _ptr(acc)))
         out = (h_est,)
         if want_logp:
             out += (logp,)
@@ -255,6 +255,37 @@ class CircModel:
             out += (acc,)
         return out if len(out) > 1 else h_est
 
+    def _estimate_fn(self):
+        return _lib.load().qce_circ_estimate
+
     def estimate_host(self, r, n_summands_or_proba='all', precision='auto'):
         rt = torch.from_numpy(np.ascontiguousarray(np.asarray(r, dtype=np.complex128))).to(self.device)
         return self.estimate(rt, n_summands_or_proba).cpu().numpy()
+
+
+class MfaModel(CircModel):
+    """Woodbury-form MFA parameter set on the GPU (qce_mfa_model); A = I, n_bits > 1 or infinite resolution."""
+
+    def __init__(self, prep, flags=0):          # noqa: D107  (does not call CircModel.__init__: different handle type)
+        lib = _lib.require_device()
+        self.n_obs = self.n_ant = int(prep['n_ant'])
+        self.n_comp = int(prep['n_comp'])
+        self.handle = C.c_void_p()
+        _lib.check(lib.qce_mfa_model_create(self.n_ant, int(prep['latent']), self.n_comp, int(flags), C.byref(self.handle)))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        names = ('inv_delta', 'evec', 'D', 'Y', 'm_r', 'mu', 'logc')
+        t = [prep[k].to(dev).contiguous() for k in names]
+        _lib.check(lib.qce_mfa_model_set_params(self.handle, _stream(), *[_ptr(x) for x in t]))
+        torch.cuda.current_stream().synchronize()
+        self.device = dev
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None) and self.handle.value:
+                _lib.load().qce_mfa_model_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def _estimate_fn(self):
+        return _lib.load().qce_mfa_estimate

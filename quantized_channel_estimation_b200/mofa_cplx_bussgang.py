@@ -32,7 +32,9 @@ class Mofa:
         self.amps = None
         self.zero_mean = False
         self.precision = 'auto'
+        self.use_structure = True          # Woodbury (low-rank + diagonal) kernel when A = I and n_bits != 1
         self._cache = _PreparedCache()
+        self._covs_are_low_rank = False
         self._last = None                  # handle prepared by the last estimate_from_y (for predict_proba)
 
     @classmethod
@@ -50,7 +52,10 @@ class Mofa:
         self.M = self.lambdas.shape[-1]
         if covs is None:          # C_k = Lambda Lambda^H + diag(psi)   (reference :313-319)
             covs = self.lambdas @ np.transpose(self.lambdas.conj(), [0, 2, 1]) + np.stack([np.diag(p) for p in self.psis])
+        lr = self.lambdas @ np.transpose(self.lambdas.conj(), [0, 2, 1]) + np.stack([np.diag(p) for p in self.psis])
         self.covs = np.array(covs, dtype=complex)
+        # the Woodbury kernel is only valid if the covariances really are Lambda Lambda^H + diag(psi)
+        self._covs_are_low_rank = bool(np.allclose(self.covs, lr, rtol=1e-10, atol=1e-12))
         self._cache.clear()
         return self
 
@@ -67,6 +72,18 @@ class Mofa:
         A = np.asarray(A)
         nb = 'inf' if (n_bits == 'inf' or n_bits == np.inf) else int(n_bits)
         tables = _table_key(quantizer) if (nb != 1 and nb != 'inf' and quantizer_type == 'lloyd') else None
+        woodbury = (self.use_structure and nb != 1 and self.lambdas is not None and self.psis is not None and
+                    A.shape == (self.D, self.D) and np.array_equal(A, np.eye(self.D)) and self._covs_are_low_rank)
+        if woodbury:
+            key = ('woodbury', float(snr_dB), nb, quantizer_type if nb != 'inf' else None, tables, id(self.means), id(self.lambdas),
+                   id(self.psis), id(self.amps))
+
+            def make_w():
+                prep = precompute.prepare_mfa_woodbury(self.means, self.lambdas, self.psis, self.amps, snr_dB,
+                                                       np.inf if nb == 'inf' else nb, quantizer_type, quantizer)
+                return engine.MfaModel(prep, flags=_lib.FLAG_TOP1_EXP_ARGMAX)
+            self._last = self._cache.get(key, make_w)
+            return self._last
         key = (float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, A.shape, A.tobytes(),
                id(self.means), id(self.covs), id(self.amps))
 

@@ -160,3 +160,53 @@ def prepare_circulant(c, weights, blocks, snr_dB, n_bits=1, quantizer_type='unif
     logc = np.log(np.asarray(weights, dtype=float)) - N * math.log(math.pi) - np.log(lam).sum(axis=1)
     t = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=device)
     return dict(inv_lambda_t=t((1 / lam).T), gain=t(gain), logc=t(logc), n1=n1, n2=n2, n_ant=N, n_comp=K)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# mixture of factor analysers: Woodbury (low-rank + diagonal) form, A = I, n_bits > 1 (or infinite resolution)
+# --------------------------------------------------------------------------------------------------------------
+
+def prepare_mfa_woodbury(means, lambdas, psis, amps, snr_dB, n_bits, quantizer_type='uniform', quantizer=None, device=None):
+    """Parameter blocks of ``qce_mfa_model_set_params`` (include/qce_b200.h).  ``C_r,k = beta^2 Lambda Lambda^H + Delta_k``
+    (reference mofa:199-202 written out for ``C_h = Lambda Lambda^H + diag(psi)``) is never formed."""
+    if n_bits == 1:
+        raise ValueError('the arcsine law destroys the low-rank structure: 1-bit MFA uses the dense path')
+    if device is None:
+        device = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
+    cd, fd = torch.complex128, torch.float64
+    mu = torch.as_tensor(np.asarray(means), dtype=cd, device=device)
+    Lam = torch.as_tensor(np.asarray(lambdas), dtype=cd, device=device)               # [K,N,M]
+    psi = torch.as_tensor(np.asarray(psis), dtype=fd, device=device)                  # [K,N]
+    w = torch.as_tensor(np.asarray(amps), dtype=fd, device=device)
+    K, N, M = Lam.shape
+    sigma2 = 10 ** (-snr_dB / 10)
+    d = (Lam.real ** 2 + Lam.imag ** 2).sum(-1) + psi + sigma2                        # diag C_y            (mofa:167-169)
+    b = torch.as_tensor(bussgang_gain(d.cpu().numpy(), snr_dB, n_bits, quantizer_type, quantizer), dtype=fd, device=device)
+    m_r = b * mu                                                                      #                     (mofa:183-184)
+    if _is_inf(n_bits):
+        beta = torch.ones(K, dtype=fd, device=device)
+    else:
+        beta = b.mean(dim=1).clamp(0, 1)                                              #                     (mofa:199-202)
+    b2 = (beta ** 2)[:, None]
+    Delta = b2 * (psi + sigma2) + (1 - b2) * d                                        # diagonal part of C_r
+    if not bool((Delta > 0).all()):
+        raise ValueError(NOT_PD_MSG)
+    invD = 1 / Delta
+    U = beta[:, None, None] * Lam                                                     # C_r = U U^H + Delta
+    UhD = U.conj().transpose(1, 2) * invD[:, None, :]                                 # U^H Delta^-1       [K,M,N]
+    S = torch.eye(M, dtype=cd, device=device) + UhD @ U                               # [K,M,M]
+    LS, info = torch.linalg.cholesky_ex(S)
+    if int(info.max()) != 0:
+        raise ValueError(NOT_PD_MSG)
+    T = torch.linalg.solve_triangular(LS, UhD, upper=False)                           # L_S^-1 U^H Delta^-1
+    Q = torch.linalg.solve_triangular(LS.conj().transpose(1, 2), T, upper=True)       # S^-1 U^H Delta^-1
+    P = Lam.conj().transpose(1, 2) * (b * invD)[:, None, :]                           # Lambda^H B Delta^-1 [K,M,N]
+    V1 = P - (P @ U) @ Q
+    e = psi * b * invD                                                                # diagonal part of W
+    LSinvH = torch.linalg.solve_triangular(LS, torch.eye(M, dtype=cd, device=device).expand(K, M, M), upper=False).conj().transpose(1, 2)
+    Y = torch.cat([Lam, -(e[:, :, None] * U) @ LSinvH], dim=2)                        # [K,N,2M]
+    D = torch.cat([V1, T], dim=1)                                                     # [K,2M,N]
+    logdet = torch.log(Delta).sum(1) + 2 * torch.log(torch.diagonal(LS, dim1=1, dim2=2).real).sum(1)
+    logc = torch.log(w) - N * math.log(math.pi) - logdet
+    return dict(inv_delta=invD.contiguous(), evec=e.contiguous(), D=D.contiguous(), Y=Y.contiguous(), m_r=m_r.contiguous(),
+                mu=mu.contiguous(), logc=logc.contiguous(), n_ant=N, latent=M, n_comp=K)

@@ -271,3 +271,32 @@ def test_circulant_kernel_vs_dense_oracle(qce, n1, n2, K, nb, qt, tol):
     m.use_structure = True
     m._cache.clear()
     assert relerr(m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz), dense) < max(tol, 1e-5)
+
+
+# ----------------------------------------------------------------------------- MFA Woodbury kernel
+
+@pytest.mark.parametrize('K,N,M,nb,qt,ms', [
+    (6, 48, 8, 2, 'uniform', 0.3),
+    (8, 64, 16, 3, 'lloyd', 0.0),
+    (4, 128, 16, 2, 'uniform', 0.1),          # config 4 shape: 128 antennas, latent rank 16, 2-bit uniform
+    (3, 20, 3, np.inf, 'uniform', 0.2),
+])
+def test_mfa_woodbury_vs_dense_oracle(qce, K, N, M, nb, qt, ms):
+    """Low-rank + diagonal kernel against the oracle's dense MFA path (what the reference computes, mofa:162-216)."""
+    from quantized_channel_estimation_b200.engine import MfaModel, DenseModel
+    B, snr = 120, 9
+    means, lam, psi, amps = orc.random_mfa(K, N, M, seed=K + N, mean_scale=ms)
+    covs = orc.mofa_covs(lam, psi)
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    h, noise, _ = orc.sample_gmm_channels(means, covs, amps, B, seed=4)
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    m = qce.Mofa(K, M, verbose=False).set_parameters(means, lam, psi, amps)
+    assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), MfaModel)
+    for mode in ('all', 1, 2, 0.9):
+        ref, aux = orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
+                                            quantizer=qz, return_aux=True)
+        est = m.estimate_from_y(r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz)
+        assert relerr(est, ref) < 1e-10, (mode, relerr(est, ref))
+    np.testing.assert_allclose(m.predict_proba(r), aux['proba'], rtol=1e-8, atol=1e-300)
+    # 1 bit destroys the low-rank structure: dense path
+    assert isinstance(m._prepared(np.eye(N), snr, 1, 'uniform', (None, None, None)), DenseModel)

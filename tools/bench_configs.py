@@ -71,7 +71,7 @@ def main():
     mf = qce.Mofa(64, 16, verbose=False).set_parameters(means, lambdas, psis, amps)
     r = pilots(1 << 15, 128, 2, qz)
     ms = timeit(lambda: mf.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=2, quantizer_type='uniform', quantizer=qz))
-    out.append(dict(config='C4 MFA N=128 K=64 M=16 2-bit uniform', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='dense fp64'))
+    out.append(dict(config='C4 MFA N=128 K=64 M=16 2-bit uniform', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='woodbury fp64'))
     for o in out:
         print(json.dumps(o), flush=True)
 
