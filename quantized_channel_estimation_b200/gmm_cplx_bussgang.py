@@ -90,13 +90,14 @@ class Gmm_nbit:
         return self
 
     def fit(self, h, blocks=None, zero_mean=False):
-        """Fit the complex GMM with EM (reference :96-163).  Training is outside the hot path this package
-        rebuilds: fit with the reference and transplant the result with
-        :meth:`from_reference` / :meth:`set_parameters`."""
+        """Fit the complex GMM with EM (reference :96-163); see ``em.py``.  'full', 'circulant', 'block-circulant'
+        (``blocks=(n1, n2)``); the Toeplitz types raise ``NotImplementedError``."""
         if self.gm.covariance_type not in _SUPPORTED_TYPES:
             raise NotImplementedError(f'Fitting for covariance_type = {self.gm.covariance_type} is not implemented.')
-        raise NotImplementedError('Gmm_nbit.fit is not part of the B200 inference path yet: fit with the reference and use '
-                                  'Gmm_nbit.from_reference(obj) or set_parameters(means, covs, weights)')
+        from . import em
+        em.fit_gmm(self, h, blocks=blocks, zero_mean=zero_mean)
+        self._cache.clear()
+        return self
 
     # ------------------------------------------------------------------ inference
     def set_circulant_parameters(self, c, weights, blocks):

@@ -60,11 +60,11 @@ class Mofa:
         return self
 
     def fit(self, data, zero_mean=False):
-        """EM for the mixture of factor analysers (reference :94-113, :219-339).  Training is outside the hot path
-        this package rebuilds: fit with the reference and transplant with
-        :meth:`from_reference` / :meth:`set_parameters`."""
-        raise NotImplementedError('Mofa.fit is not part of the B200 inference path yet: fit with the reference and use '
-                                  'Mofa.from_reference(obj) or set_parameters(means, lambdas, psis, amps)')
+        """EM for the mixture of factor analysers (reference :94-113, :219-339); see ``em.py``."""
+        from . import em
+        em.fit_mofa(self, data, zero_mean=zero_mean)
+        self._cache.clear()
+        return self
 
     def _prepared(self, A, snr_dB, n_bits, quantizer_type, quantizer):
         if self.means is None or self.covs is None or self.amps is None:

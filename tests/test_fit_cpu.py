@@ -1,0 +1,63 @@
+"""fit(): our EM (em.py) must reach the likelihood level the reference's EM reaches on the same seeded data
+(tests/golden/fit.npz, produced by running the shimmed reference fit -- tests/golden/make_golden_fit.py).  EM depends on
+the k-means / random initialisation, so the comparison is statistical: mean log-likelihood within 0.02 nat per sample."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from fit_common import avg_loglik, make_data
+import quantized_channel_estimation_b200 as qce
+
+TOL = 0.02
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return load_golden('fit')
+
+
+@pytest.mark.parametrize('tag,ctype,blocks,zm', [('full_zm', 'full', None, True), ('full_mean', 'full', None, False),
+                                                 ('circ', 'circulant', None, True), ('bccb', 'block-circulant', (2, 4), True)])
+def test_gmm_fit_reaches_reference_likelihood(gold, tag, ctype, blocks, zm):
+    h, true = make_data(tag)
+    g = qce.Gmm_nbit(n_components=3, covariance_type=ctype, random_state=0, max_iter=200, tol=1e-5, n_init=2)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        g.fit(h, blocks=blocks, zero_mean=zm)
+    ll = avg_loglik(h, g.gm.weights_, g.means_cplx, g.covs_cplx)
+    assert ll > float(gold[f'{tag}_ref_ll']) - TOL, (ll, float(gold[f'{tag}_ref_ll']))
+    assert ll > float(gold[f'{tag}_true_ll']) - TOL
+    assert g.gm.covariance_type == 'full' and g.covs_cplx.shape == (3, h.shape[1], h.shape[1])      # densified like the reference
+    assert abs(g.gm.weights_.sum() - 1) < 1e-9
+    if zm:
+        assert not np.any(g.means_cplx)
+    if ctype != 'full':
+        assert g.blocks == ((1, 8) if ctype == 'circulant' else (2, 4)) and g.fft_covs.shape == (3, 8)
+        # the dense covariances are exactly F^H diag(c) F
+        from quantized_channel_estimation_b200 import precompute
+        b, c = precompute.detect_blocks(g.covs_cplx)
+        assert b is not None
+        np.testing.assert_allclose(c, g.fft_covs, rtol=1e-9, atol=1e-12)
+
+
+def test_mofa_fit_reaches_reference_likelihood(gold):
+    h, true = make_data('mfa')
+    m = qce.Mofa(3, 2, verbose=False, maxiter=300)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m.fit(h, zero_mean=False)
+    ll = avg_loglik(h, m.amps, m.means, m.covs)
+    assert ll > float(gold['mfa_ref_ll']) - 0.05, (ll, float(gold['mfa_ref_ll']))
+    assert m.lambdas.shape == (3, 8, 2) and m.psis.shape == (3, 8) and m._covs_are_low_rank
+    np.testing.assert_allclose(m.inv_covs @ m.covs, np.stack([np.eye(8)] * 3), atol=1e-8)
+
+
+def test_toeplitz_fit_not_implemented():
+    g = qce.Gmm_nbit(n_components=2, covariance_type='toeplitz')
+    with pytest.raises(NotImplementedError):
+        g.fit(np.ones((10, 4), complex))
+    g = qce.Gmm_nbit(n_components=2, covariance_type='banded')
+    with pytest.raises(NotImplementedError):
+        g.fit(np.ones((10, 4), complex))

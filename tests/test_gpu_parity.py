@@ -300,3 +300,24 @@ def test_mfa_woodbury_vs_dense_oracle(qce, K, N, M, nb, qt, ms):
     np.testing.assert_allclose(m.predict_proba(r), aux['proba'], rtol=1e-8, atol=1e-300)
     # 1 bit destroys the low-rank structure: dense path
     assert isinstance(m._prepared(np.eye(N), snr, 1, 'uniform', (None, None, None)), DenseModel)
+
+
+# ----------------------------------------------------------------------------- fit -> estimate end to end
+
+def test_fit_then_estimate_matches_true_model_nmse(qce):
+    """EM on the GPU, then the hot path: the fitted model's NMSE is within 0.1 dB of the data-generating model's."""
+    import warnings
+    K, N, snr = 4, 16, 10
+    means, covs, w = orc.random_psd_gmm(K, N, seed=5)
+    htrain, _, _ = orc.sample_gmm_channels(means, covs, w, 20000, seed=6)
+    hval, noise, _ = orc.sample_gmm_channels(means, covs, w, 4000, seed=7)
+    r = orc.get_observation_nbit(hval, snr, noise, None, 1)
+    g = qce.Gmm_nbit(n_components=K, covariance_type='full', random_state=0, max_iter=200, tol=1e-5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        g.fit(htrain, zero_mean=True)
+    est_fit = g.estimate_from_y(r, snr, N, n_summands_or_proba='all')
+    true = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w)
+    est_true = true.estimate_from_y(r, snr, N, n_summands_or_proba='all')
+    d_db = 10 * np.log10(orc.mse(est_fit, hval) / orc.mse(est_true, hval))
+    assert abs(d_db) < 0.1, d_db
