@@ -199,13 +199,17 @@ def main():
     noise = torch.view_as_complex(torch.randn((B, N_ANT, 2), generator=g, device=dev, dtype=torch.float64)) * np.sqrt(0.5)
     noise = noise.contiguous()
     acc = torch.zeros((len(SNRS), 3), dtype=torch.float64, device=dev)
+    acc_sweep, acc_total = torch.zeros_like(acc), torch.zeros_like(acc)
     del Lc, lab
 
     def step(i):
         j = i % len(SNRS)
         models[j].pipeline(quant, h, noise, 10 ** (-SNRS[j] / 20), 'all', args.precision, acc=acc[j])
-        if world > 1:                                   # the path's only exchange: NMSE accumulators
-            dist.all_reduce(acc[j])
+        # the path's only exchange: ONE all-reduce of the [n_snr, 3] NMSE accumulators per completed SNR sweep
+        if world > 1 and j == len(SNRS) - 1:
+            dist.all_reduce(acc_sweep.copy_(acc))
+            acc_total.add_(acc_sweep)
+            acc.zero_()
 
     def barrier():
         if world > 1:
@@ -216,6 +220,7 @@ def main():
         step(i)
     barrier()
     acc.zero_()
+    acc_total.zero_()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -225,6 +230,9 @@ def main():
     ev0.record()
     for i in range(args.steps):
         step(i)
+    if world > 1:                                        # remainder of an unfinished sweep (inside the timed region)
+        dist.all_reduce(acc_sweep.copy_(acc))
+        acc_total.add_(acc_sweep)
     ev1.record()
     barrier()
     launches = _lib.launch_count() - l0
@@ -234,9 +242,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
-    accs = acc.cpu().numpy()
-    if world > 1:
-        accs = accs / world                              # each step's all_reduce summed over ranks; every rank did the same steps
+    accs = (acc_total if world > 1 else acc).cpu().numpy()
 
     # --- roofline: the dense estimate kernel alone on resident quantised pilots
     pk = peaks()
