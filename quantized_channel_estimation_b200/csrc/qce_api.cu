@@ -22,12 +22,13 @@ using namespace qce;
 
 namespace {
 struct HostStaging {            // qce_estimate_host: double-buffered pinned + device staging, shared by all models
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
-    void* pin_in[2] = {nullptr, nullptr};
-    void* pin_out[2] = {nullptr, nullptr};
-    void* dev_in[2] = {nullptr, nullptr};
-    void* dev_out[2] = {nullptr, nullptr};
+    static constexpr int NSLOT = 4;  // chunks in flight: keeps the H2D and the D2H copy engines busy back to back
+    cudaStream_t streams[NSLOT] = {};
+    cudaEvent_t done[NSLOT] = {};
+    void* pin_in[NSLOT] = {};
+    void* pin_out[NSLOT] = {};
+    void* dev_in[NSLOT] = {};
+    void* dev_out[NSLOT] = {};
     size_t in_bytes = 0, out_bytes = 0;
 };
 HostStaging g_staging;
@@ -357,16 +358,17 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
                              void* h_est_host) {
     if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
     const size_t in_row = (size_t)m->n_obs * 16, out_row = (size_t)m->n_ant * 16;
-    // process-wide staging: two slots, each 64 MiB of pilots / estimates (pinned host + device), grown on demand
+    // process-wide staging: NSLOT slots, each 32 MiB of pilots / estimates (pinned host + device), grown on demand
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     HostStaging* hs = &g_staging;
-    const size_t slot_bytes = (size_t)64 << 20;
+    const size_t slot_bytes = (size_t)32 << 20;
+    constexpr int NSLOT = HostStaging::NSLOT;
     int64_t chunk = (int64_t)(slot_bytes / (in_row > out_row ? in_row : out_row));
     if (chunk < 128) chunk = 128;
     {
         const size_t need_in = (size_t)chunk * in_row, need_out = (size_t)chunk * out_row;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NSLOT; ++i) {
             if (!hs->streams[i]) {
                 QCE_CUDA_TRY(cudaStreamCreateWithFlags(&hs->streams[i], cudaStreamNonBlocking));
                 QCE_CUDA_TRY(cudaEventCreateWithFlags(&hs->done[i], cudaEventDisableTiming));
@@ -396,7 +398,8 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
         return at.type == cudaMemoryTypeHost;
     };
     const bool in_pinned = is_pinned(r_host), out_pinned = is_pinned(h_est_host);
-    int64_t pending_b0[2] = {-1, -1}, pending_nb[2] = {0, 0};
+    int64_t pending_b0[NSLOT], pending_nb[NSLOT];
+    for (int i = 0; i < NSLOT; ++i) { pending_b0[i] = -1; pending_nb[i] = 0; }
     auto drain = [&](int slot) -> qce_status {
         if (pending_b0[slot] < 0) return QCE_OK;
         QCE_CUDA_TRY(cudaEventSynchronize(hs->done[slot]));
@@ -406,7 +409,7 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
         return QCE_OK;
     };
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int slot = (int)(c & 1);
+        const int slot = (int)(c % NSLOT);
         qce_status st = drain(slot);
         if (st) return st;
         const int64_t b0 = c * chunk, nb = (B - b0) < chunk ? (B - b0) : chunk;
@@ -422,7 +425,7 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
         QCE_CUDA_TRY(cudaEventRecord(hs->done[slot], s));
         pending_b0[slot] = b0; pending_nb[slot] = nb;
     }
-    for (int slot = 0; slot < 2; ++slot) {
+    for (int slot = 0; slot < NSLOT; ++slot) {
         qce_status st = drain(slot);
         if (st) return st;
     }
