@@ -321,3 +321,94 @@ def test_fit_then_estimate_matches_true_model_nmse(qce):
     est_true = true.estimate_from_y(r, snr, N, n_summands_or_proba='all')
     d_db = 10 * np.log10(orc.mse(est_fit, hval) / orc.mse(est_true, hval))
     assert abs(d_db) < 0.1, d_db
+
+
+# ----------------------------------------------------------------------------- tensor-core path: edges and variants
+
+@pytest.mark.parametrize('B', [1, 127, 129, 511, 513, 1025])
+def test_tc_ragged_batches(qce, B):
+    """Unit / tile boundaries of the persistent SM-pair kernel (512 pilots per work unit, 128 per tile)."""
+    K, N, snr = 3, 32, 5
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.1, seed=B)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    for mode in ('all', 2):
+        ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=1)
+        est = m.estimate_from_y(torch.from_numpy(r).cuda(), snr, N, n_summands_or_proba=mode).cpu().numpy()
+        assert est.shape == (B, N) and np.isfinite(est.view(np.float64)).all()
+        if mode == 'all':
+            assert relerr(est, ref) < TOL_TC
+        else:
+            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert np.mean(per > 1e-4) <= 0.02 + 1.0 / B
+
+
+def test_tc_single_component_and_many_components(qce):
+    for K, N in ((1, 64), (130, 16)):
+        means, covs, w, h, noise, qz, r = _case(K, N, 300, 10, 1, 'uniform', 0.0, seed=K)
+        m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+        m.precision = 'tc'
+        ref = orc.gmm_estimate_from_y(means, covs, w, r, 10, n_summands_or_proba='all', n_bits=1)
+        est = m.estimate_from_y(torch.from_numpy(r).cuda(), 10, N, n_summands_or_proba='all').cpu().numpy()
+        assert relerr(est, ref) < TOL_TC
+
+
+def test_tc_off_grid_pilots_come_back_nan(qce):
+    """Data that is not on the declared quantiser grid cannot be represented exactly: those rows fail loudly (NaN)."""
+    K, N, B, snr = 4, 32, 200, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.0, seed=2)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    bad = r.copy()
+    bad[7, 3] = 0.3 + 0.1j
+    bad[150, 0] = complex(np.nan, 0.0)
+    est = m.estimate_from_y(torch.from_numpy(bad).cuda(), snr, N, n_summands_or_proba='all').cpu().numpy()
+    ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=1)
+    rows = np.zeros(B, bool)
+    rows[[7, 150]] = True
+    assert np.isnan(est[rows].view(np.float64)).all()
+    assert relerr(est[~rows], ref[~rows]) < TOL_TC
+
+
+def test_tc_non_triangular_whitening_uses_single_cta_variant(qce):
+    """A whitening factor that is not lower triangular (Q L^-1 with Q unitary gives the same quadratic form) takes the
+    cta_group::1 variant without column skipping; results must not change."""
+    from quantized_channel_estimation_b200 import precompute, engine
+    K, N, B, snr = 6, 64, 700, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.2, seed=11)
+    prep = precompute.prepare(means, covs, w, np.eye(N), snr, 1)
+    rng = np.random.default_rng(0)
+    Q = torch.as_tensor(np.linalg.qr(orc.crandn(N, N, rng=rng))[0]).to(prep['Linv'].device)
+    prep2 = dict(prep)
+    prep2['Linv'] = (Q[None] @ prep['Linv']).contiguous()
+    prep2['zoff'] = (Q[None] @ prep['zoff'][:, :, None])[:, :, 0].contiguous()
+    ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=1)
+    rt = torch.from_numpy(r).cuda()
+    for p in (prep, prep2):
+        model = engine.DenseModel(p)
+        est = model.estimate(rt, 'all', 'tc').cpu().numpy()
+        assert relerr(est, ref) < TOL_TC
+        est64 = model.estimate(rt, 'all', 'fp64').cpu().numpy()
+        assert relerr(est64, ref) < 1e-9
+
+
+def test_tc_single_cta_variant_env(qce):
+    """QCE_TC_CG=1 forces the cta_group::1 kernel (read once per process): run it in a subprocess."""
+    import os, subprocess, sys
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import qce_oracle as orc\n"
+        "import quantized_channel_estimation_b200 as qce\n"
+        "K,N,B,snr=5,64,900,5\n"
+        "means,covs,w=orc.random_psd_gmm(K,N,seed=3)\n"
+        "h,noise,_=orc.sample_gmm_channels(means,covs,w,B,seed=4)\n"
+        "r=orc.get_observation_nbit(h,snr,noise,None,1)\n"
+        "m=qce.Gmm_nbit(n_components=K).set_parameters(means,covs,w,detect_structure=False); m.precision='tc'\n"
+        "est=m.estimate_from_y(torch.from_numpy(r).cuda(),snr,N,n_summands_or_proba='all').cpu().numpy()\n"
+        "ref=orc.gmm_estimate_from_y(means,covs,w,r,snr,n_summands_or_proba='all',n_bits=1)\n"
+        "print('RELERR', np.linalg.norm(est-ref)/np.linalg.norm(ref))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, QCE_TC_CG='1'), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    err = float([l for l in out.stdout.splitlines() if l.startswith('RELERR')][0].split()[1])
+    assert err < TOL_TC
