@@ -565,27 +565,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 c_h += QCE_CLK() - c2;
             }
 
-            // ---- finalise: normalise, write the estimate row, NMSE accumulators
+            // ---- finalise: normalise, write the estimate row, NMSE accumulators (FP32 per row: FP64 stalls behind the
+            // tensor pipe; the per-row sums enter the FP64 accumulators once)
             const int64_t g = tile_base + row;
             if (EPI != 1 && g < a.B) {
                 const float invs = row_bad ? __int_as_float(0x7fc00000) : (EPI == 2 ? 1.f : 1.f / ssum);
-                double2* out = a.h_est ? a.h_est + g * N : nullptr;
-                #pragma unroll
-                for (int j = 0; j < NH / 2; ++j) {
-                    const double2 e = make_double2((double)(acc[j].x * invs), (double)(acc[j].y * invs));
-                    if (out) out[j] = e;
-                    if (a.acc && a.h_true) {
-                        double2 h;
+                if (a.h_est) {
+                    double2* out = a.h_est + g * N;
+                    #pragma unroll
+                    for (int j = 0; j < NH / 2; ++j) out[j] = make_double2((double)(acc[j].x * invs), (double)(acc[j].y * invs));
+                }
+                if (a.acc && a.h_true) {
+                    float errf = 0.f, pwf = 0.f;
+                    #pragma unroll
+                    for (int j = 0; j < NH / 2; ++j) {      // full unroll: acc[] must stay in registers
+                        float2 h;
                         if (a.h_true_c64) {
-                            const float2 hf = reinterpret_cast<const float2*>(a.h_true)[g * N + j];
-                            h = make_double2((double)hf.x, (double)hf.y);
+                            h = reinterpret_cast<const float2*>(a.h_true)[g * N + j];
                         } else {
-                            h = reinterpret_cast<const double2*>(a.h_true)[g * N + j];
+                            const double2 hd = reinterpret_cast<const double2*>(a.h_true)[g * N + j];
+                            h = make_float2((float)hd.x, (float)hd.y);
                         }
-                        const double dx = e.x - h.x, dy = e.y - h.y;
-                        err += dx * dx + dy * dy;
-                        pw += h.x * h.x + h.y * h.y;
+                        const float dx = acc[j].x * invs - h.x, dy = acc[j].y * invs - h.y;
+                        errf = fmaf(dx, dx, fmaf(dy, dy, errf));
+                        pwf = fmaf(h.x, h.x, fmaf(h.y, h.y, pwf));
                     }
+                    err += (double)errf;
+                    pw += (double)pwf;
                 }
                 cnt += 1.0;
             }
