@@ -63,6 +63,13 @@ struct TcParams {
     bool has_offsets = false;
     bool triangular = false;
     bool ready = false;
+    // split path (n_obs or n_ant above 64): a whitening-only image and up to two LMMSE row-block images; the estimate runs as
+    // log-probability launch -> selection -> one launch per row block
+    bool split = false;
+    void* image_z = nullptr;
+    void* image_h[2] = {nullptr, nullptr};
+    int h_parts = 0;            // number of row-block launches
+    int part_cols = 0;          // real columns (of the 2 n_ant) per row block
 };
 
 struct qce_circ_model {

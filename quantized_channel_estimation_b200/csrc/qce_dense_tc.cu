@@ -49,16 +49,20 @@ __host__ __device__ constexpr int tc2_rank_comp_bytes(int nt, int tri16, int ksp
     return 2 * (tc2_chunk_bytes(nt, tri16, ksps, 0) + tc2_chunk_bytes(nt, tri16, ksps, 1));
 }
 
-template <int NZ, int NH, int CG>
+// ORDER 0 = tile-major (all chunks of a component for tile 0, then for tile 1: the accumulators complete half a component
+// apart), ORDER 1 = chunk-major (each chunk feeds both tiles, then is released: two ring stages suffice -- the split
+// launches of the large shapes, whose pilot tiles leave less than 100 KB for the ring)
+template <int KD_, int NZ, int NH, int CG, int ORDER = 0>
 struct TcCfg {
-    static constexpr int KD = NZ;                                   // GEMM reduction length 2*n_obs
+    static constexpr int KD = KD_;                                  // GEMM reduction length 2*n_obs
     static constexpr int NT = NZ + NH;                              // fused MMA N: Z columns then H columns
+    static constexpr int TRI16 = NZ > 0 ? 16 : 0;                   // CG=2 image: K-step ks skips the first 16 ks (Z) rows
     static constexpr int A_TILE_BYTES = TILE_M * KD * 2;
     static constexpr int KSPS = KD / 32;                            // K-steps (of 16) per staged chunk = half the K range
     // CG=1: a chunk is one K-half of the stacked hi (or lo) image, 4 chunks per component.
     // CG=2: a chunk is this CTA's share of the whole hi (or lo) image (triangular layout), 2 chunks per component.
     static constexpr int NCHUNK = (CG == 2) ? 2 : 4;
-    static constexpr int CB0 = tc2_chunk_bytes(NT, 16, KSPS, 0), CB1 = tc2_chunk_bytes(NT, 16, KSPS, 1);
+    static constexpr int CB0 = tc2_chunk_bytes(NT, TRI16, KSPS, 0), CB1 = tc2_chunk_bytes(NT, TRI16, KSPS, 1);
     static constexpr int STAGE_BYTES = (CG == 2) ? (CB0 + CB1) : NT * (KD / 2) * 2;
     static constexpr int CTRL_BYTES = 1024;
     static constexpr int STAGES_FIT = (SMEM_LIMIT - TILES * A_TILE_BYTES - CTRL_BYTES) / STAGE_BYTES;
@@ -68,7 +72,9 @@ struct TcCfg {
     static constexpr int TMEM_COLS_USED = TILES * NT;
     static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
                                      : TMEM_COLS_USED <= 256 ? 256 : 512;
-    static_assert(STAGES >= NCHUNK + 1, "tile-major schedule keeps the chunks of a component resident plus one prefetch");
+    static_assert(STAGES >= (ORDER == 0 ? NCHUNK + 1 : 2), "tile-major schedule keeps the chunks of a component resident plus one prefetch");
+    static_assert(NZ == 0 || NZ == KD, "the whitening block is square");
+    static_assert(NT >= 32, "empty launch");
     static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
     static_assert(NT <= 256, "fused MMA N exceeds 256");
     static_assert(TMEM_COLS_USED <= 512, "accumulators exceed TMEM");
@@ -84,12 +90,47 @@ struct TcCtrl {
 };
 static_assert(sizeof(TcCtrl) <= 1024, "control block");
 
+// All MMAs of one staged chunk q for one tile (every argument but the two descriptor bases folds to an immediate after
+// unrolling; the whole warp executes this with uniform control flow, the elected lane issues).
+template <class Cfg, int CG>
+__device__ __forceinline__ void tc_issue_chunk(const int q, const uint32_t d_tile, const uint32_t a_lo_t, const uint32_t b_addr_s,
+                                               const int tri16, const bool elected) {
+    constexpr int NT = Cfg::NT, KSPS = Cfg::KSPS;
+    constexpr uint32_t A_LBO = (TILE_M / 8) * 128;                              // SBO = 128 for both operands
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                      // SBO field | descriptor version 1
+    constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)((CG * TILE_M) >> 4) << 24);
+    constexpr int KS_PER_CHUNK = (CG == 2) ? 2 * KSPS : KSPS;
+    #pragma unroll
+    for (int s2 = 0; s2 < KS_PER_CHUNK; ++s2) {
+        const int ks = (CG == 2) ? s2 : (q & 1) * KSPS + s2;           // K-step within the full K range
+        const bool lo_pass = (CG == 2) ? (q == 1) : (q >= 2);
+        const uint32_t skip = (uint32_t)(tri16 * ks);                   // structurally zero leading columns
+        const uint32_t np = NT - skip;                                  // N' of this MMA
+        const uint32_t a_lo = a_lo_t + ks * ((2 * A_LBO) >> 4);
+        uint32_t b_lo;
+        if (CG == 2) {  // per-CTA half image: sub-block of N'/2 rows, LBO = (N'/16) cores * 128 B (all immediates)
+            const int half = ks / KSPS, sb = ks % KSPS;
+            const int off = (half ? Cfg::CB0 : 0) + tc2_sub_off(NT, Cfg::TRI16, KSPS, half, sb);
+            b_lo = (b_addr_s + (uint32_t)(off >> 4)) | ((np >> 1) << 16);
+        } else {        // full stacked image: skip the leading row blocks
+            b_lo = (b_addr_s + s2 * (((2 * NT / 8) * 128) >> 4) + (skip >> 3) * (128 >> 4)) | ((((NT / 8) * 128) >> 4) << 16);
+        }
+        const uint32_t idesc = IDESC0 | ((np >> 3) << 17);
+        const uint32_t accum = (lo_pass || ks > 0) ? 1u : 0u;
+        if (elected) {
+            if (CG == 2) umma2_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
+            else umma_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
+        }
+    }
+}
+
 // EPI selects the epilogue: 0 = fused 'all' estimate (online softmax), 1 = export the weighted log-probabilities l_k only,
 // 2 = combine with given per-pilot weights (the top-1 / top-n / cumulative-probability modes run 1 -> select -> 2)
-template <int NCHZ, int NCHH, bool OFFS, int CG, int EPI>
+// KDC = n_obs / 16 (reduction length 32 KDC); NCHZ = 0 (no whitening columns: an H-part launch) or KDC; NCHH = H columns / 32
+template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
-    using Cfg = TcCfg<NZ, NH, CG>;
+    using Cfg = TcCfg<32 * KDC, NZ, NH, CG, ORDER>;
     constexpr int KD = Cfg::KD;
     constexpr int S = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -103,7 +144,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     const int64_t n_units = (a.B + CG * TILES * TILE_M - 1) / (CG * TILES * TILE_M);
     const int64_t unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
     // the SM-pair variant is only launched for triangular Linv (the common, Cholesky case): its offsets are compile-time
-    const int tri16 = (CG == 2) ? 16 : (a.tri ? 16 : 0);
+    const int tri16 = (CG == 2) ? Cfg::TRI16 : (a.tri ? 16 : 0);
 
     if (threadIdx.x == 0) {
         // CG=2: the leader's "full" barriers also collect one remote arrival from the peer CTA ("my half has landed too")
@@ -173,10 +214,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             // latency, so descriptors are 32-bit base + compile-time immediate and barrier waits are kept to
             // NCHUNK + TILES per component.
             const bool elected = elect_one();
-            constexpr int NT = Cfg::NT, KSPS = Cfg::KSPS;
-            constexpr uint32_t A_LBO = (TILE_M / 8) * 128;                              // SBO = 128 for both operands
-            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                      // SBO field | descriptor version 1
-            constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)((CG * TILE_M) >> 4) << 24);
+            constexpr int NT = Cfg::NT;
+            constexpr uint32_t A_LBO = (TILE_M / 8) * 128;
             const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFF) | ((A_LBO >> 4) << 16);
             const uint32_t b_addr0 = (smem_u32(sB) >> 4) & 0x3FFF;
             int stage0 = 0;                          // ring slot / parity of chunk 0 of the current component
@@ -190,6 +229,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 tc_fence_after();
                 w_a += QCE_CLK() - ca;
                 for (int k = 0; k < a.K; ++k) {
+                    if (ORDER == 0) {
                     #pragma unroll
                     for (int t = 0; t < TILES; ++t) {
                         // the first MMA overwrites the accumulator: the epilogue must have drained component k-1
@@ -210,36 +250,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                                 tc_fence_after();
                                 w_full += QCE_CLK() - c0;
                             }
-                            const uint32_t b_addr_s = b_addr0 + stage * (Cfg::STAGE_BYTES >> 4);
-                            constexpr int KS_PER_CHUNK = (CG == 2) ? 2 * KSPS : KSPS;
-                            #pragma unroll
-                            for (int s2 = 0; s2 < KS_PER_CHUNK; ++s2) {
-                                const int ks = (CG == 2) ? s2 : (q & 1) * KSPS + s2;           // K-step within the full K range
-                                const bool lo_pass = (CG == 2) ? (q == 1) : (q >= 2);
-                                const uint32_t skip = (uint32_t)(tri16 * ks);                   // structurally zero leading columns
-                                const uint32_t np = NT - skip;                                  // N' of this MMA
-                                const uint32_t a_lo = a_lo_t + ks * ((2 * A_LBO) >> 4);
-                                uint32_t b_lo;
-                                if (CG == 2) {  // per-CTA half image: sub-block of N'/2 rows, LBO = (N'/16) cores * 128 B (all immediates)
-                                    const int half = ks / KSPS, sb = ks % KSPS;
-                                    const int off = (half ? Cfg::CB0 : 0) + tc2_sub_off(NT, 16, KSPS, half, sb);
-                                    b_lo = (b_addr_s + (uint32_t)(off >> 4)) | ((np >> 1) << 16);
-                                } else {        // full stacked image: skip the leading row blocks
-                                    b_lo = (b_addr_s + s2 * (((2 * NT / 8) * 128) >> 4) + (skip >> 3) * (128 >> 4)) | ((((NT / 8) * 128) >> 4) << 16);
-                                }
-                                const uint32_t idesc = IDESC0 | ((np >> 3) << 17);
-                                const uint32_t accum = (lo_pass || ks > 0) ? 1u : 0u;
-                                if (elected) {
-                                    if (CG == 2) umma2_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
-                                    else umma_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
-                                }
-                            }
+                            tc_issue_chunk<Cfg, CG>(q, d_tile, a_lo_t, b_addr0 + stage * (Cfg::STAGE_BYTES >> 4), tri16, elected);
                             if (t == TILES - 1 && elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->empty[stage])); else tc_commit(smem_u32(&ctrl->empty[stage])); }
                             if (++stage == S) { stage = 0; phase ^= 1; }
                         }
                         if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->acc_full[t])); else tc_commit(smem_u32(&ctrl->acc_full[t])); }
                         __syncwarp();
                         if (t == TILES - 1) { stage0 = stage; phase0 = phase; }
+                    }
+                    } else {
+                    // chunk-major: a chunk feeds both tiles and is released at once
+                    #pragma unroll
+                    for (int q = 0; q < Cfg::NCHUNK; ++q) {
+                        long long c0 = QCE_CLK();
+                        mbar_wait(smem_u32(&ctrl->full[stage0]), phase0);
+                        tc_fence_after();
+                        w_full += QCE_CLK() - c0;
+                        #pragma unroll
+                        for (int t = 0; t < TILES; ++t) {
+                            if (q == 0) {
+                                c0 = QCE_CLK();
+                                if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
+                                else { mbar_wait(smem_u32(&ctrl->acc_empty[1]), eph1 ^ 1); eph1 ^= 1; }
+                                tc_fence_after();
+                                w_empty += QCE_CLK() - c0;
+                            }
+                            tc_issue_chunk<Cfg, CG>(q, tmem_base + t * NT, a_lo0 + t * (Cfg::A_TILE_BYTES >> 4),
+                                                    b_addr0 + stage0 * (Cfg::STAGE_BYTES >> 4), tri16, elected);
+                            if (q == Cfg::NCHUNK - 1 && elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->acc_full[t])); else tc_commit(smem_u32(&ctrl->acc_full[t])); }
+                        }
+                        if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->empty[stage0])); else tc_commit(smem_u32(&ctrl->empty[stage0])); }
+                        __syncwarp();
+                        if (++stage0 == S) { stage0 = 0; phase0 ^= 1; }
+                    }
                     }
                 }
                 if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->a_free)); else tc_commit(smem_u32(&ctrl->a_free)); }
@@ -274,7 +317,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         const uint32_t th = tz + NZ;
         uint32_t fph = 0;
         const int N = a.N;
-        double err = 0.0, pw = 0.0, cnt = 0.0;
+        double err = 0.0, pw = 0.0, cnt = 0.0;     // cnt also gates the atomics (rows handled by this thread)
         long long w_acc = 0, c_z = 0, c_h = 0, c_pro = 0, c_ld = 0;
 
         for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
@@ -284,7 +327,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             if (tile_base + row < a.B) row_bad = __ldg(a.bad + tile_base + row) != 0;
             c_pro += QCE_CLK() - c0;
 
-            float2 acc[NH / 2];                        // the estimate row, (re, im) pairs: packed FFMA2 arithmetic
+            float2 acc[NH > 0 ? NH / 2 : 1];           // the estimate row, (re, im) pairs: packed FFMA2 arithmetic
             #pragma unroll
             for (int j = 0; j < NH / 2; ++j) acc[j] = make_float2(0.f, 0.f);
             float mref_hi = 0.f, mref_lo = 0.f;
@@ -396,7 +439,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                             for (int u = 0; u < 16; ++u) {
                                 acc[ch * 16 + u] = __ffma2_rn(ph, make_float2(v[2 * u], v[2 * u + 1]), acc[ch * 16 + u]);
                                 if (OFFS) {
-                                    const float2 ho = __ldg(reinterpret_cast<const float2*>(a.hoff + (size_t)k * NH + ch * 32 + 2 * u));
+                                    const float2 ho = __ldg(reinterpret_cast<const float2*>(a.hoff + (size_t)k * a.h_stride + a.h_col0 + ch * 32 + 2 * u));
                                     acc[ch * 16 + u] = __ffma2_rn(make_float2(p, p), ho, acc[ch * 16 + u]);
                                 }
                             }
@@ -418,7 +461,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             if (EPI != 1 && g < a.B) {
                 const float invs = row_bad ? __int_as_float(0x7fc00000) : (EPI == 2 ? 1.f : 1.f / ssum);
                 if (a.h_est) {
-                    double2* out = a.h_est + g * N;
+                    double2* out = a.h_est + g * N + (a.h_col0 >> 1);
                     #pragma unroll
                     for (int j = 0; j < NH / 2; ++j) out[j] = make_double2((double)(acc[j].x * invs), (double)(acc[j].y * invs));
                 }
@@ -428,9 +471,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     for (int j = 0; j < NH / 2; ++j) {      // full unroll: acc[] must stay in registers
                         float2 h;
                         if (a.h_true_c64) {
-                            h = reinterpret_cast<const float2*>(a.h_true)[g * N + j];
+                            h = reinterpret_cast<const float2*>(a.h_true)[g * N + (a.h_col0 >> 1) + j];
                         } else {
-                            const double2 hd = reinterpret_cast<const double2*>(a.h_true)[g * N + j];
+                            const double2 hd = reinterpret_cast<const double2*>(a.h_true)[g * N + (a.h_col0 >> 1) + j];
                             h = make_float2((float)hd.x, (float)hd.y);
                         }
                         const float dx = acc[j].x * invs - h.x, dy = acc[j].y * invs - h.y;
@@ -456,7 +499,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             if (lane == 0 && cnt > 0.0) {
                 atomicAdd(a.acc + 0, err);
                 atomicAdd(a.acc + 1, pw);
-                atomicAdd(a.acc + 2, cnt);
+                if (a.count_rows) atomicAdd(a.acc + 2, cnt);
             }
         }
     }
@@ -503,6 +546,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict_
     const int e = (mx > 0.0 && isfinite(mx)) ? 13 - ex : 0;
     const double sc = ldexp(data_scale, e);
     if (threadIdx.x == 0) (which ? hscale : zscale)[k] = (float)ldexp(1.0, -e);
+    if (!image) return;                                    // split path: only the scales and the triangular flag are needed
     const int ncols = 2 * R, kd = 2 * No, nt = 2 * No + 2 * N;
     __half* hi = image + (size_t)k * 2 * nt * kd;
     __half* lo = hi + (size_t)nt * kd;
@@ -522,12 +566,13 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const double2* __restrict_
 }
 
 // CG=2 operand images (layout: see tc2_nprime / tc2_sub_off).  One block per (component, rank); the power-of-two scales
-// were fixed by tc_pack_kernel.
+// were fixed by tc_pack_kernel.  The stacked operand consists of the first nz rows of E(Linv_k) (nz = 0 or 2No) followed by
+// the rows [h0, h0 + nh) of E(W_k): the fused launch uses (2No, 0, 2N), the split launches (2No, -, 0) and (0, h0, nh).
 __global__ void __launch_bounds__(256) tc2_pack_kernel(const double2* __restrict__ Linv, const double2* __restrict__ W, int No, int N,
                                                        double data_scale, const float* __restrict__ zscale, const float* __restrict__ hscale,
-                                                       int tri16, unsigned char* __restrict__ image2) {
+                                                       int tri16, int nz, int h0, int nh, unsigned char* __restrict__ image2) {
     const int k = blockIdx.x >> 1, rank = blockIdx.x & 1;
-    const int kd = 2 * No, nz = 2 * No, nt = 2 * No + 2 * N, ksps = kd / 32;
+    const int kd = 2 * No, nt = nz + nh, ksps = kd / 32;
     const double scz = data_scale / (double)zscale[k], sch = data_scale / (double)hscale[k];
     const int cb0 = tc2_chunk_bytes(nt, tri16, ksps, 0), cb1 = tc2_chunk_bytes(nt, tri16, ksps, 1);
     unsigned char* base = image2 + ((size_t)k * 2 + rank) * (size_t)(2 * (cb0 + cb1));
@@ -543,7 +588,7 @@ __global__ void __launch_bounds__(256) tc2_pack_kernel(const double2* __restrict
                 const int nb = core % (rows / 8), kc = core / (rows / 8);
                 const int n = n0 + nb * 8 + (within >> 3), kk = ks * 16 + kc * 8 + (within & 7);
                 const bool isz = n < nz;
-                const int rrow = isz ? n : n - nz;
+                const int rrow = isz ? n : h0 + n - nz;
                 const double2 v = isz ? Linv[((size_t)k * No + (rrow >> 1)) * No + (kk >> 1)] : W[((size_t)k * N + (rrow >> 1)) * No + (kk >> 1)];
                 const int aa = rrow & 1, bb = kk & 1;
                 const double x = (aa == bb ? v.x : (aa ? v.y : -v.y)) * (isz ? scz : sch);
@@ -763,17 +808,34 @@ static qce_status tc_scratch_aux(TileScratch* t, size_t rows, size_t K) {
     return QCE_OK;
 }
 
+// fused launch (Z|H in one MMA, estimate row in registers): n_obs, n_ant <= 64
+static bool tc_instantiated(const qce_model* m) {
+    if (m->n_obs % 16 || m->n_ant % 16) return false;
+    const int cz = m->n_obs / 16, ch = m->n_ant / 16;
+    return (cz == ch && cz >= 1 && cz <= 4) || (cz == 4 && ch == 2) || (cz == 2 && ch == 1);
+}
+
+// split launches: the 2 n_ant estimate columns are produced in row blocks of at most 128 (64 packed register accumulators
+// per pilot), the 2 n_obs whitening columns by a launch of their own
+static bool tc_split_shape(int No, int N, int* parts, int* part_cols) {
+    if (No == 128 && (N == 64 || N == 128)) { *part_cols = 128; *parts = 2 * N / 128; return true; }
+    if (No == 96 && (N == 48 || N == 96)) { *part_cols = 96; *parts = 2 * N / 96; return true; }
+    return false;
+}
+
 bool tc_supported(const qce_model* m, int mode) {
+    if (!(m->data_scale > 0.0)) return false;
+    int parts = 0, pc = 0;
+    if (tc_split_shape(m->n_obs, m->n_ant, &parts, &pc)) return !m->tc.ready || m->tc.triangular;
     // the modes other than the fused 'all' need the SM-pair variant (triangular whitening factor)
     if (mode != QCE_MODE_ALL && m->tc.ready && !m->tc.triangular) return false;
-    if (m->n_obs % 16 || m->n_ant % 16 || m->n_obs > 64 || m->n_ant > 64) return false;
-    if (!(m->data_scale > 0.0)) return false;
-    return true;
+    return tc_instantiated(m);
 }
 
 void tc_free(qce_model* m) {
     TcParams& p = m->tc;
     cudaFree(p.image); cudaFree(p.image2); cudaFree(p.zoff); cudaFree(p.hoff); cudaFree(p.zscale); cudaFree(p.hscale); cudaFree(p.logc2); cudaFree(p.flags);
+    cudaFree(p.image_z); cudaFree(p.image_h[0]); cudaFree(p.image_h[1]);
     p = TcParams();
 }
 
@@ -781,9 +843,12 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     TcParams& p = m->tc;
     const size_t K = m->n_comp, No = m->n_obs, N = m->n_ant;
     const size_t comp_halfs = 2 * (2 * No + 2 * N) * (2 * No);
-    if (!p.image) {
-        p.image_bytes = K * comp_halfs * sizeof(__half);
-        QCE_CUDA_TRY(cudaMalloc(&p.image, p.image_bytes));
+    p.split = tc_split_shape((int)No, (int)N, &p.h_parts, &p.part_cols);
+    if (!p.zoff) {
+        if (!p.split) {
+            p.image_bytes = K * comp_halfs * sizeof(__half);
+            QCE_CUDA_TRY(cudaMalloc(&p.image, p.image_bytes));
+        }
         QCE_CUDA_TRY(cudaMalloc(&p.zoff, K * 2 * No * sizeof(float)));
         QCE_CUDA_TRY(cudaMalloc(&p.hoff, K * 2 * N * sizeof(float)));
         QCE_CUDA_TRY(cudaMalloc(&p.zscale, K * sizeof(float)));
@@ -804,13 +869,30 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     QCE_CUDA_TRY(cudaStreamSynchronize(s));
     p.has_offsets = h_flags[0] != 0;
     p.triangular = h_flags[1] == 0;
-    {   // per-CTA half images of the SM-pair kernel (their layout depends on the triangular flag)
-        const int nt = (int)(2 * No + 2 * N), ksps = (int)(2 * No) / 32, tri16 = p.triangular ? 16 : 0;
+    const int ksps = (int)(2 * No) / 32;
+    if (p.split) {
+        if (!p.triangular) { p.ready = false; return QCE_OK; }      // only the SM-pair (triangular) layout exists for these shapes
+        const size_t bytes_z = K * 2 * (size_t)tc2_rank_comp_bytes((int)(2 * No), 16, ksps);
+        const size_t bytes_h = K * 2 * (size_t)tc2_rank_comp_bytes(p.part_cols, 0, ksps);
+        if (!p.image_z) QCE_CUDA_TRY(cudaMalloc(&p.image_z, bytes_z));
+        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+                                                          p.zscale, p.hscale, 16, (int)(2 * No), 0, 0, (unsigned char*)p.image_z);
+        QCE_CHECK_LAUNCH("tc2_pack_kernel");
+        for (int part = 0; part < p.h_parts; ++part) {
+            if (!p.image_h[part]) QCE_CUDA_TRY(cudaMalloc(&p.image_h[part], bytes_h));
+            tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+                                                              p.zscale, p.hscale, 0, 0, part * p.part_cols, p.part_cols,
+                                                              (unsigned char*)p.image_h[part]);
+            QCE_CHECK_LAUNCH("tc2_pack_kernel");
+        }
+        QCE_CUDA_TRY(cudaStreamSynchronize(s));
+    } else {   // per-CTA half images of the SM-pair kernel (their layout depends on the triangular flag)
+        const int nt = (int)(2 * No + 2 * N), tri16 = p.triangular ? 16 : 0;
         const size_t bytes = K * 2 * (size_t)tc2_rank_comp_bytes(nt, tri16, ksps);
         if (p.image2 && bytes > p.image2_bytes) { QCE_CUDA_TRY(cudaFree(p.image2)); p.image2 = nullptr; }
         if (!p.image2) { QCE_CUDA_TRY(cudaMalloc(&p.image2, bytes)); p.image2_bytes = bytes; }
         tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
-                                                          p.zscale, p.hscale, tri16, (unsigned char*)p.image2);
+                                                          p.zscale, p.hscale, tri16, (int)(2 * No), 0, (int)(2 * N), (unsigned char*)p.image2);
         QCE_CHECK_LAUNCH("tc2_pack_kernel");
         QCE_CUDA_TRY(cudaStreamSynchronize(s));
     }
@@ -818,11 +900,11 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     return QCE_OK;
 }
 
-template <int NCHZ, int NCHH, bool OFFS, int CG, int EPI>
+template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER>
 static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
-    using Cfg = TcCfg<32 * NCHZ, 32 * NCHH, CG>;
+    using Cfg = TcCfg<32 * KDC, 32 * NCHZ, 32 * NCHH, CG, ORDER>;
     static bool attr_set = false;
-    auto kern = dense_tc_kernel<NCHZ, NCHH, OFFS, CG, EPI>;
+    auto kern = dense_tc_kernel<KDC, NCHZ, NCHH, OFFS, CG, EPI, ORDER>;
     if (!attr_set) {
         QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
@@ -853,24 +935,54 @@ static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
 template <int NCHZ, int NCHH>
 static qce_status launch_offs(const TcArgs& a, bool offs, int cg, int epi, cudaStream_t s) {
     if (cg == 2) {
-        if (epi == 1) return offs ? launch_cfg<NCHZ, NCHH, true, 2, 1>(a, s) : launch_cfg<NCHZ, NCHH, false, 2, 1>(a, s);
-        if (epi == 2) return offs ? launch_cfg<NCHZ, NCHH, true, 2, 2>(a, s) : launch_cfg<NCHZ, NCHH, false, 2, 2>(a, s);
-        return offs ? launch_cfg<NCHZ, NCHH, true, 2, 0>(a, s) : launch_cfg<NCHZ, NCHH, false, 2, 0>(a, s);
+        if (epi == 1) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 1, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 1, 0>(a, s);
+        if (epi == 2) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 2, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 2, 0>(a, s);
+        return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 0, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 0, 0>(a, s);
     }
     if (epi != 0) { set_error("tensor-core kernel: the single-CTA variant only implements the fused 'all' epilogue"); return QCE_ERR_UNSUPPORTED; }
-    return offs ? launch_cfg<NCHZ, NCHH, true, 1, 0>(a, s) : launch_cfg<NCHZ, NCHH, false, 1, 0>(a, s);
+    return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 1, 0, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 1, 0, 0>(a, s);
 }
 
-static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
-                         double* acc, int epi = 0) {
+// split path: epi 1 = whitening-only launch (log-probabilities), epi 2 = one LMMSE row block with the given weights
+template <int KDC, int NCHH>
+static qce_status launch_split(const TcArgs& a, bool offs, int epi, cudaStream_t s) {
+    if (epi == 1) return offs ? launch_cfg<KDC, KDC, 0, true, 2, 1, 1>(a, s) : launch_cfg<KDC, KDC, 0, false, 2, 1, 1>(a, s);
+    return offs ? launch_cfg<KDC, 0, NCHH, true, 2, 2, 1>(a, s) : launch_cfg<KDC, 0, NCHH, false, 2, 2, 1>(a, s);
+}
+
+static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc,
+                         TcArgs* out) {
     const TcParams& p = m->tc;
-    TcArgs a;
+    TcArgs& a = *out;
     a.image = (const __half*)p.image; a.image2 = (const unsigned char*)p.image2; a.zscale = p.zscale; a.hscale = p.hscale; a.zoff = p.zoff; a.hoff = p.hoff;
     a.logc2 = (const float2*)p.logc2; a.a_img = (const __half*)ts->img; a.bad = (const unsigned char*)ts->bad;
     a.h_est = (double2*)h_est; a.h_true = h_true; a.h_true_c64 = h_true_c64;
     a.lp_out = (float2*)ts->lp2; a.w_in = (const float*)ts->wts;
     a.acc = acc; a.B = B; a.K = m->n_comp; a.No = m->n_obs; a.N = m->n_ant;
     a.tri = p.triangular ? 1 : 0;
+    a.prof = nullptr;
+    a.h_stride = 2 * m->n_ant; a.h_col0 = 0; a.count_rows = 1;
+}
+
+static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,
+                               const void* h_true, int h_true_c64, double* acc) {
+    const TcParams& p = m->tc;
+    TcArgs a;
+    tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
+    a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
+    a.h_col0 = part * p.part_cols;
+    a.count_rows = part == 0;
+    if (m->n_obs == 128) return launch_split<8, 4>(a, p.has_offsets, epi, s);
+    if (m->n_obs == 96) return launch_split<6, 3>(a, p.has_offsets, epi, s);
+    set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant);
+    return QCE_ERR_UNSUPPORTED;
+}
+
+static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
+                         double* acc, int epi = 0) {
+    const TcParams& p = m->tc;
+    TcArgs a;
+    tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
     static long long* prof = nullptr;
     static const bool want_prof = getenv("QCE_TC_PROF") != nullptr;
     if (want_prof && !prof) cudaMallocManaged(&prof, 16 * sizeof(long long));
@@ -897,13 +1009,8 @@ static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t
     return st;
 }
 
-static bool tc_instantiated(const qce_model* m) {
-    const int cz = m->n_obs / 16, ch = m->n_ant / 16;
-    return (cz == ch && cz >= 1 && cz <= 4) || (cz == 4 && ch == 2) || (cz == 2 && ch == 1);
-}
-
 static qce_status tc_format_into(qce_model* m, cudaStream_t s, const double* r, int64_t B, TileScratch** out) {
-    if (!tc_instantiated(m)) { set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant); return QCE_ERR_UNSUPPORTED; }
+    if (!tc_instantiated(m) && !m->tc.split) { set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant); return QCE_ERR_UNSUPPORTED; }
     TileScratch* ts = nullptr;
     qce_status st = tc_scratch(m, s, B, &ts);
     if (st) return st;
@@ -922,6 +1029,27 @@ qce_status tc_format(qce_model* m, cudaStream_t s, const double* r, int64_t B) {
     return tc_format_into(m, s, r, B, &ts);
 }
 
+// the general path: log-probabilities -> per-mode weights -> weighted combination (three launches)
+static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, int64_t B, int mode, int n_top, double rho, double* h_est,
+                               double* logp_out, const void* h_true, int h_true_c64, double* acc) {
+    if (m->n_comp > 1024) { set_error("tensor-core mode selection supports K <= 1024"); return QCE_ERR_UNSUPPORTED; }
+    qce_status st = tc_scratch_aux(ts, (size_t)B, (size_t)m->n_comp);
+    if (st) return st;
+    st = m->tc.split ? tc_run_split(m, ts, s, B, 1, 0, nullptr, nullptr, 0, nullptr) : tc_run(m, ts, s, B, nullptr, nullptr, 0, nullptr, 1);
+    if (st) return st;
+    const bool want_est = h_est || acc;
+    tc_select_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags,
+                                                             want_est ? (float*)ts->wts : nullptr, logp_out);
+    QCE_CHECK_LAUNCH("tc_select_kernel");
+    if (!want_est) return QCE_OK;
+    if (!m->tc.split) return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc, 2);
+    for (int part = 0; part < m->tc.h_parts; ++part) {
+        st = tc_run_split(m, ts, s, B, 2, part, h_est, h_true, h_true_c64, acc);
+        if (st) return st;
+    }
+    return QCE_OK;
+}
+
 qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc) {
     TileScratch* ts = nullptr;
     {
@@ -934,23 +1062,8 @@ qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double
         return QCE_ERR_INVALID;
     }
     if (B == 0) return QCE_OK;
+    if (m->tc.split) return tc_run_modes(m, ts, s, B, QCE_MODE_ALL, 0, 0.0, h_est, nullptr, h_true, h_true_c64, acc);
     return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
-}
-
-// the general path: log-probabilities -> per-mode weights -> weighted combination (three launches)
-static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, int64_t B, int mode, int n_top, double rho, double* h_est,
-                               double* logp_out, const void* h_true, int h_true_c64, double* acc) {
-    if (m->n_comp > 1024) { set_error("tensor-core mode selection supports K <= 1024"); return QCE_ERR_UNSUPPORTED; }
-    qce_status st = tc_scratch_aux(ts, (size_t)B, (size_t)m->n_comp);
-    if (st) return st;
-    st = tc_run(m, ts, s, B, nullptr, nullptr, 0, nullptr, 1);
-    if (st) return st;
-    const bool want_est = h_est || acc;
-    tc_select_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags,
-                                                             want_est ? (float*)ts->wts : nullptr, logp_out);
-    QCE_CHECK_LAUNCH("tc_select_kernel");
-    if (!want_est) return QCE_OK;
-    return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc, 2);
 }
 
 // pilots given as complex128 values (estimate_from_y): format, then estimate
@@ -960,7 +1073,7 @@ qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_
     TileScratch* ts = nullptr;
     qce_status st = tc_format_into(m, s, r, B, &ts);
     if (st) return st;
-    if (mode == QCE_MODE_ALL && !logp_out) return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
+    if (mode == QCE_MODE_ALL && !logp_out && !m->tc.split) return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
     return tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
 }
 
@@ -969,7 +1082,7 @@ qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_
 qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t s, const void* h, int h_is_c64, const double* noise,
                               double noise_scale, int64_t B, int mode, int n_top, double rho, double* h_est, double* acc) {
     if (B == 0) return QCE_OK;
-    if (!tc_instantiated(m)) { set_error("tensor-core pipeline: shape not supported"); return QCE_ERR_UNSUPPORTED; }
+    if (!tc_instantiated(m) && !m->tc.split) { set_error("tensor-core pipeline: shape not supported"); return QCE_ERR_UNSUPPORTED; }
     TileScratch* ts = nullptr;
     qce_status st = tc_scratch(m, s, B, &ts);
     if (st) return st;
@@ -984,7 +1097,7 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
                                                              (__half*)ts->img, (unsigned char*)ts->bad);
     QCE_CHECK_LAUNCH("tc_format_kernel(observe)");
     ts->owner = m; ts->rows = B;
-    if (mode == QCE_MODE_ALL) return tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
+    if (mode == QCE_MODE_ALL && !m->tc.split) return tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
     return tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);
 }
 

@@ -1,4 +1,4 @@
-// Shared pieces of the tensor-core estimate kernels (qce_dense_tc.cu: N <= 64, qce_dense_tcbig.cu: 64 < N <= 128):
+// Shared pieces of the tensor-core estimate kernels (qce_dense_tc.cu):
 // kernel arguments, mbarrier / bulk-copy / tcgen05 PTX wrappers, pilot-tile scratch.
 #pragma once
 #include <math.h>
@@ -41,6 +41,11 @@ struct TcArgs {
     int K, No, N;
     long long* prof;           // optional per-role cycle counters of block 0 (QCE_TC_PROF=1), else null
     int tri;                   // Linv_k lower triangular (Cholesky whitening): skip the structurally zero columns
+    // H-part launches of the split path (64 < N <= 128): this launch produces the real columns [h_col0, h_col0 + NH) of the
+    // 2N-column estimate row
+    int h_stride;              // floats per component in hoff (2N)
+    int h_col0;
+    int count_rows;            // add the number of rows to acc[2] (only one of the H-part launches does)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -170,11 +175,5 @@ struct TileScratch {
     const qce_model* owner = nullptr;      // model whose pilots are currently formatted here
     int64_t rows = 0;
 };
-
-// qce_dense_tcbig.cu
-bool tcbig_shape_ok(const qce_model* m);
-qce_status tcbig_pack_params(qce_model* m, cudaStream_t s);
-qce_status tcbig_run(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true,
-                     int h_true_c64, double* acc);
 
 }  // namespace qce

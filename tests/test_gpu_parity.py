@@ -343,6 +343,72 @@ def test_tc_ragged_batches(qce, B):
             assert np.mean(per > 1e-4) <= 0.02 + 1.0 / B
 
 
+def _check_modes(est_fn, ref_fn, B):
+    for mode in ('all', 1, 3, 0.95):
+        est, ref = est_fn(mode), ref_fn(mode)
+        assert np.isfinite(est.view(np.float64)).all()
+        if mode == 'all':
+            assert relerr(est, ref) < TOL_TC, (mode, relerr(est, ref))
+        else:
+            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert np.mean(per > 1e-4) <= 0.02 + 1.0 / B, (mode, np.sort(per)[-5:])
+
+
+@pytest.mark.parametrize('K,N,B,snr,nb,ms', [
+    (6, 128, 700, 10, 1, 0.0),      # two row blocks of 128 estimate columns, zero means
+    (5, 128, 300, 5, 2, 0.1),       # 2-bit uniform, non-zero means (offset epilogues)
+    (4, 96, 515, 0, 1, 0.1),        # 96 antennas: 192-column whitening launch, two row blocks of 96
+    (70, 128, 130, 20, 3, 0.0),     # more components than the config-4 shape, 3-bit uniform grid (odd integers up to 7)
+])
+def test_tc_split_path_large_antenna_counts(qce, K, N, B, snr, nb, ms):
+    """64 < N <= 128: whitening-only launch -> selection -> LMMSE row-block launches (all four modes)."""
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, 'uniform', ms, seed=K + N)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    rt = torch.from_numpy(r).cuda()
+    _check_modes(lambda mode: m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer=qz).cpu().numpy(),
+                 lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer=qz), B)
+    # NMSE accumulators of the fused pipeline: each row block adds its columns, the row count is added once
+    from quantized_channel_estimation_b200 import engine, precompute
+    model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, nb, 'uniform', qz))
+    est, acc = model.estimate(rt, 'all', 'tc', h_true=torch.from_numpy(h).cuda())
+    acc = acc.cpu().numpy()
+    assert acc[2] == B
+    np.testing.assert_allclose(acc[0], np.sum(np.abs(est.cpu().numpy() - h) ** 2), rtol=1e-5)
+    np.testing.assert_allclose(acc[1], np.sum(np.abs(h) ** 2), rtol=1e-5)
+
+
+def test_tc_split_path_two_pilots(qce):
+    """A = kron(x, I): n_obs = 2 N = 128 observations of 64 antennas (one row block of 128 columns)."""
+    K, N, B, snr = 5, 64, 400, 5
+    means, covs, w = orc.random_psd_gmm(K, N, seed=21, mean_scale=0.1)
+    h, _, _ = orc.sample_gmm_channels(means, covs, w, B, seed=22)
+    A = np.kron(np.array([[1.0], [1j]]), np.eye(N))
+    noise = orc.crandn(B, 2 * N, rng=np.random.default_rng(23))
+    r = orc.get_observation_nbit(h, snr, noise, A, 1)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    rt = torch.from_numpy(r).cuda()
+    _check_modes(lambda mode: m.estimate_from_y(rt, snr, N, A=A, n_summands_or_proba=mode).cpu().numpy(),
+                 lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, snr, A=A, n_summands_or_proba=mode, n_bits=1), B)
+
+
+def test_tc_split_path_mfa_config4_shape(qce):
+    """MFA, N = 128, latent 16, 2-bit uniform (BASELINE config 4 with fewer components) through the dense tensor-core path."""
+    K, N, M, B, snr = 8, 128, 16, 300, 10
+    means, lambdas, psis, amps = orc.random_mfa(K, N, M, seed=5, mean_scale=0.1)
+    covs = orc.mofa_covs(lambdas, psis)
+    qz = orc.get_quantizer([snr], 2, 'uniform')[snr]
+    h, noise, _ = orc.sample_gmm_channels(means, covs, amps, B, seed=6)
+    r = orc.get_observation_nbit(h, snr, noise, None, 2, qz[0], qz[1])
+    mf = qce.Mofa(K, M, verbose=False).set_parameters(means, lambdas, psis, amps)
+    mf.use_structure = False
+    mf.precision = 'tc'
+    rt = torch.from_numpy(r).cuda()
+    _check_modes(lambda mode: mf.estimate_from_y(rt, snr, n_summands_or_proba=mode, n_bits=2, quantizer=qz).cpu().numpy(),
+                 lambda mode: orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba=mode, n_bits=2, quantizer=qz), B)
+
+
 def test_tc_single_component_and_many_components(qce):
     for K, N in ((1, 64), (130, 16)):
         means, covs, w, h, noise, qz, r = _case(K, N, 300, 10, 1, 'uniform', 0.0, seed=K)

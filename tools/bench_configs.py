@@ -72,6 +72,23 @@ def main():
     r = pilots(1 << 15, 128, 2, qz)
     ms = timeit(lambda: mf.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=2, quantizer_type='uniform', quantizer=qz))
     out.append(dict(config='C4 MFA N=128 K=64 M=16 2-bit uniform', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='woodbury fp64'))
+    # C4 through the dense tensor-core split path (whitening launch -> selection -> two row-block launches)
+    mf.use_structure = False
+    mf.precision = 'tc'
+    r = pilots(1 << 19, 128, 2, qz)
+    for mode in ('all', 1):
+        ms = timeit(lambda: mf.estimate_from_y(r, snr, n_summands_or_proba=mode, n_bits=2, quantizer_type='uniform', quantizer=qz))
+        out.append(dict(config=f'C4 MFA N=128 K=64 M=16 2-bit uniform mode={mode}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
+                        path='dense tc split', tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9,
+                        tflops_woodbury_equiv=(32 * 64 * 128 * 16 + 8 * 64 * 16 * 16) * r.shape[0] / ms / 1e9))
+    # GMM full, 1 bit, N=128, K=64 (same kernels)
+    means, covs, w = orc.random_psd_gmm(64, 128, seed=0)
+    m = qce.Gmm_nbit(n_components=64).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    r = pilots(1 << 19, 128, 1, (None, None))
+    ms = timeit(lambda: m.estimate_from_y(r, snr, 128, n_summands_or_proba='all'))
+    out.append(dict(config='GMM full 1-bit N=128 K=64', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='dense tc split',
+                    tflops_algorithmic=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9))
     for o in out:
         print(json.dumps(o), flush=True)
 
