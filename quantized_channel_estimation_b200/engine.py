@@ -27,6 +27,15 @@ def parse_mode(n_summands_or_proba):
     return _lib.MODE_CUMPROB, 0, float(x)
 
 
+def tc_shape_ok(n_obs, n_ant):
+    """Shapes the tensor-core kernels are instantiated for (mirrors tc_instantiated / tc_split_shape in qce_dense_tc.cu)."""
+    if n_obs % 16 or n_ant % 16:
+        return False
+    if n_obs <= 64 and n_ant <= 64:
+        return n_obs == n_ant or (n_obs, n_ant) in ((64, 32), (32, 16))
+    return (n_obs, n_ant) in ((128, 64), (128, 128), (96, 48), (96, 96))
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

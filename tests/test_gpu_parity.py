@@ -291,6 +291,7 @@ def test_mfa_woodbury_vs_dense_oracle(qce, K, N, M, nb, qt, ms):
     h, noise, _ = orc.sample_gmm_channels(means, covs, amps, B, seed=4)
     r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
     m = qce.Mofa(K, M, verbose=False).set_parameters(means, lam, psi, amps)
+    m.precision = 'fp64'              # complex128 path: the Woodbury kernel ('auto' prefers the tensor-core kernels on grid data)
     assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), MfaModel)
     for mode in ('all', 1, 2, 0.9):
         ref, aux = orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
@@ -300,6 +301,15 @@ def test_mfa_woodbury_vs_dense_oracle(qce, K, N, M, nb, qt, ms):
     np.testing.assert_allclose(m.predict_proba(r), aux['proba'], rtol=1e-8, atol=1e-300)
     # 1 bit destroys the low-rank structure: dense path
     assert isinstance(m._prepared(np.eye(N), snr, 1, 'uniform', (None, None, None)), DenseModel)
+    # 'auto': pilots on a uniform grid and a tensor-core shape go to the dense tcgen05 kernels, everything else stays Woodbury
+    m.precision = 'auto'
+    from quantized_channel_estimation_b200.engine import tc_shape_ok
+    on_grid = qt == 'uniform' and np.isfinite(nb)
+    assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), DenseModel if (on_grid and tc_shape_ok(N, N)) else MfaModel)
+    if on_grid and tc_shape_ok(N, N):
+        ref = orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+        est = m.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+        assert relerr(est, ref) < TOL_TC
 
 
 # ----------------------------------------------------------------------------- fit -> estimate end to end
