@@ -38,6 +38,8 @@ _SIGS = {
     'qce_circ_model_set_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qce_circ_estimate': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    'qce_circ_estimate_prec': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'qce_mfa_model_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     'qce_mfa_model_destroy': (None, [C.c_void_p]),
     'qce_mfa_model_set_params': (C.c_int, [C.c_void_p] * 9),

@@ -270,6 +270,7 @@ qce_status qce_circ_model_create(int n1, int n2, int n_comp, int flags, qce_circ
 
 void qce_circ_model_destroy(qce_circ_model* m) {
     if (!m) return;
+    circ_tc_free(m);
     cudaFree(m->inv_lambda_t); cudaFree(m->gain); cudaFree(m->logc);
     delete m;
 }
@@ -282,15 +283,23 @@ qce_status qce_circ_model_set_params(qce_circ_model* m, void* stream, const doub
     QCE_CUDA_TRY(cudaMemcpyAsync(m->gain, gain, N * K * 8, cudaMemcpyDeviceToDevice, s));
     QCE_CUDA_TRY(cudaMemcpyAsync(m->logc, logc, K * 8, cudaMemcpyDeviceToDevice, s));
     m->params_set = true;
-    return QCE_OK;
+    return circ_tc_pack(m, s);
+}
+
+qce_status qce_circ_estimate_prec(qce_circ_model* m, void* stream, const void* r, int64_t B, int mode, int n_top, double rho, int precision,
+                                  void* h_est, double* logp_out, const void* h_true, double* acc) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && !r)) { set_error("qce_circ_estimate: invalid argument"); return QCE_ERR_INVALID; }
+    qce_status st = check_mode(mode, n_top, rho, m->n_comp);
+    if (st) return st;
+    if (precision == QCE_PREC_TC)
+        return launch_circ_tc(m, (cudaStream_t)stream, (const double*)r, B, mode, n_top, rho, (double*)h_est, logp_out, (const double*)h_true, acc);
+    if (precision != QCE_PREC_FP64) { set_error("unknown precision %d", precision); return QCE_ERR_INVALID; }
+    return launch_circ(m, (cudaStream_t)stream, (const double*)r, B, mode, n_top, rho, (double*)h_est, logp_out, (const double*)h_true, acc);
 }
 
 qce_status qce_circ_estimate(qce_circ_model* m, void* stream, const void* r, int64_t B, int mode, int n_top, double rho, void* h_est,
                              double* logp_out, const void* h_true, double* acc) {
-    if (!m || !m->params_set || B < 0 || (B > 0 && !r)) { set_error("qce_circ_estimate: invalid argument"); return QCE_ERR_INVALID; }
-    qce_status st = check_mode(mode, n_top, rho, m->n_comp);
-    if (st) return st;
-    return launch_circ(m, (cudaStream_t)stream, (const double*)r, B, mode, n_top, rho, (double*)h_est, logp_out, (const double*)h_true, acc);
+    return qce_circ_estimate_prec(m, stream, r, B, mode, n_top, rho, QCE_PREC_FP64, h_est, logp_out, h_true, acc);
 }
 
 qce_status qce_mfa_model_create(int n_ant, int latent, int n_comp, int flags, qce_mfa_model** out) {

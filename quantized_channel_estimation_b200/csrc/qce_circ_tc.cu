@@ -1,0 +1,472 @@
+// Block-circulant (16 x 16) Bussgang-GMM estimate kernel, FP32 + tensor-core version of qce_circ.cu (QCE_PREC_TC).
+//
+// Same maths as circ_kernel (C_h,k = F^H diag(c_k) F, F = F_16 (x) F_16, A = I, zero means):
+//     rt = F r        l_k = logc_k - sum_i |rt_i|^2 / lambda_k,i        h = F^H [ (sum_k w_k(l) g_k) .* rt ]
+// The roofline of this path is HBM (32 N bytes of complex128 I/O per pilot); to get there the side work
+// must leave the FP64 pipe:
+//   * the two 2-D DFTs run as radix-4 FFTs in FP32 registers (one thread per 16-point transform), rows fused into the global
+//     load / store, columns through a XOR-swizzled shared-memory tile;
+//   * the two [N x K] real contractions run on the tensor cores as split-FP16 GEMMs (mma.sync m16n8k16, FP32 accumulation):
+//     both operands are computed data, so each is a (hi, lo) FP16 pair and a product is three MMAs (hi*hi + lo*hi + hi*lo,
+//     ~22 significant bits).  |rt|^2 is scaled per pilot by a power of two (Parseval bounds it), the parameter matrices by a
+//     global power of two fixed at set_params time.  The constant operands are pre-packed in mma fragment order (one 16-byte
+//     load per lane per 8 x 16 block, hi and lo together) and stream from L2.
+// One CTA = 32 pilots, 256 threads, ~100 KB shared memory -> two CTAs per SM overlap each other's load / compute / store phases.
+// Any real-valued pilots are accepted (no grid assumption: Lloyd-Max labels, infinite resolution).
+#include "qce_common.cuh"
+
+namespace qce {
+
+namespace {
+
+constexpr int CT_P = 32;             // pilots per CTA
+constexpr int CT_N = 256;            // bins (16 x 16)
+constexpr int CT_EP = CT_N + 8;      // pitch (halves) of the |rt|^2 operand rows: 528 B = odd multiple of 16 B (ldmatrix conflict-free)
+constexpr int CT_R_BYTES = 34816;    // operand region: E hi/lo, later log-probabilities | weight hi/lo
+constexpr float CT_WSCALE = 1024.f;  // weights (<= 1) are scaled into the FP16 normal range
+
+struct CircTcArgs {
+    int K;
+    int64_t B;
+    const uint4* b1;                 // packed 1/lambda fragments  [K/8][16][32]
+    const uint4* b2;                 // packed gain fragments      [32][K/16][32]
+    const float2* logc2;             // [K] logc as (hi, lo)
+    float inv_s1, inv_s2;            // 2^-s of the packed operands
+    const double2* r;
+    double2* h_est;
+    double* logp_out;
+    const double2* h_true;
+    double* acc;
+    int mode, n_top, flags;
+    double rho;
+};
+
+__device__ __forceinline__ float2 operator+(const float2 a, const float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator-(const float2 a, const float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// a * (-i) for the forward transform, a * (+i) for the inverse
+template <bool INV>
+__device__ __forceinline__ float2 rot90(const float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+// a * (c -+ i s)
+template <bool INV>
+__device__ __forceinline__ float2 twid(const float2 a, const float c, const float s) {
+    return INV ? make_float2(a.x * c - a.y * s, a.y * c + a.x * s) : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+    const float2 s0 = a + c, s1 = a - c, s2 = b + d, s3 = rot90<INV>(b - d);
+    a = s0 + s2; b = s1 + s3; c = s0 - s2; d = s1 - s3;
+}
+// 16-point DFT in registers (radix 4, decimation in time), scaled by 1/4 (unitary); in and out in natural order
+template <bool INV>
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+    #pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) dft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);      // over n1: position 4 k1 + n2
+    // twiddles W16^(n2 k1)
+    v[4 + 1] = twid<INV>(v[4 + 1], C1, S1);   v[4 + 2] = twid<INV>(v[4 + 2], C2, C2);     v[4 + 3] = twid<INV>(v[4 + 3], S1, C1);
+    v[8 + 1] = twid<INV>(v[8 + 1], C2, C2);   v[8 + 2] = rot90<INV>(v[8 + 2]);            v[8 + 3] = twid<INV>(v[8 + 3], -C2, C2);
+    v[12 + 1] = twid<INV>(v[12 + 1], S1, C1); v[12 + 2] = twid<INV>(v[12 + 2], -C2, C2);  v[12 + 3] = twid<INV>(v[12 + 3], -C1, -S1);
+    #pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft4<INV>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);   // over n2: X[k1 + 4 k2] at 4 k1 + k2
+    float2 o[16];
+    #pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1)
+        #pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) o[k1 + 4 * k2] = v[4 * k1 + k2];
+    #pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = make_float2(o[i].x * 0.25f, o[i].y * 0.25f);
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_half(const float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+// KNB = K / 64: GEMM 1 gives each of the 8 warps KNB 8-component blocks
+template <int KNB>
+__global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
+    constexpr int K = 64 * KNB;
+    constexpr int LP = K + 4;                  // pitch (floats) of the log-probability rows
+    constexpr int WP = K + 8;                  // pitch (halves) of the weight operand rows
+    static_assert(CT_P * LP * 4 + 2 * CT_P * WP * 2 <= CT_R_BYTES, "operand region");
+    static_assert(2 * CT_P * CT_EP * 2 <= CT_R_BYTES, "operand region");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* X = reinterpret_cast<float2*>(smem_raw);                               // [32][16][16], column index XOR row index
+    unsigned char* R = smem_raw + CT_P * CT_N * sizeof(float2);
+    __half* Ehi = reinterpret_cast<__half*>(R);
+    __half* Elo = Ehi + CT_P * CT_EP;
+    float* lbuf = reinterpret_cast<float*>(R);                                     // aliases E (dead after GEMM 1)
+    __half* Whi = reinterpret_cast<__half*>(R + CT_P * LP * 4);
+    __half* Wlo = Whi + CT_P * WP;
+    float* invsc = reinterpret_cast<float*>(R + CT_R_BYTES);                       // [32] 1 / per-pilot scale of |rt|^2
+    double* red = reinterpret_cast<double*>(R + CT_R_BYTES + 128);                 // [2]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t base = (int64_t)blockIdx.x * CT_P;
+    const int nvalid = (int)((a.B - base) < CT_P ? (a.B - base) : CT_P);
+    if (tid < 2) red[tid] = 0.0;
+
+    // ---- load + forward FFT along the contiguous axis (thread = one row of 16 bins of one pilot)
+    #pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
+        float2 v[16];
+        if (p < nvalid) {
+            const double2* src = a.r + ((base + p) * CT_N + ar * 16);
+            #pragma unroll
+            for (int b = 0; b < 16; ++b) { const double2 d = __ldcs(src + b); v[b] = make_float2((float)d.x, (float)d.y); }
+        } else {
+            #pragma unroll
+            for (int b = 0; b < 16; ++b) v[b] = make_float2(0.f, 0.f);
+        }
+        fft16<false>(v);
+        #pragma unroll
+        for (int b = 0; b < 16; ++b) X[(p * 16 + ar) * 16 + (b ^ ar)] = v[b];
+    }
+    __syncthreads();
+
+    // ---- forward FFT along the block axis (thread = one column), |rt|^2 as per-pilot scaled FP16 (hi, lo)
+    #pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = tid + 256 * j, p = idx >> 4, b = idx & 15;
+        float2 v[16];
+        #pragma unroll
+        for (int ar = 0; ar < 16; ++ar) v[ar] = X[(p * 16 + ar) * 16 + (b ^ ar)];
+        fft16<false>(v);
+        float e[16], psum = 0.f;
+        #pragma unroll
+        for (int ar = 0; ar < 16; ++ar) {
+            X[(p * 16 + ar) * 16 + (b ^ ar)] = v[ar];
+            e[ar] = v[ar].x * v[ar].x + v[ar].y * v[ar].y;
+            psum += e[ar];
+        }
+        #pragma unroll
+        for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);     // the 16 columns of pilot p
+        int ex = 0;
+        float sc = 1.f;
+        if (psum > 0.f && psum < 3.0e38f) { frexpf(psum, &ex); sc = ldexpf(1.f, 14 - ex); }         // every e * sc < 2^14
+        if (b == 0) invsc[p] = 1.f / sc;
+        #pragma unroll
+        for (int ar = 0; ar < 16; ++ar) {
+            __half hi, lo;
+            split_half(e[ar] * sc, hi, lo);
+            Ehi[p * CT_EP + ar * 16 + b] = hi;
+            Elo[p * CT_EP + ar * 16 + b] = lo;
+        }
+    }
+    __syncthreads();
+
+    // ---- GEMM 1: q[p][k] = sum_i E[p][i] / lambda[k][i]   (warp: 32 pilots x KNB blocks of 8 components)
+    const int g = lane >> 2, t4 = lane & 3;
+    {
+        float acc[2][KNB][4];
+        #pragma unroll
+        for (int m = 0; m < 2; ++m)
+            #pragma unroll
+            for (int n = 0; n < KNB; ++n)
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) acc[m][n][c] = 0.f;
+        const uint4* bp = a.b1 + ((size_t)(warp * KNB) * 16) * 32 + lane;
+        #pragma unroll 4
+        for (int ks = 0; ks < CT_N / 16; ++ks) {
+            uint32_t ah[2][4], al[2][4];
+            #pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int off = (m * 16 + (lane & 15)) * CT_EP + ks * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(ah[m], Ehi + off);
+                ldmatrix_x4(al[m], Elo + off);
+            }
+            #pragma unroll
+            for (int n = 0; n < KNB; ++n) {
+                const uint4 bv = __ldg(bp + ((size_t)n * 16 + ks) * 32);
+                #pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    mma16816(acc[m][n], ah[m], bv.x, bv.y);
+                    mma16816(acc[m][n], al[m], bv.x, bv.y);
+                    mma16816(acc[m][n], ah[m], bv.z, bv.w);
+                }
+            }
+        }
+        __syncthreads();                       // every warp is done with E: its space becomes the log-probability rows
+        #pragma unroll
+        for (int m = 0; m < 2; ++m)
+            #pragma unroll
+            for (int n = 0; n < KNB; ++n) {
+                const int k = (warp * KNB + n) * 8 + 2 * t4;
+                const float2 lc0 = __ldg(a.logc2 + k), lc1 = __ldg(a.logc2 + k + 1);
+                #pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int p = m * 16 + g + 8 * hh;
+                    const float s = invsc[p] * a.inv_s1;
+                    const float l0 = (lc0.x - acc[m][n][2 * hh] * s) + lc0.y, l1 = (lc1.x - acc[m][n][2 * hh + 1] * s) + lc1.y;
+                    *reinterpret_cast<float2*>(lbuf + p * LP + k) = make_float2(l0, l1);
+                }
+            }
+    }
+    __syncthreads();
+
+    // ---- combination weights per pilot
+    if (a.logp_out) {
+        for (int o = tid; o < nvalid * K; o += 256) a.logp_out[base * K + o] = (double)lbuf[(o / K) * LP + (o % K)];
+        __syncthreads();
+    }
+    if (a.mode == QCE_MODE_ALL) {
+        #pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            const int p = warp * 4 + pp;
+            float v[K / 32], mx = -INFINITY;
+            #pragma unroll
+            for (int j = 0; j < K / 32; ++j) { v[j] = lbuf[p * LP + lane + 32 * j]; mx = fmaxf(mx, v[j]); }
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            float sum = 0.f;
+            #pragma unroll
+            for (int j = 0; j < K / 32; ++j) { v[j] = expf(v[j] - mx); sum += v[j]; }
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            const float inv = CT_WSCALE / sum;
+            #pragma unroll
+            for (int j = 0; j < K / 32; ++j) {
+                __half hi, lo;
+                split_half(v[j] * inv, hi, lo);
+                Whi[p * WP + lane + 32 * j] = hi;
+                Wlo[p * WP + lane + 32 * j] = lo;
+            }
+        }
+    } else {
+        if (tid < CT_P) weights_from_logp(lbuf + tid * LP, K, a.mode, a.n_top, a.rho, a.flags);
+        __syncthreads();
+        for (int o = tid; o < CT_P * K; o += 256) {
+            const int p = o / K, k = o % K;
+            __half hi, lo;
+            split_half(lbuf[p * LP + k] * CT_WSCALE, hi, lo);
+            Whi[p * WP + k] = hi;
+            Wlo[p * WP + k] = lo;
+        }
+    }
+    __syncthreads();
+
+    // ---- GEMM 2: G[p][i] = sum_k w[p][k] g[k][i]   (warp: 32 pilots x 4 blocks of 8 bins), rt <- G .* rt
+    if (a.h_est || a.acc) {
+        float acc[2][4][4];
+        #pragma unroll
+        for (int m = 0; m < 2; ++m)
+            #pragma unroll
+            for (int n = 0; n < 4; ++n)
+                #pragma unroll
+                for (int c = 0; c < 4; ++c) acc[m][n][c] = 0.f;
+        const uint4* bp = a.b2 + ((size_t)(warp * 4) * (K / 16)) * 32 + lane;
+        #pragma unroll 2
+        for (int ks = 0; ks < K / 16; ++ks) {
+            uint32_t ah[2][4], al[2][4];
+            #pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int off = (m * 16 + (lane & 15)) * WP + ks * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(ah[m], Whi + off);
+                ldmatrix_x4(al[m], Wlo + off);
+            }
+            #pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const uint4 bv = __ldg(bp + ((size_t)n * (K / 16) + ks) * 32);
+                #pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    mma16816(acc[m][n], ah[m], bv.x, bv.y);
+                    mma16816(acc[m][n], al[m], bv.x, bv.y);
+                    mma16816(acc[m][n], ah[m], bv.z, bv.w);
+                }
+            }
+        }
+        const float gs = a.inv_s2 / CT_WSCALE;
+        #pragma unroll
+        for (int m = 0; m < 2; ++m)
+            #pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int bin = (warp * 4 + n) * 8 + 2 * t4, ar = bin >> 4, b = bin & 15;
+                #pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int p = m * 16 + g + 8 * hh;
+                    float2* x0 = X + (p * 16 + ar) * 16 + (b ^ ar);
+                    float2* x1 = X + (p * 16 + ar) * 16 + ((b + 1) ^ ar);
+                    const float g0 = acc[m][n][2 * hh] * gs, g1 = acc[m][n][2 * hh + 1] * gs;
+                    *x0 = make_float2(x0->x * g0, x0->y * g0);
+                    *x1 = make_float2(x1->x * g1, x1->y * g1);
+                }
+            }
+        __syncthreads();
+
+        // ---- inverse FFT along the block axis
+        #pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = tid + 256 * j, p = idx >> 4, b = idx & 15;
+            float2 v[16];
+            #pragma unroll
+            for (int ar = 0; ar < 16; ++ar) v[ar] = X[(p * 16 + ar) * 16 + (b ^ ar)];
+            fft16<true>(v);
+            #pragma unroll
+            for (int ar = 0; ar < 16; ++ar) X[(p * 16 + ar) * 16 + (b ^ ar)] = v[ar];
+        }
+        __syncthreads();
+
+        // ---- inverse FFT along the contiguous axis fused into the store, NMSE accumulators
+        float errf = 0.f, pwf = 0.f;
+        #pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
+            float2 v[16];
+            #pragma unroll
+            for (int b = 0; b < 16; ++b) v[b] = X[(p * 16 + ar) * 16 + (b ^ ar)];
+            fft16<true>(v);
+            if (p < nvalid) {
+                const size_t o = (size_t)(base + p) * CT_N + ar * 16;
+                if (a.h_est) {
+                    #pragma unroll
+                    for (int b = 0; b < 16; ++b) __stcs(a.h_est + o + b, make_double2((double)v[b].x, (double)v[b].y));
+                }
+                if (a.acc && a.h_true) {
+                    #pragma unroll
+                    for (int b = 0; b < 16; ++b) {
+                        const double2 h = __ldcs(a.h_true + o + b);
+                        const float hx = (float)h.x, hy = (float)h.y, dx = v[b].x - hx, dy = v[b].y - hy;
+                        errf = fmaf(dx, dx, fmaf(dy, dy, errf));
+                        pwf = fmaf(hx, hx, fmaf(hy, hy, pwf));
+                    }
+                }
+            }
+        }
+        if (a.acc) {
+            double err = (double)errf, pw = (double)pwf;
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                err += __shfl_xor_sync(0xffffffffu, err, off);
+                pw += __shfl_xor_sync(0xffffffffu, pw, off);
+            }
+            if (lane == 0) { atomicAdd(&red[0], err); atomicAdd(&red[1], pw); }
+            __syncthreads();
+            if (tid == 0) { atomicAdd(a.acc + 0, red[0]); atomicAdd(a.acc + 1, red[1]); atomicAdd(a.acc + 2, (double)nvalid); }
+        }
+    }
+}
+
+// Constant operands in mma.m16n8k16 B-fragment order.  Thread (g = lane / 4, t = lane % 4) of block (nb, ks) holds
+// b0 = {B[16 ks + 2t][8 nb + g], B[16 ks + 2t + 1][.]}, b1 = the same 8 rows further; stored as uint4 {b0 hi, b1 hi, b0 lo, b1 lo}.
+// which = 0: B[i][k] = 1 / lambda (source inv_lambda_t [N][K]),  which = 1: B[k][i] = gain (source gain [K][N]).
+__global__ void circ_tc_pack_kernel(const double* __restrict__ src, int rows, int cols, double scale, uint4* __restrict__ out) {
+    const int nks = rows / 16, nnb = cols / 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nnb * nks * 32) return;
+    const int lane = idx & 31, ks = (idx >> 5) % nks, nb = (idx >> 5) / nks;
+    const int g = lane >> 2, t = lane & 3, col = nb * 8 + g;
+    __half hi[4], lo[4];
+    #pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int row = ks * 16 + 2 * t + (e & 1) + 8 * (e >> 1);
+        const double x = src[(size_t)row * cols + col] * scale;
+        hi[e] = __double2half(x);
+        lo[e] = __double2half(x - (double)__half2float(hi[e]));
+    }
+    auto pack = [](__half a0, __half a1) { return (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(a1) << 16); };
+    out[idx] = make_uint4(pack(hi[0], hi[1]), pack(hi[2], hi[3]), pack(lo[0], lo[1]), pack(lo[2], lo[3]));
+}
+
+__global__ void circ_tc_logc_kernel(const double* __restrict__ logc, int K, float2* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) { const double l = logc[k]; const float hi = (float)l; out[k] = make_float2(hi, (float)(l - (double)hi)); }
+}
+
+double pow2_scale_for(const double* dev, size_t n, cudaStream_t s, qce_status* st) {
+    // power of two that puts the largest magnitude into [2^12, 2^13)
+    double* host = (double*)malloc(n * sizeof(double));
+    *st = QCE_OK;
+    if (!host || cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        free(host);
+        set_error("circulant tensor-core pack: device read failed");
+        *st = QCE_ERR_CUDA;
+        return 1.0;
+    }
+    double mx = 0.0;
+    bool finite = true;
+    for (size_t i = 0; i < n; ++i) { const double v = fabs(host[i]); if (!(v < 1e300)) finite = false; if (v > mx) mx = v; }
+    free(host);
+    if (!finite || !(mx > 0.0)) return 0.0;
+    int ex = 0;
+    frexp(mx, &ex);
+    return ldexp(1.0, 13 - ex);
+}
+
+}  // namespace
+
+bool circ_tc_shape_ok(const qce_circ_model* m) { return m->n1 == 16 && m->n2 == 16 && (m->n_comp == 64 || m->n_comp == 128); }
+
+void circ_tc_free(qce_circ_model* m) {
+    cudaFree(m->tc_b1); cudaFree(m->tc_b2); cudaFree(m->tc_logc2);
+    m->tc_b1 = m->tc_b2 = m->tc_logc2 = nullptr;
+    m->tc_ready = false;
+}
+
+qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s) {
+    m->tc_ready = false;
+    if (!circ_tc_shape_ok(m)) return QCE_OK;
+    const size_t N = m->n_ant, K = m->n_comp;
+    qce_status st = QCE_OK;
+    const double s1 = pow2_scale_for(m->inv_lambda_t, N * K, s, &st);
+    if (st) return st;
+    const double s2 = pow2_scale_for(m->gain, N * K, s, &st);
+    if (st) return st;
+    if (!(s1 > 0.0) || !(s2 > 0.0)) return QCE_OK;                      // degenerate parameters: complex128 kernel only
+    const size_t frag_bytes = (N * K / 4) * sizeof(uint4);              // 4 values per lane entry, hi and lo: 16 B
+    if (!m->tc_b1) {
+        QCE_CUDA_TRY(cudaMalloc(&m->tc_b1, frag_bytes));
+        QCE_CUDA_TRY(cudaMalloc(&m->tc_b2, frag_bytes));
+        QCE_CUDA_TRY(cudaMalloc(&m->tc_logc2, K * sizeof(float2)));
+    }
+    const int total = (int)(N * K / 4);
+    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->inv_lambda_t, (int)N, (int)K, s1, (uint4*)m->tc_b1);
+    QCE_CHECK_LAUNCH("circ_tc_pack_kernel");
+    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->gain, (int)K, (int)N, s2, (uint4*)m->tc_b2);
+    QCE_CHECK_LAUNCH("circ_tc_pack_kernel");
+    circ_tc_logc_kernel<<<(unsigned)((K + 127) / 128), 128, 0, s>>>(m->logc, (int)K, (float2*)m->tc_logc2);
+    QCE_CHECK_LAUNCH("circ_tc_logc_kernel");
+    m->tc_inv_s1 = (float)(1.0 / s1);
+    m->tc_inv_s2 = (float)(1.0 / s2);
+    m->tc_ready = true;
+    return QCE_OK;
+}
+
+template <int KNB>
+static qce_status launch_circ_tc_k(const CircTcArgs& a, cudaStream_t s) {
+    constexpr size_t SMEM = CT_P * CT_N * sizeof(float2) + CT_R_BYTES + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QCE_CUDA_TRY(cudaFuncSetAttribute(circ_tc_kernel<KNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr_set = true;
+    }
+    circ_tc_kernel<KNB><<<(unsigned)((a.B + CT_P - 1) / CT_P), 256, SMEM, s>>>(a);
+    QCE_CHECK_LAUNCH("circ_tc_kernel");
+    return QCE_OK;
+}
+
+qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
+                          double* h_est, double* logp_out, const double* h_true, double* acc) {
+    if (!m->tc_ready) { set_error("circulant tensor-core kernel: n1=%d n2=%d K=%d not supported", m->n1, m->n2, m->n_comp); return QCE_ERR_UNSUPPORTED; }
+    if (B == 0) return QCE_OK;
+    CircTcArgs a;
+    a.K = m->n_comp; a.B = B;
+    a.b1 = (const uint4*)m->tc_b1; a.b2 = (const uint4*)m->tc_b2; a.logc2 = (const float2*)m->tc_logc2;
+    a.inv_s1 = m->tc_inv_s1; a.inv_s2 = m->tc_inv_s2;
+    a.r = (const double2*)r; a.h_est = (double2*)h_est; a.logp_out = logp_out; a.h_true = (const double2*)h_true; a.acc = acc;
+    a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;
+    return m->n_comp == 64 ? launch_circ_tc_k<1>(a, s) : launch_circ_tc_k<2>(a, s);
+}
+
+}  // namespace qce

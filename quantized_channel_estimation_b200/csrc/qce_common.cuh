@@ -78,6 +78,12 @@ struct qce_circ_model {
     double* gain = nullptr;           // [K][N]  b_k c_k / lambda_k
     double* logc = nullptr;           // [K]
     bool params_set = false;
+    // FP32 / tensor-core kernel (qce_circ_tc.cu): the two parameter matrices as FP16 (hi, lo) mma fragments
+    void* tc_b1 = nullptr;
+    void* tc_b2 = nullptr;
+    void* tc_logc2 = nullptr;
+    float tc_inv_s1 = 0.f, tc_inv_s2 = 0.f;
+    bool tc_ready = false;
 };
 
 struct qce_mfa_model {
@@ -110,8 +116,9 @@ struct qce_model {
 
 #ifdef __CUDACC__
 namespace qce {
-// Per-sample weights from weighted log-probabilities, in place (lp[k] -> w[k]).
-__device__ inline void weights_from_logp(double* lp, int K, int mode, int n_top, double rho, int flags) {
+// Per-sample weights from weighted log-probabilities, in place (lp[k] -> w[k]); T = double, or float for the FP32 kernels.
+template <typename T>
+__device__ inline void weights_from_logp(T* lp, int K, int mode, int n_top, double rho, int flags) {
     double mx = lp[0];
     int amax = 0;
     for (int k = 1; k < K; ++k)
@@ -119,13 +126,13 @@ __device__ inline void weights_from_logp(double* lp, int K, int mode, int n_top,
     if (mode == QCE_MODE_TOP1) {
         // gmm:349 argmax of the weighted log-prob; mofa:359-366 argmax of exp(.) -> 0 when all underflow
         if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
-        for (int k = 0; k < K; ++k) lp[k] = (k == amax) ? 1.0 : 0.0;
+        for (int k = 0; k < K; ++k) lp[k] = (k == amax) ? (T)1.0 : (T)0.0;
         return;
     }
     double sum = 0.0;
-    for (int k = 0; k < K; ++k) sum += exp(lp[k] - mx);
+    for (int k = 0; k < K; ++k) sum += exp((double)lp[k] - mx);
     const double lse = mx + log(sum);               // scipy.special.logsumexp (gmm:652) / _log_sum (mofa:394-400)
-    for (int k = 0; k < K; ++k) lp[k] = exp(lp[k] - lse);
+    for (int k = 0; k < K; ++k) lp[k] = (T)exp((double)lp[k] - lse);
     if (mode == QCE_MODE_ALL) return;
     // descending selection (np.argsort(p)[::-1], gmm:210 / :233); selected entries are marked by the sign bit
     const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
@@ -134,14 +141,14 @@ __device__ inline void weights_from_logp(double* lp, int K, int mode, int n_top,
         int best = -1;
         double bv = -1.0;
         for (int k = 0; k < K; ++k)
-            if (!signbit(lp[k]) && lp[k] > bv) { bv = lp[k]; best = k; }
+            if (!signbit(lp[k]) && (double)lp[k] > bv) { bv = (double)lp[k]; best = k; }
         if (best < 0) break;
-        lp[best] = -bv;
+        lp[best] = (T)(-bv);
         cum += bv;
         // searchsorted(cumsum, rho) + 1 (gmm:234): stop after the first prefix with cumsum >= rho
         if (mode == QCE_MODE_CUMPROB && cum >= rho) break;
     }
-    for (int k = 0; k < K; ++k) lp[k] = signbit(lp[k]) ? (-lp[k]) / cum : 0.0;
+    for (int k = 0; k < K; ++k) lp[k] = signbit(lp[k]) ? (T)((double)(-lp[k]) / cum) : (T)0.0;
 }
 
 }  // namespace qce
@@ -176,6 +183,12 @@ bool tc_supported(const qce_model* m, int mode);
 // qce_mfa.cu
 qce_status launch_mfa(const qce_mfa_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
                       double* h_est, double* logp_out, const double* h_true, double* acc);
+// qce_circ_tc.cu
+bool circ_tc_shape_ok(const qce_circ_model* m);
+qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s);
+void circ_tc_free(qce_circ_model* m);
+qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
+                          double* h_est, double* logp_out, const double* h_true, double* acc);
 // qce_circ.cu
 qce_status launch_circ(const qce_circ_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
                        double* h_est, double* logp_out, const double* h_true, double* acc);

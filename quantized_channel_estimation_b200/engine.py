@@ -255,8 +255,7 @@ class CircModel:
             h_true = _as_c128_cuda(h_true, 'h_true')
             acc = torch.zeros(3, dtype=torch.float64, device=r.device)
         with torch.cuda.device(r.device):
-            _lib.check(self._estimate_fn()(self.handle, _stream(), _ptr(r), B, mode, n_top, rho, _ptr(h_est), _ptr(logp),
-                                           _ptr(h_true), _ptr(acc)))
+            self._run(precision, (_stream(), _ptr(r), B, mode, n_top, rho), (_ptr(h_est), _ptr(logp), _ptr(h_true), _ptr(acc)))
         out = (h_est,)
         if want_logp:
             out += (logp,)
@@ -264,12 +263,22 @@ class CircModel:
             out += (acc,)
         return out if len(out) > 1 else h_est
 
-    def _estimate_fn(self):
-        return _lib.load().qce_circ_estimate
+    def _run(self, precision, head, tail):
+        """'fp64': complex128 kernel; 'tc': FP32-FFT / tensor-core kernel (16 x 16 blocks, K = 64 or 128); 'auto': the latter
+        when the shape is supported."""
+        lib = _lib.load()
+        if precision not in ('fp64', 'tc', 'auto'):
+            raise ValueError(f'unknown precision {precision!r}')
+        if precision != 'fp64':
+            st = lib.qce_circ_estimate_prec(self.handle, *head, _lib.PREC_TC, *tail)
+            if not (st == _lib.ERR_UNSUPPORTED and precision == 'auto'):
+                _lib.check(st)
+                return
+        _lib.check(lib.qce_circ_estimate_prec(self.handle, *head, _lib.PREC_FP64, *tail))
 
     def estimate_host(self, r, n_summands_or_proba='all', precision='auto'):
         rt = torch.from_numpy(np.ascontiguousarray(np.asarray(r, dtype=np.complex128))).to(self.device)
-        return self.estimate(rt, n_summands_or_proba).cpu().numpy()
+        return self.estimate(rt, n_summands_or_proba, precision).cpu().numpy()
 
 
 class MfaModel(CircModel):
@@ -296,5 +305,7 @@ class MfaModel(CircModel):
         except Exception:
             pass
 
-    def _estimate_fn(self):
-        return _lib.load().qce_mfa_estimate
+    def _run(self, precision, head, tail):          # complex128 only
+        if precision not in ('fp64', 'tc', 'auto'):
+            raise ValueError(f'unknown precision {precision!r}')
+        _lib.check(_lib.load().qce_mfa_estimate(self.handle, *head, *tail))

@@ -273,6 +273,46 @@ def test_circulant_kernel_vs_dense_oracle(qce, n1, n2, K, nb, qt, tol):
     assert relerr(m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz), dense) < max(tol, 1e-5)
 
 
+@pytest.mark.parametrize('K,nb,qt,B', [
+    (128, 3, 'lloyd', 150),          # config 3: 256 antennas, 16x16 blocks, 3-bit Lloyd-Max, K = 128 (ragged batch)
+    (64, 1, 'uniform', 97),
+    (64, np.inf, 'uniform', 33),     # unquantised pilots: no grid assumption in this kernel
+])
+def test_circulant_tc_kernel_vs_dense_oracle(qce, K, nb, qt, B):
+    """FP32-FFT + split-FP16 tensor-core version of the DFT-domain kernel against the oracle's dense path."""
+    from quantized_channel_estimation_b200.engine import CircModel
+    n1 = n2 = 16
+    N, snr = 256, 8
+    c, covs, w, F = orc.circulant_gmm(K, n1, n2, seed=K)
+    h, noise, _ = orc.sample_gmm_channels(np.zeros((K, N), complex), covs, w, B, seed=5)
+    qz = orc.get_quantizer([snr], nb, qt)[snr] if np.isfinite(nb) else (None, None, None)
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
+    m.set_circulant_parameters(c, w, (n1, n2))
+    model = m._prepared(np.eye(N), snr, nb, qt, qz)
+    assert isinstance(model, CircModel)
+    rt = torch.from_numpy(r).cuda()
+    for mode in ('all', 1, 3, 0.9):
+        ref = orc.gmm_estimate_from_y(np.zeros((K, N)), covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
+                                      quantizer=qz)
+        est = model.estimate(rt, mode, 'tc').cpu().numpy()
+        assert est.shape == (B, N) and np.isfinite(est.view(np.float64)).all()
+        if mode == 'all':
+            assert relerr(est, ref) < TOL_TC, relerr(est, ref)
+        else:
+            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert np.mean(per > 1e-4) <= 0.02 + 1.0 / B, (mode, np.sort(per)[-5:])
+    # log-probabilities, NMSE accumulators, agreement with the complex128 kernel; 'auto' picks the fast kernel
+    est64, lp64 = model.estimate(rt, 'all', 'fp64', want_logp=True)
+    est_tc, lp_tc, acc = model.estimate(rt, 'all', 'auto', want_logp=True, h_true=torch.from_numpy(h).cuda())
+    assert relerr(est_tc.cpu().numpy(), est64.cpu().numpy()) < TOL_TC
+    assert float((lp_tc - lp64).abs().max()) < 2e-3 * max(1.0, float(lp64.abs().max()) / 300)
+    acc = acc.cpu().numpy()
+    assert acc[2] == B
+    np.testing.assert_allclose(acc[0], np.sum(np.abs(est_tc.cpu().numpy() - h) ** 2), rtol=1e-4)
+    np.testing.assert_allclose(acc[1], np.sum(np.abs(h) ** 2), rtol=1e-4)
+
+
 # ----------------------------------------------------------------------------- MFA Woodbury kernel
 
 @pytest.mark.parametrize('K,N,M,nb,qt,ms', [

@@ -61,10 +61,10 @@ def main():
     m = qce.Gmm_nbit(n_components=128, covariance_type='block-circulant')
     m.covs_cplx = None
     m.set_circulant_parameters(c, w, (16, 16))
-    r = pilots(1 << 17, 256, 3, qz)
+    r = pilots(1 << 19, 256, 3, qz)
     ms = timeit(lambda: m.estimate_from_y(r, snr, 256, n_summands_or_proba='all', n_bits=3, quantizer_type='lloyd', quantizer=qz))
     out.append(dict(config='C3 GMM block-circulant 16x16 3-bit Lloyd N=256 K=128', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
-                    path='circ fp64', gbytes_per_s=32 * 256 * r.shape[0] / ms / 1e6))
+                    path='circ tc (fp32 fft + split-fp16 mma)', gbytes_per_s=32 * 256 * r.shape[0] / ms / 1e6))
     # C4: MFA N=128, K=64, latent 16, 2-bit uniform (dense path, as the reference computes it)
     means, lambdas, psis, amps = orc.random_mfa(64, 128, 16, seed=0)
     qz = qce.get_quantizer([snr], 2, 'uniform')[snr]
