@@ -4,8 +4,9 @@
 //     rt = F r        l_k = logc_k - sum_i |rt_i|^2 / lambda_k,i        h = F^H [ (sum_k w_k(l) g_k) .* rt ]
 // The roofline of this path is HBM (32 N bytes of complex128 I/O per pilot); to get there the side work
 // must leave the FP64 pipe:
-//   * the two 2-D DFTs run as radix-4 FFTs in FP32 registers (one thread per 16-point transform), rows fused into the global
-//     load / store, columns through a XOR-swizzled shared-memory tile;
+//   * the two 2-D DFTs run as radix-4 FFTs in FP32 registers (one thread per 16-point transform): the block axis fused into
+//     the coalesced global load / store (16 lanes = 256 contiguous bytes), the contiguous axis through a pair-swizzled
+//     shared-memory tile (row owners use 128-bit, column owners 64-bit accesses, both bank-conflict free);
 //   * the two [N x K] real contractions run on the tensor cores as split-FP16 GEMMs (mma.sync m16n8k16, FP32 accumulation):
 //     both operands are computed data, so each is a (hi, lo) FP16 pair and a product is three MMAs (hi*hi + lo*hi + hi*lo,
 //     ~22 significant bits).  |rt|^2 is scaled per pilot by a power of two (Parseval bounds it), the parameter matrices by a
@@ -23,6 +24,8 @@ constexpr int CT_P = 32;             // pilots per CTA
 constexpr int CT_N = 256;            // bins (16 x 16)
 constexpr int CT_EP = CT_N + 8;      // pitch (halves) of the |rt|^2 operand rows: 528 B = odd multiple of 16 B (ldmatrix conflict-free)
 constexpr int CT_R_BYTES = 34816;    // operand region: E hi/lo, later log-probabilities | weight hi/lo
+constexpr int CT_XP = CT_N + 8;      // pitch (float2) of one pilot's rt tile: 2112 B = 64 mod 128, so that the float4 updates of
+                                     // two pilots (GEMM 2 epilogue) fall into different halves of the 32 banks
 constexpr float CT_WSCALE = 1024.f;  // weights (<= 1) are scaled into the FP16 normal range
 
 struct CircTcArgs {
@@ -102,8 +105,8 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
     static_assert(CT_P * LP * 4 + 2 * CT_P * WP * 2 <= CT_R_BYTES, "operand region");
     static_assert(2 * CT_P * CT_EP * 2 <= CT_R_BYTES, "operand region");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* X = reinterpret_cast<float2*>(smem_raw);                               // [32][16][16], column index XOR row index
-    unsigned char* R = smem_raw + CT_P * CT_N * sizeof(float2);
+    float2* X = reinterpret_cast<float2*>(smem_raw);                               // [32][CT_XP]: 16 x 16 bins per pilot, swizzled
+    unsigned char* R = smem_raw + CT_P * CT_XP * sizeof(float2);
     __half* Ehi = reinterpret_cast<__half*>(R);
     __half* Elo = Ehi + CT_P * CT_EP;
     float* lbuf = reinterpret_cast<float*>(R);                                     // aliases E (dead after GEMM 1)
@@ -117,57 +120,67 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
     const int nvalid = (int)((a.B - base) < CT_P ? (a.B - base) : CT_P);
     if (tid < 2) red[tid] = 0.0;
 
-    // ---- load + forward FFT along the contiguous axis (thread = one row of 16 bins of one pilot)
-    #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
-        float2 v[16];
-        if (p < nvalid) {
-            const double2* src = a.r + ((base + p) * CT_N + ar * 16);
-            #pragma unroll
-            for (int b = 0; b < 16; ++b) { const double2 d = __ldcs(src + b); v[b] = make_float2((float)d.x, (float)d.y); }
-        } else {
-            #pragma unroll
-            for (int b = 0; b < 16; ++b) v[b] = make_float2(0.f, 0.f);
-        }
-        fft16<false>(v);
-        #pragma unroll
-        for (int b = 0; b < 16; ++b) X[(p * 16 + ar) * 16 + (b ^ ar)] = v[b];
-    }
-    __syncthreads();
+    // X element (pilot p, block row ar, column b): pairs of columns are XOR-swizzled with the row so that a thread owning a row
+    // (128-bit accesses) and a thread owning a column (64-bit accesses) are both bank-conflict free
+    auto xidx = [](int p, int ar, int b) { return p * CT_XP + ar * 16 + ((((b >> 1) ^ (ar & 7)) << 1) | (b & 1)); };
 
-    // ---- forward FFT along the block axis (thread = one column), |rt|^2 as per-pilot scaled FP16 (hi, lo)
+    // ---- load (coalesced: the 16 lanes of a pilot read 256 contiguous bytes) + forward FFT along the block axis
     #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int idx = tid + 256 * j, p = idx >> 4, b = idx & 15;
         float2 v[16];
+        if (p < nvalid) {
+            const double2* src = a.r + ((base + p) * CT_N + b);
+            #pragma unroll
+            for (int ar = 0; ar < 16; ++ar) { const double2 d = __ldcs(src + ar * 16); v[ar] = make_float2((float)d.x, (float)d.y); }
+        } else {
+            #pragma unroll
+            for (int ar = 0; ar < 16; ++ar) v[ar] = make_float2(0.f, 0.f);
+        }
+        fft16<false>(v);
         #pragma unroll
-        for (int ar = 0; ar < 16; ++ar) v[ar] = X[(p * 16 + ar) * 16 + (b ^ ar)];
+        for (int ar = 0; ar < 16; ++ar) X[xidx(p, ar, b)] = v[ar];
+    }
+    __syncthreads();
+
+    // ---- forward FFT along the contiguous axis (thread = one row), |rt|^2 as per-pilot scaled FP16 (hi, lo)
+    #pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
+        float2 v[16];
+        float4* row = reinterpret_cast<float4*>(X + p * CT_XP + ar * 16);
+        #pragma unroll
+        for (int c = 0; c < 8; ++c) { const float4 q = row[c ^ (ar & 7)]; v[2 * c] = make_float2(q.x, q.y); v[2 * c + 1] = make_float2(q.z, q.w); }
         fft16<false>(v);
         float e[16], psum = 0.f;
         #pragma unroll
-        for (int ar = 0; ar < 16; ++ar) {
-            X[(p * 16 + ar) * 16 + (b ^ ar)] = v[ar];
-            e[ar] = v[ar].x * v[ar].x + v[ar].y * v[ar].y;
-            psum += e[ar];
-        }
+        for (int c = 0; c < 8; ++c) row[c ^ (ar & 7)] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
         #pragma unroll
-        for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);     // the 16 columns of pilot p
+        for (int b = 0; b < 16; ++b) { e[b] = v[b].x * v[b].x + v[b].y * v[b].y; psum += e[b]; }
+        #pragma unroll
+        for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);     // the 16 rows of pilot p
         int ex = 0;
         float sc = 1.f;
         if (psum > 0.f && psum < 3.0e38f) { frexpf(psum, &ex); sc = ldexpf(1.f, 14 - ex); }         // every e * sc < 2^14
-        if (b == 0) invsc[p] = 1.f / sc;
+        if (ar == 0) invsc[p] = 1.f / sc;
+        uint32_t hi2[8], lo2[8];
         #pragma unroll
-        for (int ar = 0; ar < 16; ++ar) {
-            __half hi, lo;
-            split_half(e[ar] * sc, hi, lo);
-            Ehi[p * CT_EP + ar * 16 + b] = hi;
-            Elo[p * CT_EP + ar * 16 + b] = lo;
+        for (int c = 0; c < 8; ++c) {
+            __half h0, l0, h1, l1;
+            split_half(e[2 * c] * sc, h0, l0);
+            split_half(e[2 * c + 1] * sc, h1, l1);
+            hi2[c] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lo2[c] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
+        uint4* eh = reinterpret_cast<uint4*>(Ehi + p * CT_EP + ar * 16);
+        uint4* el = reinterpret_cast<uint4*>(Elo + p * CT_EP + ar * 16);
+        eh[0] = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]); eh[1] = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);
+        el[0] = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]); el[1] = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
     }
     __syncthreads();
 
     // ---- GEMM 1: q[p][k] = sum_i E[p][i] / lambda[k][i]   (warp: 32 pilots x KNB blocks of 8 components)
+    // The constant fragments stream from L2: they are fetched PF k-steps ahead of their MMAs.
     const int g = lane >> 2, t4 = lane & 3;
     {
         float acc[2][KNB][4];
@@ -178,8 +191,14 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[m][n][c] = 0.f;
         const uint4* bp = a.b1 + ((size_t)(warp * KNB) * 16) * 32 + lane;
-        #pragma unroll 4
-        for (int ks = 0; ks < CT_N / 16; ++ks) {
+        constexpr int KS = CT_N / 16, PF = 4;
+        uint4 bq[PF][KNB];
+        #pragma unroll
+        for (int f = 0; f < PF; ++f)
+            #pragma unroll
+            for (int n = 0; n < KNB; ++n) bq[f][n] = __ldg(bp + ((size_t)n * 16 + f) * 32);
+        #pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
             uint32_t ah[2][4], al[2][4];
             #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -187,16 +206,20 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
                 ldmatrix_x4(ah[m], Ehi + off);
                 ldmatrix_x4(al[m], Elo + off);
             }
+            uint4 bv[KNB];
             #pragma unroll
             for (int n = 0; n < KNB; ++n) {
-                const uint4 bv = __ldg(bp + ((size_t)n * 16 + ks) * 32);
+                bv[n] = bq[ks % PF][n];
+                if (ks + PF < KS) bq[ks % PF][n] = __ldg(bp + ((size_t)n * 16 + ks + PF) * 32);
+            }
+            #pragma unroll
+            for (int n = 0; n < KNB; ++n)
                 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                    mma16816(acc[m][n], ah[m], bv.x, bv.y);
-                    mma16816(acc[m][n], al[m], bv.x, bv.y);
-                    mma16816(acc[m][n], ah[m], bv.z, bv.w);
+                    mma16816(acc[m][n], ah[m], bv[n].x, bv[n].y);
+                    mma16816(acc[m][n], al[m], bv[n].x, bv[n].y);
+                    mma16816(acc[m][n], ah[m], bv[n].z, bv[n].w);
                 }
-            }
         }
         __syncthreads();                       // every warp is done with E: its space becomes the log-probability rows
         #pragma unroll
@@ -267,8 +290,14 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[m][n][c] = 0.f;
         const uint4* bp = a.b2 + ((size_t)(warp * 4) * (K / 16)) * 32 + lane;
-        #pragma unroll 2
-        for (int ks = 0; ks < K / 16; ++ks) {
+        constexpr int KS = K / 16, PF = 2;
+        uint4 bq[PF][4];
+        #pragma unroll
+        for (int f = 0; f < PF; ++f)
+            #pragma unroll
+            for (int n = 0; n < 4; ++n) bq[f][n] = __ldg(bp + ((size_t)n * KS + f) * 32);
+        #pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
             uint32_t ah[2][4], al[2][4];
             #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -276,68 +305,72 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
                 ldmatrix_x4(ah[m], Whi + off);
                 ldmatrix_x4(al[m], Wlo + off);
             }
+            uint4 bv[4];
             #pragma unroll
             for (int n = 0; n < 4; ++n) {
-                const uint4 bv = __ldg(bp + ((size_t)n * (K / 16) + ks) * 32);
+                bv[n] = bq[ks % PF][n];
+                if (ks + PF < KS) bq[ks % PF][n] = __ldg(bp + ((size_t)n * KS + ks + PF) * 32);
+            }
+            #pragma unroll
+            for (int n = 0; n < 4; ++n)
                 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                    mma16816(acc[m][n], ah[m], bv.x, bv.y);
-                    mma16816(acc[m][n], al[m], bv.x, bv.y);
-                    mma16816(acc[m][n], ah[m], bv.z, bv.w);
+                    mma16816(acc[m][n], ah[m], bv[n].x, bv[n].y);
+                    mma16816(acc[m][n], al[m], bv[n].x, bv[n].y);
+                    mma16816(acc[m][n], ah[m], bv[n].z, bv[n].w);
                 }
-            }
         }
         const float gs = a.inv_s2 / CT_WSCALE;
         #pragma unroll
         for (int m = 0; m < 2; ++m)
             #pragma unroll
             for (int n = 0; n < 4; ++n) {
-                const int bin = (warp * 4 + n) * 8 + 2 * t4, ar = bin >> 4, b = bin & 15;
+                const int bin = (warp * 4 + n) * 8 + 2 * t4, ar = bin >> 4, b = bin & 15;      // bins (b, b + 1): one swizzled pair
                 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int p = m * 16 + g + 8 * hh;
-                    float2* x0 = X + (p * 16 + ar) * 16 + (b ^ ar);
-                    float2* x1 = X + (p * 16 + ar) * 16 + ((b + 1) ^ ar);
+                    float4* x = reinterpret_cast<float4*>(X + xidx(p, ar, b));
                     const float g0 = acc[m][n][2 * hh] * gs, g1 = acc[m][n][2 * hh + 1] * gs;
-                    *x0 = make_float2(x0->x * g0, x0->y * g0);
-                    *x1 = make_float2(x1->x * g1, x1->y * g1);
+                    const float4 q = *x;
+                    *x = make_float4(q.x * g0, q.y * g0, q.z * g1, q.w * g1);
                 }
             }
         __syncthreads();
 
-        // ---- inverse FFT along the block axis
+        // ---- inverse FFT along the contiguous axis (thread = one row)
+        #pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
+            float2 v[16];
+            float4* row = reinterpret_cast<float4*>(X + p * CT_XP + ar * 16);
+            #pragma unroll
+            for (int c = 0; c < 8; ++c) { const float4 q = row[c ^ (ar & 7)]; v[2 * c] = make_float2(q.x, q.y); v[2 * c + 1] = make_float2(q.z, q.w); }
+            fft16<true>(v);
+            #pragma unroll
+            for (int c = 0; c < 8; ++c) row[c ^ (ar & 7)] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
+        }
+        __syncthreads();
+
+        // ---- inverse FFT along the block axis fused into the (coalesced) store, NMSE accumulators
+        float errf = 0.f, pwf = 0.f;
         #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int idx = tid + 256 * j, p = idx >> 4, b = idx & 15;
             float2 v[16];
             #pragma unroll
-            for (int ar = 0; ar < 16; ++ar) v[ar] = X[(p * 16 + ar) * 16 + (b ^ ar)];
-            fft16<true>(v);
-            #pragma unroll
-            for (int ar = 0; ar < 16; ++ar) X[(p * 16 + ar) * 16 + (b ^ ar)] = v[ar];
-        }
-        __syncthreads();
-
-        // ---- inverse FFT along the contiguous axis fused into the store, NMSE accumulators
-        float errf = 0.f, pwf = 0.f;
-        #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
-            float2 v[16];
-            #pragma unroll
-            for (int b = 0; b < 16; ++b) v[b] = X[(p * 16 + ar) * 16 + (b ^ ar)];
+            for (int ar = 0; ar < 16; ++ar) v[ar] = X[xidx(p, ar, b)];
             fft16<true>(v);
             if (p < nvalid) {
-                const size_t o = (size_t)(base + p) * CT_N + ar * 16;
+                const size_t o = (size_t)(base + p) * CT_N + b;
                 if (a.h_est) {
                     #pragma unroll
-                    for (int b = 0; b < 16; ++b) __stcs(a.h_est + o + b, make_double2((double)v[b].x, (double)v[b].y));
+                    for (int ar = 0; ar < 16; ++ar) __stcs(a.h_est + o + ar * 16, make_double2((double)v[ar].x, (double)v[ar].y));
                 }
                 if (a.acc && a.h_true) {
                     #pragma unroll
-                    for (int b = 0; b < 16; ++b) {
-                        const double2 h = __ldcs(a.h_true + o + b);
-                        const float hx = (float)h.x, hy = (float)h.y, dx = v[b].x - hx, dy = v[b].y - hy;
+                    for (int ar = 0; ar < 16; ++ar) {
+                        const double2 h = __ldcs(a.h_true + o + ar * 16);
+                        const float hx = (float)h.x, hy = (float)h.y, dx = v[ar].x - hx, dy = v[ar].y - hy;
                         errf = fmaf(dx, dx, fmaf(dy, dy, errf));
                         pwf = fmaf(hx, hx, fmaf(hy, hy, pwf));
                     }
@@ -445,7 +478,7 @@ qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s) {
 
 template <int KNB>
 static qce_status launch_circ_tc_k(const CircTcArgs& a, cudaStream_t s) {
-    constexpr size_t SMEM = CT_P * CT_N * sizeof(float2) + CT_R_BYTES + 256;
+    constexpr size_t SMEM = CT_P * CT_XP * sizeof(float2) + CT_R_BYTES + 256;
     static bool attr_set = false;
     if (!attr_set) {
         QCE_CUDA_TRY(cudaFuncSetAttribute(circ_tc_kernel<KNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
