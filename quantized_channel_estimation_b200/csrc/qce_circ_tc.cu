@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
         #pragma unroll
         for (int ar = 0; ar < 16; ++ar) X[xidx(p, ar, b)] = v[ar];
     }
-    __syncthreads();
+    __syncwarp();                              // pilot p is written and read by the same 16 lanes (idx >> 4 in both phases)
 
     // ---- forward FFT along the contiguous axis (thread = one row), |rt|^2 as per-pilot scaled FP16 (hi, lo)
     #pragma unroll
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
             for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
             float sum = 0.f;
             #pragma unroll
-            for (int j = 0; j < K / 32; ++j) { v[j] = expf(v[j] - mx); sum += v[j]; }
+            for (int j = 0; j < K / 32; ++j) { v[j] = __expf(v[j] - mx); sum += v[j]; }
             #pragma unroll
             for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
             const float inv = CT_WSCALE / sum;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
             #pragma unroll
             for (int c = 0; c < 8; ++c) row[c ^ (ar & 7)] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
         }
-        __syncthreads();
+        __syncwarp();                          // same 16 lanes per pilot again
 
         // ---- inverse FFT along the block axis fused into the (coalesced) store, NMSE accumulators
         float errf = 0.f, pwf = 0.f;

@@ -63,6 +63,10 @@ struct TcParams {
     bool has_offsets = false;
     bool triangular = false;
     bool ready = false;
+    // pilots off the integer grid (data_scale = 0: Lloyd-Max labels, unquantised data): staged as FP16 (hi, lo) tile pairs of
+    // r / eff_scale, three tensor passes
+    bool split_a = false;
+    double eff_scale = 0.0;     // data_scale, or 2^-8 when split_a
     // split path (n_obs or n_ant above 64): a whitening-only image and up to two LMMSE row-block images; the estimate runs as
     // log-probability launch -> selection -> one launch per row block
     bool split = false;

@@ -52,12 +52,15 @@ __host__ __device__ constexpr int tc2_rank_comp_bytes(int nt, int tri16, int ksp
 // ORDER 0 = tile-major (all chunks of a component for tile 0, then for tile 1: the accumulators complete half a component
 // apart), ORDER 1 = chunk-major (each chunk feeds both tiles, then is released: two ring stages suffice -- the split
 // launches of the large shapes, whose pilot tiles leave less than 100 KB for the ring)
-template <int KD_, int NZ, int NH, int CG, int ORDER = 0>
+// AC = 2: pilots that are not on an integer grid (Lloyd-Max labels, unquantised data) are staged as an FP16 (hi, lo) pair of tile
+// images; the hi parameter image is then multiplied with both (three tensor passes instead of two)
+template <int KD_, int NZ, int NH, int CG, int ORDER = 0, int AC = 1>
 struct TcCfg {
     static constexpr int KD = KD_;                                  // GEMM reduction length 2*n_obs
     static constexpr int NT = NZ + NH;                              // fused MMA N: Z columns then H columns
     static constexpr int TRI16 = NZ > 0 ? 16 : 0;                   // CG=2 image: K-step ks skips the first 16 ks (Z) rows
-    static constexpr int A_TILE_BYTES = TILE_M * KD * 2;
+    static constexpr int A_COPY_BYTES = TILE_M * KD * 2;
+    static constexpr int A_TILE_BYTES = AC * A_COPY_BYTES;
     static constexpr int KSPS = KD / 32;                            // K-steps (of 16) per staged chunk = half the K range
     // CG=1: a chunk is one K-half of the stacked hi (or lo) image, 4 chunks per component.
     // CG=2: a chunk is this CTA's share of the whole hi (or lo) image (triangular layout), 2 chunks per component.
@@ -120,6 +123,10 @@ __device__ __forceinline__ void tc_issue_chunk(const int q, const uint32_t d_til
         if (elected) {
             if (CG == 2) umma2_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
             else umma_f16(d_tile + skip, a_lo, b_lo, DESC_HI, idesc, accum);
+            if (Cfg::A_TILE_BYTES != Cfg::A_COPY_BYTES && !lo_pass) {       // lo term of the pilots x hi term of the parameters
+                if (CG == 2) umma2_f16(d_tile + skip, a_lo + (Cfg::A_COPY_BYTES >> 4), b_lo, DESC_HI, idesc, 1u);
+                else umma_f16(d_tile + skip, a_lo + (Cfg::A_COPY_BYTES >> 4), b_lo, DESC_HI, idesc, 1u);
+            }
         }
     }
 }
@@ -127,11 +134,10 @@ __device__ __forceinline__ void tc_issue_chunk(const int q, const uint32_t d_til
 // EPI selects the epilogue: 0 = fused 'all' estimate (online softmax), 1 = export the weighted log-probabilities l_k only,
 // 2 = combine with given per-pilot weights (the top-1 / top-n / cumulative-probability modes run 1 -> select -> 2)
 // KDC = n_obs / 16 (reduction length 32 KDC); NCHZ = 0 (no whitening columns: an H-part launch) or KDC; NCHH = H columns / 32
-template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER>
+template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
-    using Cfg = TcCfg<32 * KDC, NZ, NH, CG, ORDER>;
-    constexpr int KD = Cfg::KD;
+    using Cfg = TcCfg<32 * KDC, NZ, NH, CG, ORDER, AC>;
     constexpr int S = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;
@@ -618,7 +624,8 @@ __global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const dou
 // K cores, i.e. the CTA reads 8 full pilot rows (coalesced 64 B segments) and every warp writes one 128 B core matrix.
 // OBSERVE = true fuses get_observation_nbit + quant (modules/utils.py:241-251, :189-203) in front: y = h + s*n with
 // two roundings, then the same sign / digitize decisions as quantize_kernel (bit-exact), then the level's grid index.
-template <bool OBSERVE, bool H_C64>
+// SPLIT = true: arbitrary real data, written as the FP16 pair (hi, lo) of m = r / eff_scale into two consecutive tile images.
+template <bool OBSERVE, bool H_C64, bool SPLIT>
 __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__ src, const double2* __restrict__ noise, double noise_scale,
                                                         QuantTables qt, int64_t B, int No, double inv_data_scale,
                                                         __half* __restrict__ img, unsigned char* __restrict__ bad) {
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
     const int rr = mb * 8 + (lane & 7);
     const int64_t g = tile * TILE_M + rr;
     const float inv = (float)inv_data_scale;
-    __half* tile_img = img + (size_t)tile * TILE_M * KD;
+    __half* tile_img = img + (size_t)tile * TILE_M * KD * (SPLIT ? 2 : 1);
     int my_bad = 0;
     for (int kb = warp; kb < kbs; kb += 8) {
         const int j = kb * 4 + (lane >> 3);
@@ -666,14 +673,22 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
                 v.y *= inv_data_scale;
             }
         }
+        const size_t core_off = (size_t)(kb * (TILE_M / 8) + mb) * 128 + (lane & 7) * 16 + (lane >> 3) * 4;
+        if (SPLIT) {
+            if (!(fabs(v.x) <= 60000.0 && fabs(v.y) <= 60000.0)) { my_bad = 1; v = make_double2(0.0, 0.0); }     // out of FP16 range / NaN
+            const __half hr = __double2half(v.x), hi_ = __double2half(v.y);
+            const __half lr = __double2half(v.x - (double)__half2float(hr)), li = __double2half(v.y - (double)__half2float(hi_));
+            *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img) + core_off) = __halves2half2(hr, hi_);
+            *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img + (size_t)TILE_M * KD) + core_off) = __halves2half2(lr, li);
+            continue;
+        }
         const float mr = (float)v.x, mi = (float)v.y;
         const float qr = rintf(mr), qi = rintf(mi);
         // off-grid / out-of-range / NaN data cannot be represented exactly: flag the row (its estimate becomes NaN)
         if (!(fabsf(mr - qr) <= 1e-4f * fmaxf(1.f, fabsf(qr)) && fabsf(mi - qi) <= 1e-4f * fmaxf(1.f, fabsf(qi)) &&
               fabsf(qr) <= 2048.f && fabsf(qi) <= 2048.f))
             my_bad = 1;
-        *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img) + (size_t)(kb * (TILE_M / 8) + mb) * 128 + (lane & 7) * 16 +
-                                    (lane >> 3) * 4) = __floats2half2_rn(qr, qi);
+        *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img) + core_off) = __floats2half2_rn(qr, qi);
         (void)inv;
     }
     if (my_bad) s_bad[lane & 7] = 1;
@@ -771,7 +786,7 @@ static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, T
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     TileScratch& t = g_scratch[s];
     const size_t tiles = (size_t)((rows + TILE_M - 1) / TILE_M + 4);   // the last work unit (up to 4 tiles) may reach past the end
-    const size_t need_img = tiles * TILE_M * 2 * (size_t)m->n_obs * sizeof(__half), need_bad = tiles * TILE_M;
+    const size_t need_img = tiles * TILE_M * 2 * (size_t)m->n_obs * sizeof(__half) * (m->tc.split_a ? 2 : 1), need_bad = tiles * TILE_M;
     if (need_img > t.img_bytes) {
         if (t.img) QCE_CUDA_TRY(cudaFree(t.img));
         t.img = nullptr; t.img_bytes = 0;
@@ -824,9 +839,10 @@ static bool tc_split_shape(int No, int N, int* parts, int* part_cols) {
 }
 
 bool tc_supported(const qce_model* m, int mode) {
-    if (!(m->data_scale > 0.0)) return false;
+    if (!(m->data_scale >= 0.0)) return false;
     int parts = 0, pc = 0;
-    if (tc_split_shape(m->n_obs, m->n_ant, &parts, &pc)) return !m->tc.ready || m->tc.triangular;
+    if (tc_split_shape(m->n_obs, m->n_ant, &parts, &pc)) return m->data_scale > 0.0 && (!m->tc.ready || m->tc.triangular);
+    if (m->data_scale == 0.0 && m->tc.ready && !m->tc.triangular) return false;      // off-grid pilots: SM-pair variant only
     // the modes other than the fused 'all' need the SM-pair variant (triangular whitening factor)
     if (mode != QCE_MODE_ALL && m->tc.ready && !m->tc.triangular) return false;
     return tc_instantiated(m);
@@ -844,6 +860,8 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     const size_t K = m->n_comp, No = m->n_obs, N = m->n_ant;
     const size_t comp_halfs = 2 * (2 * No + 2 * N) * (2 * No);
     p.split = tc_split_shape((int)No, (int)N, &p.h_parts, &p.part_cols);
+    p.split_a = !(m->data_scale > 0.0);
+    p.eff_scale = p.split_a ? 1.0 / 256.0 : m->data_scale;
     if (!p.zoff) {
         if (!p.split) {
             p.image_bytes = K * comp_halfs * sizeof(__half);
@@ -857,7 +875,7 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
         QCE_CUDA_TRY(cudaMalloc(&p.flags, 2 * sizeof(int)));
     }
     QCE_CUDA_TRY(cudaMemsetAsync(p.flags, 0, 2 * sizeof(int), s));
-    tc_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+    tc_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, p.eff_scale,
                                                      (__half*)p.image, p.zscale, p.hscale, p.flags);
     QCE_CHECK_LAUNCH("tc_pack_kernel");
     const size_t nmax = K * (No > N ? No : N);
@@ -875,23 +893,24 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
         const size_t bytes_z = K * 2 * (size_t)tc2_rank_comp_bytes((int)(2 * No), 16, ksps);
         const size_t bytes_h = K * 2 * (size_t)tc2_rank_comp_bytes(p.part_cols, 0, ksps);
         if (!p.image_z) QCE_CUDA_TRY(cudaMalloc(&p.image_z, bytes_z));
-        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, p.eff_scale,
                                                           p.zscale, p.hscale, 16, (int)(2 * No), 0, 0, (unsigned char*)p.image_z);
         QCE_CHECK_LAUNCH("tc2_pack_kernel");
         for (int part = 0; part < p.h_parts; ++part) {
             if (!p.image_h[part]) QCE_CUDA_TRY(cudaMalloc(&p.image_h[part], bytes_h));
-            tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+            tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, p.eff_scale,
                                                               p.zscale, p.hscale, 0, 0, part * p.part_cols, p.part_cols,
                                                               (unsigned char*)p.image_h[part]);
             QCE_CHECK_LAUNCH("tc2_pack_kernel");
         }
         QCE_CUDA_TRY(cudaStreamSynchronize(s));
     } else {   // per-CTA half images of the SM-pair kernel (their layout depends on the triangular flag)
+        if (p.split_a && !p.triangular) { p.ready = false; return QCE_OK; }      // off-grid pilots: SM-pair variant only
         const int nt = (int)(2 * No + 2 * N), tri16 = p.triangular ? 16 : 0;
         const size_t bytes = K * 2 * (size_t)tc2_rank_comp_bytes(nt, tri16, ksps);
         if (p.image2 && bytes > p.image2_bytes) { QCE_CUDA_TRY(cudaFree(p.image2)); p.image2 = nullptr; }
         if (!p.image2) { QCE_CUDA_TRY(cudaMalloc(&p.image2, bytes)); p.image2_bytes = bytes; }
-        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, m->data_scale,
+        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, p.eff_scale,
                                                           p.zscale, p.hscale, tri16, (int)(2 * No), 0, (int)(2 * N), (unsigned char*)p.image2);
         QCE_CHECK_LAUNCH("tc2_pack_kernel");
         QCE_CUDA_TRY(cudaStreamSynchronize(s));
@@ -900,11 +919,11 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     return QCE_OK;
 }
 
-template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER>
+template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC = 1>
 static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
-    using Cfg = TcCfg<32 * KDC, 32 * NCHZ, 32 * NCHH, CG, ORDER>;
+    using Cfg = TcCfg<32 * KDC, 32 * NCHZ, 32 * NCHH, CG, ORDER, AC>;
     static bool attr_set = false;
-    auto kern = dense_tc_kernel<KDC, NCHZ, NCHH, OFFS, CG, EPI, ORDER>;
+    auto kern = dense_tc_kernel<KDC, NCHZ, NCHH, OFFS, CG, EPI, ORDER, AC>;
     if (!attr_set) {
         QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
@@ -933,7 +952,13 @@ static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
 }
 
 template <int NCHZ, int NCHH>
-static qce_status launch_offs(const TcArgs& a, bool offs, int cg, int epi, cudaStream_t s) {
+static qce_status launch_offs(const TcArgs& a, bool offs, int cg, int epi, bool split_a, cudaStream_t s) {
+    if (split_a) {      // pilots as FP16 (hi, lo) pairs: SM-pair variant only
+        if (cg != 2) { set_error("tensor-core kernel: pilots off the integer grid need the SM-pair (triangular whitening) variant"); return QCE_ERR_UNSUPPORTED; }
+        if (epi == 1) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 1, 0, 2>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 1, 0, 2>(a, s);
+        if (epi == 2) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 2, 0, 2>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 2, 0, 2>(a, s);
+        return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 0, 0, 2>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 0, 0, 2>(a, s);
+    }
     if (cg == 2) {
         if (epi == 1) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 1, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 1, 0>(a, s);
         if (epi == 2) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 2, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 2, 0>(a, s);
@@ -994,7 +1019,7 @@ static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t
     const int cg = p.triangular ? cg_env : 1;
     qce_status st = QCE_ERR_UNSUPPORTED;
     bool hit = false;
-#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, cg, epi, s); hit = true; }
+#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, cg, epi, p.split_a, s); hit = true; }
     QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
 #undef QCE_TC_CASE
     if (!hit) {
@@ -1016,8 +1041,12 @@ static qce_status tc_format_into(qce_model* m, cudaStream_t s, const double* r, 
     if (st) return st;
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
     QuantTables none{};
-    tc_format_kernel<false, false><<<(unsigned)(tiles * (TILE_M / 8)), 256, 0, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->data_scale,
-                                                                                  (__half*)ts->img, (unsigned char*)ts->bad);
+    if (m->tc.split_a)
+        tc_format_kernel<false, false, true><<<(unsigned)(tiles * (TILE_M / 8)), 256, 0, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
+                                                                                            (__half*)ts->img, (unsigned char*)ts->bad);
+    else
+        tc_format_kernel<false, false, false><<<(unsigned)(tiles * (TILE_M / 8)), 256, 0, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
+                                                                                             (__half*)ts->img, (unsigned char*)ts->bad);
     QCE_CHECK_LAUNCH("tc_format_kernel");
     ts->owner = m; ts->rows = B;
     *out = ts;
@@ -1089,12 +1118,12 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
     const size_t smem = (qt->n_bits > 1) ? (size_t)(2 * qt->n_thr + 1) * sizeof(double) : 0;
     const unsigned grid = (unsigned)(tiles * (TILE_M / 8));
-    if (h_is_c64)
-        tc_format_kernel<true, true><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, 1.0 / m->data_scale,
-                                                            (__half*)ts->img, (unsigned char*)ts->bad);
-    else
-        tc_format_kernel<true, false><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, 1.0 / m->data_scale,
-                                                             (__half*)ts->img, (unsigned char*)ts->bad);
+    const double inv_scale = 1.0 / m->tc.eff_scale;
+#define QCE_FMT(C64, SPL) tc_format_kernel<true, C64, SPL><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, inv_scale, \
+                                                                                 (__half*)ts->img, (unsigned char*)ts->bad)
+    if (h_is_c64) { if (m->tc.split_a) QCE_FMT(true, true); else QCE_FMT(true, false); }
+    else { if (m->tc.split_a) QCE_FMT(false, true); else QCE_FMT(false, false); }
+#undef QCE_FMT
     QCE_CHECK_LAUNCH("tc_format_kernel(observe)");
     ts->owner = m; ts->rows = B;
     if (mode == QCE_MODE_ALL && !m->tc.split) return tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);

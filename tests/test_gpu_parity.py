@@ -344,7 +344,7 @@ def test_mfa_woodbury_vs_dense_oracle(qce, K, N, M, nb, qt, ms):
     # 'auto': pilots on a uniform grid and a tensor-core shape go to the dense tcgen05 kernels, everything else stays Woodbury
     m.precision = 'auto'
     from quantized_channel_estimation_b200.engine import tc_shape_ok
-    on_grid = qt == 'uniform' and np.isfinite(nb)
+    on_grid = (qt == 'uniform' and np.isfinite(nb)) or N <= 64       # off-grid pilots: split FP16 pilot tiles, N <= 64
     assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), DenseModel if (on_grid and tc_shape_ok(N, N)) else MfaModel)
     if on_grid and tc_shape_ok(N, N):
         ref = orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
@@ -457,6 +457,33 @@ def test_tc_split_path_mfa_config4_shape(qce):
     rt = torch.from_numpy(r).cuda()
     _check_modes(lambda mode: mf.estimate_from_y(rt, snr, n_summands_or_proba=mode, n_bits=2, quantizer=qz).cpu().numpy(),
                  lambda mode: orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba=mode, n_bits=2, quantizer=qz), B)
+
+
+@pytest.mark.parametrize('K,N,B,snr,nb,qt,ms', [
+    (10, 64, 400, 10, 3, 'lloyd', 0.1),          # Lloyd-Max labels are not on an integer grid
+    (7, 32, 300, 0, 2, 'lloyd', 0.0),
+    (6, 64, 260, 15, np.inf, 'uniform', 0.2),    # unquantised pilots
+])
+def test_tc_off_grid_pilots_three_pass(qce, K, N, B, snr, nb, qt, ms):
+    """Pilots that are not integer multiples of a step are staged as FP16 (hi, lo) tile pairs: three tensor passes."""
+    means, covs, w = orc.random_psd_gmm(K, N, seed=K + N, mean_scale=ms)
+    h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=K)
+    qz = orc.get_quantizer([snr], nb, qt)[snr] if np.isfinite(nb) else (None, None, None)
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    rt = torch.from_numpy(r).cuda()
+    _check_modes(lambda mode: m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz).cpu().numpy(),
+                 lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
+                                                      quantizer=qz), B)
+    if np.isfinite(nb):     # fused observe -> quantise -> estimate pipeline with Lloyd-Max tables
+        from quantized_channel_estimation_b200 import engine, precompute
+        model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, nb, qt, qz))
+        quant = engine.Quantizer.get(nb, qz[0], qz[1])
+        est, acc = model.pipeline(quant, torch.from_numpy(h).cuda(), torch.from_numpy(noise).cuda(), 10 ** (-snr / 20), 'all', 'tc', want_est=True)
+        ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+        assert relerr(est.cpu().numpy(), ref) < TOL_TC
+        assert acc.cpu().numpy()[2] == B
 
 
 def test_tc_single_component_and_many_components(qce):

@@ -69,6 +69,7 @@ def main():
     means, lambdas, psis, amps = orc.random_mfa(64, 128, 16, seed=0)
     qz = qce.get_quantizer([snr], 2, 'uniform')[snr]
     mf = qce.Mofa(64, 16, verbose=False).set_parameters(means, lambdas, psis, amps)
+    mf.precision = 'fp64'                                 # complex128: the Woodbury kernel
     r = pilots(1 << 15, 128, 2, qz)
     ms = timeit(lambda: mf.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=2, quantizer_type='uniform', quantizer=qz))
     out.append(dict(config='C4 MFA N=128 K=64 M=16 2-bit uniform', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='woodbury fp64'))
