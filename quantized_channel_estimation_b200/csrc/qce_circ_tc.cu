@@ -14,6 +14,8 @@
 //     load per lane per 8 x 16 block, hi and lo together) and stream from L2.
 // One CTA = 32 pilots, 256 threads, ~100 KB shared memory -> two CTAs per SM overlap each other's load / compute / store phases.
 // Any real-valued pilots are accepted (no grid assumption: Lloyd-Max labels, infinite resolution).
+#include <stdlib.h>
+
 #include "qce_common.cuh"
 
 namespace qce {
@@ -42,6 +44,7 @@ struct CircTcArgs {
     double* acc;
     int mode, n_top, flags;
     double rho;
+    int prefetch_dist;               // tiles ahead to prefetch into L2 (= resident CTAs), 0 = off
 };
 
 __device__ __forceinline__ float2 operator+(const float2 a, const float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -87,7 +90,7 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_p
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -96,10 +99,12 @@ __device__ __forceinline__ void split_half(const float x, __half& hi, __half& lo
     lo = __float2half_rn(x - __half2float(hi));
 }
 
-// KNB = K / 64: GEMM 1 gives each of the 8 warps KNB 8-component blocks
-template <int KNB>
-__global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
-    constexpr int K = 64 * KNB;
+// KC = K / 64.  NW warps per CTA: GEMM 1 gives each warp G1NB = K / (8 NW) blocks of 8 components, GEMM 2 G2NB = 32 / NW blocks
+// of 8 bins; the FFT phases run 512 / (32 NW) transforms per thread.
+template <int KC, int NW>
+__global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a) {
+    constexpr int K = 64 * KC, NT = 32 * NW, NJ = 512 / NT, KNB = K / (8 * NW), G2NB = 32 / NW, SPW = CT_P / NW;
+    static_assert(KNB >= 1 && G2NB >= 1 && NJ >= 1 && SPW >= 1, "warp split");
     constexpr int LP = K + 4;                  // pitch (floats) of the log-probability rows
     constexpr int WP = K + 8;                  // pitch (halves) of the weight operand rows
     static_assert(CT_P * LP * 4 + 2 * CT_P * WP * 2 <= CT_R_BYTES, "operand region");
@@ -119,6 +124,17 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
     const int64_t base = (int64_t)blockIdx.x * CT_P;
     const int nvalid = (int)((a.B - base) < CT_P ? (a.B - base) : CT_P);
     if (tid < 2) red[tid] = 0.0;
+    // The reads in flight per SM (two CTAs, each loading for ~1/5 of its life) cover only a third of the HBM bandwidth-delay
+    // product: pull the pilots of the tile that will be scheduled one wave of CTAs later into L2 now (one bulk prefetch).
+    if (tid == 0) {
+        const int64_t pb = base + (int64_t)a.prefetch_dist * CT_P;
+        if (pb < a.B) {
+            const int64_t np = (a.B - pb) < CT_P ? (a.B - pb) : CT_P;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.r + pb * CT_N), "r"((uint32_t)(np * CT_N * sizeof(double2))) : "memory");
+            if (a.acc && a.h_true)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.h_true + pb * CT_N), "r"((uint32_t)(np * CT_N * sizeof(double2))) : "memory");
+        }
+    }
 
     // X element (pilot p, block row ar, column b): pairs of columns are XOR-swizzled with the row so that a thread owning a row
     // (128-bit accesses) and a thread owning a column (64-bit accesses) are both bank-conflict free
@@ -126,8 +142,8 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
 
     // ---- load (coalesced: the 16 lanes of a pilot read 256 contiguous bytes) + forward FFT along the block axis
     #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int idx = tid + 256 * j, p = idx >> 4, b = idx & 15;
+    for (int j = 0; j < NJ; ++j) {
+        const int idx = tid + NT * j, p = idx >> 4, b = idx & 15;
         float2 v[16];
         if (p < nvalid) {
             const double2* src = a.r + ((base + p) * CT_N + b);
@@ -145,8 +161,8 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
 
     // ---- forward FFT along the contiguous axis (thread = one row), |rt|^2 as per-pilot scaled FP16 (hi, lo)
     #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
+    for (int j = 0; j < NJ; ++j) {
+        const int idx = tid + NT * j, p = idx >> 4, ar = idx & 15;
         float2 v[16];
         float4* row = reinterpret_cast<float4*>(X + p * CT_XP + ar * 16);
         #pragma unroll
@@ -212,14 +228,14 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
                 bv[n] = bq[ks % PF][n];
                 if (ks + PF < KS) bq[ks % PF][n] = __ldg(bp + ((size_t)n * 16 + ks + PF) * 32);
             }
+            // pass-major order: consecutive MMAs hit different accumulators (the HMMA latency is ~4 issue slots)
             #pragma unroll
-            for (int n = 0; n < KNB; ++n)
+            for (int pass = 0; pass < 3; ++pass)
                 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    mma16816(acc[m][n], ah[m], bv[n].x, bv[n].y);
-                    mma16816(acc[m][n], al[m], bv[n].x, bv[n].y);
-                    mma16816(acc[m][n], ah[m], bv[n].z, bv[n].w);
-                }
+                for (int n = 0; n < KNB; ++n)
+                    #pragma unroll
+                    for (int m = 0; m < 2; ++m)
+                        mma16816(acc[m][n], pass == 1 ? al[m] : ah[m], pass == 2 ? bv[n].z : bv[n].x, pass == 2 ? bv[n].w : bv[n].y);
         }
         __syncthreads();                       // every warp is done with E: its space becomes the log-probability rows
         #pragma unroll
@@ -241,13 +257,13 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
 
     // ---- combination weights per pilot
     if (a.logp_out) {
-        for (int o = tid; o < nvalid * K; o += 256) a.logp_out[base * K + o] = (double)lbuf[(o / K) * LP + (o % K)];
+        for (int o = tid; o < nvalid * K; o += NT) a.logp_out[base * K + o] = (double)lbuf[(o / K) * LP + (o % K)];
         __syncthreads();
     }
     if (a.mode == QCE_MODE_ALL) {
         #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {
-            const int p = warp * 4 + pp;
+        for (int pp = 0; pp < SPW; ++pp) {
+            const int p = warp * SPW + pp;
             float v[K / 32], mx = -INFINITY;
             #pragma unroll
             for (int j = 0; j < K / 32; ++j) { v[j] = lbuf[p * LP + lane + 32 * j]; mx = fmaxf(mx, v[j]); }
@@ -270,7 +286,7 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
     } else {
         if (tid < CT_P) weights_from_logp(lbuf + tid * LP, K, a.mode, a.n_top, a.rho, a.flags);
         __syncthreads();
-        for (int o = tid; o < CT_P * K; o += 256) {
+        for (int o = tid; o < CT_P * K; o += NT) {
             const int p = o / K, k = o % K;
             __half hi, lo;
             split_half(lbuf[p * LP + k] * CT_WSCALE, hi, lo);
@@ -280,22 +296,22 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
     }
     __syncthreads();
 
-    // ---- GEMM 2: G[p][i] = sum_k w[p][k] g[k][i]   (warp: 32 pilots x 4 blocks of 8 bins), rt <- G .* rt
+    // ---- GEMM 2: G[p][i] = sum_k w[p][k] g[k][i]   (warp: 32 pilots x G2NB blocks of 8 bins), rt <- G .* rt
     if (a.h_est || a.acc) {
-        float acc[2][4][4];
+        float acc[2][G2NB][4];
         #pragma unroll
         for (int m = 0; m < 2; ++m)
             #pragma unroll
-            for (int n = 0; n < 4; ++n)
+            for (int n = 0; n < G2NB; ++n)
                 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[m][n][c] = 0.f;
-        const uint4* bp = a.b2 + ((size_t)(warp * 4) * (K / 16)) * 32 + lane;
+        const uint4* bp = a.b2 + ((size_t)(warp * G2NB) * (K / 16)) * 32 + lane;
         constexpr int KS = K / 16, PF = 2;
-        uint4 bq[PF][4];
+        uint4 bq[PF][G2NB];
         #pragma unroll
         for (int f = 0; f < PF; ++f)
             #pragma unroll
-            for (int n = 0; n < 4; ++n) bq[f][n] = __ldg(bp + ((size_t)n * KS + f) * 32);
+            for (int n = 0; n < G2NB; ++n) bq[f][n] = __ldg(bp + ((size_t)n * KS + f) * 32);
         #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             uint32_t ah[2][4], al[2][4];
@@ -305,27 +321,26 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
                 ldmatrix_x4(ah[m], Whi + off);
                 ldmatrix_x4(al[m], Wlo + off);
             }
-            uint4 bv[4];
+            uint4 bv[G2NB];
             #pragma unroll
-            for (int n = 0; n < 4; ++n) {
+            for (int n = 0; n < G2NB; ++n) {
                 bv[n] = bq[ks % PF][n];
                 if (ks + PF < KS) bq[ks % PF][n] = __ldg(bp + ((size_t)n * KS + ks + PF) * 32);
             }
             #pragma unroll
-            for (int n = 0; n < 4; ++n)
+            for (int pass = 0; pass < 3; ++pass)
                 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    mma16816(acc[m][n], ah[m], bv[n].x, bv[n].y);
-                    mma16816(acc[m][n], al[m], bv[n].x, bv[n].y);
-                    mma16816(acc[m][n], ah[m], bv[n].z, bv[n].w);
-                }
+                for (int n = 0; n < G2NB; ++n)
+                    #pragma unroll
+                    for (int m = 0; m < 2; ++m)
+                        mma16816(acc[m][n], pass == 1 ? al[m] : ah[m], pass == 2 ? bv[n].z : bv[n].x, pass == 2 ? bv[n].w : bv[n].y);
         }
         const float gs = a.inv_s2 / CT_WSCALE;
         #pragma unroll
         for (int m = 0; m < 2; ++m)
             #pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                const int bin = (warp * 4 + n) * 8 + 2 * t4, ar = bin >> 4, b = bin & 15;      // bins (b, b + 1): one swizzled pair
+            for (int n = 0; n < G2NB; ++n) {
+                const int bin = (warp * G2NB + n) * 8 + 2 * t4, ar = bin >> 4, b = bin & 15;      // bins (b, b + 1): one swizzled pair
                 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int p = m * 16 + g + 8 * hh;
@@ -339,8 +354,8 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
 
         // ---- inverse FFT along the contiguous axis (thread = one row)
         #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int idx = tid + 256 * j, p = idx >> 4, ar = idx & 15;
+        for (int j = 0; j < NJ; ++j) {
+            const int idx = tid + NT * j, p = idx >> 4, ar = idx & 15;
             float2 v[16];
             float4* row = reinterpret_cast<float4*>(X + p * CT_XP + ar * 16);
             #pragma unroll
@@ -354,8 +369,8 @@ __global__ void __launch_bounds__(256, 2) circ_tc_kernel(const CircTcArgs a) {
         // ---- inverse FFT along the block axis fused into the (coalesced) store, NMSE accumulators
         float errf = 0.f, pwf = 0.f;
         #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int idx = tid + 256 * j, p = idx >> 4, b = idx & 15;
+        for (int j = 0; j < NJ; ++j) {
+            const int idx = tid + NT * j, p = idx >> 4, b = idx & 15;
             float2 v[16];
             #pragma unroll
             for (int ar = 0; ar < 16; ++ar) v[ar] = X[xidx(p, ar, b)];
@@ -476,15 +491,15 @@ qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s) {
     return QCE_OK;
 }
 
-template <int KNB>
+template <int KC, int NW>
 static qce_status launch_circ_tc_k(const CircTcArgs& a, cudaStream_t s) {
     constexpr size_t SMEM = CT_P * CT_XP * sizeof(float2) + CT_R_BYTES + 256;
     static bool attr_set = false;
     if (!attr_set) {
-        QCE_CUDA_TRY(cudaFuncSetAttribute(circ_tc_kernel<KNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        QCE_CUDA_TRY(cudaFuncSetAttribute(circ_tc_kernel<KC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
-    circ_tc_kernel<KNB><<<(unsigned)((a.B + CT_P - 1) / CT_P), 256, SMEM, s>>>(a);
+    circ_tc_kernel<KC, NW><<<(unsigned)((a.B + CT_P - 1) / CT_P), 32 * NW, SMEM, s>>>(a);
     QCE_CHECK_LAUNCH("circ_tc_kernel");
     return QCE_OK;
 }
@@ -499,7 +514,16 @@ qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double*
     a.inv_s1 = m->tc_inv_s1; a.inv_s2 = m->tc_inv_s2;
     a.r = (const double2*)r; a.h_est = (double2*)h_est; a.logp_out = logp_out; a.h_true = (const double2*)h_true; a.acc = acc;
     a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;
-    return m->n_comp == 64 ? launch_circ_tc_k<1>(a, s) : launch_circ_tc_k<2>(a, s);
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int pf_env = getenv("QCE_CIRC_PREFETCH") ? atoi(getenv("QCE_CIRC_PREFETCH")) : -1;
+        a.prefetch_dist = pf_env >= 0 ? pf_env : sms;     // measured: 0 -> 396, sms/2 .. sms -> 412, 2 sms -> 354 M est/s at config 3
+    }
+    const int nw = (getenv("QCE_CIRC_NW") && atoi(getenv("QCE_CIRC_NW")) == 16) ? 16 : 8;      // 16 warps x 64 registers measured 7 % slower
+    if (nw == 8) return m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 8>(a, s);
+    return m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 16>(a, s);
 }
 
 }  // namespace qce
