@@ -888,8 +888,22 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     p.has_offsets = h_flags[0] != 0;
     p.triangular = h_flags[1] == 0;
     const int ksps = (int)(2 * No) / 32;
-    if (p.split) {
-        if (!p.triangular) { p.ready = false; return QCE_OK; }      // only the SM-pair (triangular) layout exists for these shapes
+    if (p.split && !p.triangular) { p.ready = false; return QCE_OK; }       // only the SM-pair (triangular) layout exists for these shapes
+    if (!p.split) {   // fused image: per-CTA half images of the SM-pair kernel (their layout depends on the triangular flag)
+        if (p.split_a && !p.triangular) { p.ready = false; return QCE_OK; }      // off-grid pilots: SM-pair variant only
+        const int nt = (int)(2 * No + 2 * N), tri16 = p.triangular ? 16 : 0;
+        const size_t bytes = K * 2 * (size_t)tc2_rank_comp_bytes(nt, tri16, ksps);
+        if (p.image2 && bytes > p.image2_bytes) { QCE_CUDA_TRY(cudaFree(p.image2)); p.image2 = nullptr; }
+        if (!p.image2) { QCE_CUDA_TRY(cudaMalloc(&p.image2, bytes)); p.image2_bytes = bytes; }
+        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, p.eff_scale,
+                                                          p.zscale, p.hscale, tri16, (int)(2 * No), 0, (int)(2 * N), (unsigned char*)p.image2);
+        QCE_CHECK_LAUNCH("tc2_pack_kernel");
+        p.h_parts = 1;
+        p.part_cols = (int)(2 * N);
+    }
+    if (p.triangular) {
+        // per-purpose images: whitening rows only (log-probability launch) and LMMSE row blocks (given-weights launches).  The
+        // large shapes run every mode through them, the others the top-1 / top-n / cumulative modes and the log-prob export.
         const size_t bytes_z = K * 2 * (size_t)tc2_rank_comp_bytes((int)(2 * No), 16, ksps);
         const size_t bytes_h = K * 2 * (size_t)tc2_rank_comp_bytes(p.part_cols, 0, ksps);
         if (!p.image_z) QCE_CUDA_TRY(cudaMalloc(&p.image_z, bytes_z));
@@ -903,18 +917,11 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
                                                               (unsigned char*)p.image_h[part]);
             QCE_CHECK_LAUNCH("tc2_pack_kernel");
         }
-        QCE_CUDA_TRY(cudaStreamSynchronize(s));
-    } else {   // per-CTA half images of the SM-pair kernel (their layout depends on the triangular flag)
-        if (p.split_a && !p.triangular) { p.ready = false; return QCE_OK; }      // off-grid pilots: SM-pair variant only
-        const int nt = (int)(2 * No + 2 * N), tri16 = p.triangular ? 16 : 0;
-        const size_t bytes = K * 2 * (size_t)tc2_rank_comp_bytes(nt, tri16, ksps);
-        if (p.image2 && bytes > p.image2_bytes) { QCE_CUDA_TRY(cudaFree(p.image2)); p.image2 = nullptr; }
-        if (!p.image2) { QCE_CUDA_TRY(cudaMalloc(&p.image2, bytes)); p.image2_bytes = bytes; }
-        tc2_pack_kernel<<<(unsigned)(2 * K), 256, 0, s>>>((const double2*)m->Linv, (const double2*)m->W, (int)No, (int)N, p.eff_scale,
-                                                          p.zscale, p.hscale, tri16, (int)(2 * No), 0, (int)(2 * N), (unsigned char*)p.image2);
-        QCE_CHECK_LAUNCH("tc2_pack_kernel");
-        QCE_CUDA_TRY(cudaStreamSynchronize(s));
+    } else if (p.image_z) {     // parameters replaced by a non-triangular set
+        QCE_CUDA_TRY(cudaFree(p.image_z)); p.image_z = nullptr;
+        QCE_CUDA_TRY(cudaFree(p.image_h[0])); p.image_h[0] = nullptr;
     }
+    QCE_CUDA_TRY(cudaStreamSynchronize(s));
     p.ready = true;
     return QCE_OK;
 }
@@ -951,28 +958,32 @@ static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
     return QCE_OK;
 }
 
+// fused 'all' launch (Z|H in one MMA, online softmax)
 template <int NCHZ, int NCHH>
-static qce_status launch_offs(const TcArgs& a, bool offs, int cg, int epi, bool split_a, cudaStream_t s) {
+static qce_status launch_offs(const TcArgs& a, bool offs, int cg, bool split_a, cudaStream_t s) {
     if (split_a) {      // pilots as FP16 (hi, lo) pairs: SM-pair variant only
         if (cg != 2) { set_error("tensor-core kernel: pilots off the integer grid need the SM-pair (triangular whitening) variant"); return QCE_ERR_UNSUPPORTED; }
-        if (epi == 1) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 1, 0, 2>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 1, 0, 2>(a, s);
-        if (epi == 2) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 2, 0, 2>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 2, 0, 2>(a, s);
         return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 0, 0, 2>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 0, 0, 2>(a, s);
     }
-    if (cg == 2) {
-        if (epi == 1) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 1, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 1, 0>(a, s);
-        if (epi == 2) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 2, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 2, 0>(a, s);
-        return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 0, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 0, 0>(a, s);
-    }
-    if (epi != 0) { set_error("tensor-core kernel: the single-CTA variant only implements the fused 'all' epilogue"); return QCE_ERR_UNSUPPORTED; }
+    if (cg == 2) return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 2, 0, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 2, 0, 0>(a, s);
     return offs ? launch_cfg<NCHZ, NCHZ, NCHH, true, 1, 0, 0>(a, s) : launch_cfg<NCHZ, NCHZ, NCHH, false, 1, 0, 0>(a, s);
 }
 
-// split path: epi 1 = whitening-only launch (log-probabilities), epi 2 = one LMMSE row block with the given weights
+// per-purpose launches: epi 1 = whitening-only (log-probabilities), epi 2 = one LMMSE row block with the given weights.
+// ORDER 1 (chunk-major) for the large shapes, whose pilot tiles leave room for only 2-3 ring stages.
+template <int KDC, int NCHH, int ORDER, int AC>
+static qce_status launch_split_ac(const TcArgs& a, bool offs, int epi, cudaStream_t s) {
+    if (epi == 1) return offs ? launch_cfg<KDC, KDC, 0, true, 2, 1, ORDER, AC>(a, s) : launch_cfg<KDC, KDC, 0, false, 2, 1, ORDER, AC>(a, s);
+    return offs ? launch_cfg<KDC, 0, NCHH, true, 2, 2, ORDER, AC>(a, s) : launch_cfg<KDC, 0, NCHH, false, 2, 2, ORDER, AC>(a, s);
+}
 template <int KDC, int NCHH>
-static qce_status launch_split(const TcArgs& a, bool offs, int epi, cudaStream_t s) {
-    if (epi == 1) return offs ? launch_cfg<KDC, KDC, 0, true, 2, 1, 1>(a, s) : launch_cfg<KDC, KDC, 0, false, 2, 1, 1>(a, s);
-    return offs ? launch_cfg<KDC, 0, NCHH, true, 2, 2, 1>(a, s) : launch_cfg<KDC, 0, NCHH, false, 2, 2, 1>(a, s);
+static qce_status launch_split(const TcArgs& a, bool offs, int epi, bool split_a, cudaStream_t s) {
+    if constexpr (KDC > 4) {
+        if (split_a) { set_error("tensor-core kernel: pilots off the integer grid are supported up to 64 observations"); return QCE_ERR_UNSUPPORTED; }
+        return launch_split_ac<KDC, NCHH, 1, 1>(a, offs, epi, s);
+    } else {
+        return split_a ? launch_split_ac<KDC, NCHH, 0, 2>(a, offs, epi, s) : launch_split_ac<KDC, NCHH, 0, 1>(a, offs, epi, s);
+    }
 }
 
 static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc,
@@ -997,14 +1008,17 @@ static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaSt
     a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
     a.h_col0 = part * p.part_cols;
     a.count_rows = part == 0;
-    if (m->n_obs == 128) return launch_split<8, 4>(a, p.has_offsets, epi, s);
-    if (m->n_obs == 96) return launch_split<6, 3>(a, p.has_offsets, epi, s);
+    const int cz = m->n_obs / 16, ch = p.part_cols / 32;
+#define QCE_TC_SPLIT_CASE(Z, H) if (cz == Z && ch == H) return launch_split<Z, H>(a, p.has_offsets, epi, p.split_a, s);
+    QCE_TC_SPLIT_CASE(8, 4) QCE_TC_SPLIT_CASE(6, 3)
+    QCE_TC_SPLIT_CASE(4, 4) QCE_TC_SPLIT_CASE(2, 2) QCE_TC_SPLIT_CASE(1, 1) QCE_TC_SPLIT_CASE(3, 3) QCE_TC_SPLIT_CASE(4, 2) QCE_TC_SPLIT_CASE(2, 1)
+#undef QCE_TC_SPLIT_CASE
     set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant);
     return QCE_ERR_UNSUPPORTED;
 }
 
 static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
-                         double* acc, int epi = 0) {
+                         double* acc) {
     const TcParams& p = m->tc;
     TcArgs a;
     tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
@@ -1019,7 +1033,7 @@ static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t
     const int cg = p.triangular ? cg_env : 1;
     qce_status st = QCE_ERR_UNSUPPORTED;
     bool hit = false;
-#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, cg, epi, p.split_a, s); hit = true; }
+#define QCE_TC_CASE(Z, H) if (cz == Z && ch == H) { st = launch_offs<Z, H>(a, offs, cg, p.split_a, s); hit = true; }
     QCE_TC_CASE(4, 4) QCE_TC_CASE(2, 2) QCE_TC_CASE(1, 1) QCE_TC_CASE(3, 3) QCE_TC_CASE(4, 2) QCE_TC_CASE(2, 1)
 #undef QCE_TC_CASE
     if (!hit) {
@@ -1064,14 +1078,14 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
     if (m->n_comp > 1024) { set_error("tensor-core mode selection supports K <= 1024"); return QCE_ERR_UNSUPPORTED; }
     qce_status st = tc_scratch_aux(ts, (size_t)B, (size_t)m->n_comp);
     if (st) return st;
-    st = m->tc.split ? tc_run_split(m, ts, s, B, 1, 0, nullptr, nullptr, 0, nullptr) : tc_run(m, ts, s, B, nullptr, nullptr, 0, nullptr, 1);
+    if (!m->tc.image_z) { set_error("tensor-core mode selection needs a lower-triangular whitening factor"); return QCE_ERR_UNSUPPORTED; }
+    st = tc_run_split(m, ts, s, B, 1, 0, nullptr, nullptr, 0, nullptr);
     if (st) return st;
     const bool want_est = h_est || acc;
     tc_select_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags,
                                                              want_est ? (float*)ts->wts : nullptr, logp_out);
     QCE_CHECK_LAUNCH("tc_select_kernel");
     if (!want_est) return QCE_OK;
-    if (!m->tc.split) return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc, 2);
     for (int part = 0; part < m->tc.h_parts; ++part) {
         st = tc_run_split(m, ts, s, B, 2, part, h_est, h_true, h_true_c64, acc);
         if (st) return st;
