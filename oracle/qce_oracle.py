@@ -500,6 +500,64 @@ def mofa_estimate_from_y(means, covs, amps, y, snr_dB, A=None, n_summands_or_pro
 
 
 # --------------------------------------------------------------------------------------
+# K = 1 baselines: global / genie Bussgang-LMMSE and Bussgang-LS
+# --------------------------------------------------------------------------------------
+
+def toeplitz_cov(t):
+    """``toeplitz(t).T`` of the scripts (modules/utils.py:115-150 then ``.T``): first ROW ``t``, first column ``conj(t)``."""
+    return scipy.linalg.toeplitz(np.conj(t), t)
+
+
+def _baseline_operators(C, A, snr_dB, n_bits, quantizer_type, quantizer):
+    """``(A_eff, C_r, C_y)`` of one covariance -- estimators/blmmse.py:27-37 (1 bit), :46-57 (b bit), :39-45 (inf)."""
+    cy = A @ C @ A.conj().T + 10 ** (-snr_dB / 10) * np.eye(A.shape[0])
+    if n_bits == 1:
+        psi = np.real(np.diag(1 / np.sqrt(np.diag(cy))))
+        return np.sqrt(2 / np.pi) * psi @ A, _quantised_cov(cy, None, 1), cy
+    if n_bits == np.inf or n_bits == 'inf':
+        return A, cy, cy
+    b = _bussgang_diag(np.real(np.diag(cy)), snr_dB, n_bits, quantizer_type, quantizer)
+    return np.diag(b) @ A, b[0] ** 2 * cy + (1 - b[0] ** 2) * np.diag(np.diag(cy)), cy      # A_buss[0, 0] (blmmse.py:56)
+
+
+def blmmse_estimate_global(y, C, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None, Cr=None):
+    """``BLMMSE.estimate_global`` -- estimators/blmmse.py:61-97: one filter ``C A_eff^H pinv(C_r)`` for all pilots."""
+    A = np.eye(y.shape[1], dtype=complex) if A is None else A
+    a_eff, cr, _ = _baseline_operators(C, A, snr_dB, n_bits, quantizer_type, quantizer)
+    if Cr is not None and n_bits != 1 and n_bits != np.inf:
+        cr = Cr
+    return y @ (C @ a_eff.conj().T @ np.linalg.pinv(cr)).T
+
+
+def blmmse_estimate_genie(y, t, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+    """``BLMMSE.estimate_genie`` -- estimators/blmmse.py:21-58: per-pilot Toeplitz covariance ``toeplitz(t_b).T``."""
+    A = np.eye(y.shape[1], dtype=y.dtype) if A is None else A
+    out = np.zeros((y.shape[0], A.shape[1]), dtype=complex)
+    for b in range(y.shape[0]):
+        C = toeplitz_cov(t[b])
+        a_eff, cr, _ = _baseline_operators(C, A, snr_dB, n_bits, quantizer_type, quantizer)
+        out[b] = C @ a_eff.conj().T @ np.linalg.solve(cr, y[b])
+    return out
+
+
+def ls_estimate_global(y, C, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+    """``LS.estimate_global`` -- estimators/LS.py:54-74: least squares w.r.t. the Bussgang-effective pilot matrix."""
+    A = np.eye(y.shape[1], dtype=complex) if A is None else A
+    a_eff, _, _ = _baseline_operators(C, A, snr_dB, n_bits, quantizer_type, quantizer)
+    return np.linalg.lstsq(a_eff, y.T, rcond=None)[0].T
+
+
+def ls_estimate_genie(y, t, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+    """``LS.estimate_genie`` -- estimators/LS.py:21-52 (finite ``n_bits``; the reference's infinite-resolution branch is broken)."""
+    A = np.eye(y.shape[1], dtype=y.dtype) if A is None else A
+    out = np.zeros((y.shape[0], A.shape[1]), dtype=complex)
+    for b in range(y.shape[0]):
+        a_eff, _, _ = _baseline_operators(toeplitz_cov(t[b]), A, snr_dB, n_bits, quantizer_type, quantizer)
+        out[b] = np.linalg.lstsq(a_eff, y[b], rcond=None)[0]
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # Metric
 # --------------------------------------------------------------------------------------
 

@@ -38,6 +38,25 @@ def golden_mfa():
     return load_golden('mfa')
 
 
+@pytest.fixture(scope='session')
+def golden_baselines():
+    return load_golden('baselines')
+
+
+BASELINE_TAGS = [f'{b}_{a}' for b in ('b1', 'u2', 'l3', 'inf') for a in ('I', 'A2')]
+
+
+def baseline_case(g, tag):
+    """(r, A, n_bits, quantizer_type, quantizer) of one fixture case of tests/golden/make_golden_baselines.py."""
+    import numpy as np
+    nb = float(g[tag + '_nbits'])
+    nb = int(nb) if np.isfinite(nb) else np.inf
+    N = g['C_glob'].shape[0]
+    A = None if tag.endswith('_I') else np.kron(np.array([[1.0], [1j]]), np.eye(N))
+    qz = (g[tag + '_thr'], g[tag + '_lab'], None) if tag + '_thr' in g else (None, None, None)
+    return g[tag + '_r'], A, nb, str(g[tag + '_qtype']), qz
+
+
 GMM_TAGS = ['b1_zm', 'b1_mean', 'b2u_mean', 'b3l_zm', 'binf_mean', 'b1_pilots2', 'b2u_pilots2', 'b1_k1']
 GMM_MODES = {'all': 'all', 'top1': 1, 'top3': 3, 'cum90': 0.9}
 MFA_TAGS = ['b1_zm', 'b2u_mean', 'b3l_mean']

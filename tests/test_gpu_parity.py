@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GMM_MODES, GMM_TAGS, MFA_MODES, MFA_TAGS, golden_quantizer_tuple, relerr
+from conftest import BASELINE_TAGS, GMM_MODES, GMM_TAGS, MFA_MODES, MFA_TAGS, baseline_case, golden_quantizer_tuple, relerr
 from oracle import qce_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -125,6 +125,30 @@ def test_mfa_golden_fp64(qce, golden_mfa, tag):
         assert relerr(est, g[f'{tag}_est_{mtag}']) < TOL_FP64, (tag, mtag)
     np.testing.assert_allclose(m.predict_proba(g[f'{tag}_r']), g[f'{tag}_proba'], rtol=1e-9, atol=1e-300)
     assert np.array_equal(m.predict_proba_max(g[f'{tag}_r']), g[f'{tag}_labels'])
+
+
+# ----------------------------------------------------------------------------- K = 1 baselines (BLMMSE / LS)
+
+@pytest.mark.parametrize('tag', BASELINE_TAGS)
+def test_baselines_golden(qce, golden_baselines, tag):
+    """estimators.BLMMSE / LS: the global variants run on the dense estimate kernels (K = 1), the genie variants as batched
+    complex128 solves; both against the outputs of the reference's estimators/blmmse.py and estimators/LS.py."""
+    from quantized_channel_estimation_b200 import estimators
+    g = golden_baselines
+    r, A, nb, qt, qz = baseline_case(g, tag)
+    snr = float(g['snr'])
+    for prec, tol in (('fp64', TOL_FP64), ('auto', TOL_TC)):
+        bl, ls = estimators.BLMMSE(snr), estimators.LS(snr)
+        bl.precision = ls.precision = prec
+        assert relerr(bl.estimate_global(r, g['C_glob'], A, nb, qt, qz), g[tag + '_blmmse_global']) < tol
+        assert relerr(ls.estimate_global(r, g['C_glob'], A, nb, qt, qz), g[tag + '_ls_global']) < tol
+    # per-pilot solves with the arcsine-law C_r (condition numbers ~1e6): cuSOLVER vs LAPACK round differently
+    assert relerr(estimators.BLMMSE(snr).estimate_genie(r, g['t'], A, nb, qt, qz), g[tag + '_blmmse_genie']) < 1e-7
+    if tag + '_ls_genie' in g:
+        assert relerr(estimators.LS(snr).estimate_genie(r, g['t'], A, nb, qt, qz), g[tag + '_ls_genie']) < 1e-7
+    # CUDA tensors in -> CUDA tensor out; mp_eval dispatch like the scripts
+    out = estimators.mp_eval(estimators.BLMMSE(snr), torch.from_numpy(r).cuda(), torch.from_numpy(g['C_glob']).cuda(), None, False, A, nb, qt, qz)
+    assert out.is_cuda and relerr(out.cpu().numpy(), g[tag + '_blmmse_global']) < TOL_TC
 
 
 # ----------------------------------------------------------------------------- estimates vs oracle, larger shapes

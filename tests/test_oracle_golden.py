@@ -5,7 +5,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import GMM_MODES, GMM_TAGS, MFA_MODES, MFA_TAGS, golden_quantizer_tuple, relerr
+from conftest import BASELINE_TAGS, GMM_MODES, GMM_TAGS, MFA_MODES, MFA_TAGS, baseline_case, golden_quantizer_tuple, relerr
 from oracle import qce_oracle as orc
 
 
@@ -129,3 +129,16 @@ def test_mfa_estimate(golden_mfa, tag):
         if mtag == 'all':
             np.testing.assert_allclose(aux['proba'], g[f'{tag}_proba'], rtol=1e-10, atol=1e-300)
             assert np.array_equal(np.exp(aux['logrs']).argmax(axis=0), g[f'{tag}_labels'])
+
+
+@pytest.mark.parametrize('tag', BASELINE_TAGS)
+def test_baselines(golden_baselines, tag):
+    """Global / genie Bussgang-LMMSE and Bussgang-LS (estimators/blmmse.py, estimators/LS.py) against the reference's outputs."""
+    g = golden_baselines
+    r, A, nb, qt, qz = baseline_case(g, tag)
+    snr = float(g['snr'])
+    assert relerr(orc.blmmse_estimate_global(r, g['C_glob'], snr, A, nb, qt, qz), g[tag + '_blmmse_global']) < 1e-12
+    assert relerr(orc.ls_estimate_global(r, g['C_glob'], snr, A, nb, qt, qz), g[tag + '_ls_global']) < 1e-12
+    assert relerr(orc.blmmse_estimate_genie(r, g['t'], snr, A, nb, qt, qz), g[tag + '_blmmse_genie']) < 1e-11
+    if tag + '_ls_genie' in g:
+        assert relerr(orc.ls_estimate_genie(r, g['t'], snr, A, nb, qt, qz), g[tag + '_ls_genie']) < 1e-12
