@@ -701,12 +701,12 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
 // the reference's semantics (gmm:197-242 / mofa:125-158): softmax responsibilities; top-1 = argmax of l (MFA flag: argmax
 // of exp(l), i.e. label 0 when everything underflows); top-n / cumulative-rho = descending selection, renormalised.
 // K <= 1024 (32 values per lane).  Also exports l as float64 when asked.
+template <int PER>      // entries per lane: K <= 32 PER
 __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho,
                                                         int flags, float* __restrict__ w_out, double* __restrict__ logp_out) {
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
-    constexpr int PER = 32;
     double l[PER];
     const int per = (K + 31) / 32;
     double mx = -INFINITY;
@@ -739,14 +739,21 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
             if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = (k == amax) ? 1.f : 0.f; }
         return;
     }
-    double sum = 0.0;
+    // responsibilities exp(l - logsumexp(l)): the difference to the maximum is formed in FP64 (the pair carries ~48 bits),
+    // the exponential in FP32 (an FP64 exp per entry made this kernel 15 % of the top-n / split-path time)
+    float sumf = 0.f;
     #pragma unroll
-    for (int i = 0; i < PER; ++i) if (i < per && i * 32 + lane < K) sum += exp(l[i] - mx);
+    for (int i = 0; i < PER; ++i) {
+        const bool on = i < per && i * 32 + lane < K;
+        const float e = on ? expf((float)(l[i] - mx)) : 0.f;
+        l[i] = on ? (double)e : -1.0;                                                                 // -1 = no entry
+        sumf += e;
+    }
     #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    const double lse = mx + log(sum);
+    for (int off = 16; off > 0; off >>= 1) sumf += __shfl_xor_sync(0xffffffffu, sumf, off);
+    const double inv_sum = 1.0 / (double)sumf;
     #pragma unroll
-    for (int i = 0; i < PER; ++i) l[i] = (i < per && i * 32 + lane < K) ? exp(l[i] - lse) : -1.0;     // responsibilities; -1 = no entry
+    for (int i = 0; i < PER; ++i) if (l[i] >= 0.0) l[i] *= inv_sum;
     if (mode == QCE_MODE_ALL) {
         #pragma unroll
         for (int i = 0; i < PER; ++i)
@@ -1082,8 +1089,13 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
     st = tc_run_split(m, ts, s, B, 1, 0, nullptr, nullptr, 0, nullptr);
     if (st) return st;
     const bool want_est = h_est || acc;
-    tc_select_kernel<<<(unsigned)((B + 7) / 8), 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags,
-                                                             want_est ? (float*)ts->wts : nullptr, logp_out);
+    {
+        const unsigned grid = (unsigned)((B + 7) / 8);
+        float* wts = want_est ? (float*)ts->wts : nullptr;
+        if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags, wts, logp_out);
+        else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags, wts, logp_out);
+        else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags, wts, logp_out);
+    }
     QCE_CHECK_LAUNCH("tc_select_kernel");
     if (!want_est) return QCE_OK;
     for (int part = 0; part < m->tc.h_parts; ++part) {
