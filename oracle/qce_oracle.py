@@ -557,6 +557,20 @@ def ls_estimate_genie(y, t, snr_dB, A=None, n_bits=1, quantizer_type='uniform', 
     return out
 
 
+def rate_lower_bound(h_est, h, buss, Cq):
+    """Rate lower bound of the scripts -- Bussgang_GMM.py:291-309 (identical in Bussgang_MFA.py:154-172), loop form."""
+    res = np.array(h_est, dtype=complex)
+    norm_fac = np.clip(np.sum(np.abs(res) ** 2, axis=1), 1e-1, np.inf)
+    for i in range(res.shape[0]):
+        res[i] /= norm_fac[i]
+    inner = np.squeeze(np.expand_dims(res.conj(), 1) @ buss @ np.expand_dims(h, 2))
+    num = np.abs(np.mean(inner, axis=0)) ** 2
+    den1 = np.var(inner, axis=0)
+    den2 = np.real(np.squeeze(np.expand_dims(res.conj(), 1) @ Cq @ np.expand_dims(res, 2)))
+    den2 = np.mean(den2, axis=0)
+    return float(np.log2(1 + num / (den1 + den2)))
+
+
 # --------------------------------------------------------------------------------------
 # Metric
 # --------------------------------------------------------------------------------------

@@ -116,3 +116,62 @@ def mse(h_est, h):
         a, b = torch.as_tensor(h_est), torch.as_tensor(h)
         return float(((a - b.to(a.device)).abs() ** 2).sum() / b.numel())
     return float(np.sum(np.abs(h_est - h) ** 2) / h.size)
+
+
+def rate_lower_bound(h_est, h, buss, Cq):
+    """Statistical lower bound on the achievable rate, the post-processing of the scripts after every estimator
+    (Bussgang_GMM.py:291-309, Bussgang_MFA.py:154-172): with the normalised estimate ``g_b = h_est_b / clip(|h_est_b|^2, 0.1)``
+    (the scripts divide by the SQUARED norm),
+    ``inner_b = g_b^H B h_b``,  ``rate = log2(1 + |mean inner|^2 / (var inner + mean Re g_b^H C_q g_b))``.
+    ``buss`` is the Bussgang matrix ``B`` and ``Cq = C_r - B C B^H`` the quantisation-noise covariance of the global model
+    (``uniform_quantizer.get_Bussgang_matrix`` / ``get_Cr``).  Batched quadratic forms on the GPU (torch, complex128)."""
+    he, ht = _to_cuda(h_est, torch.complex128), _to_cuda(h, torch.complex128)
+    B, Cq = _to_cuda(buss, torch.complex128), _to_cuda(Cq, torch.complex128)
+    norm_fac = (he.abs() ** 2).sum(dim=1).clamp(min=1e-1)
+    g = he / norm_fac[:, None]
+    inner = (g.conj() * (ht @ B.T)).sum(dim=1)
+    num = inner.mean().abs() ** 2
+    den1 = (inner - inner.mean()).abs().pow(2).mean()                       # np.var of a complex vector
+    den2 = (g.conj() * (g @ Cq.T)).sum(dim=1).real.mean()
+    return float(torch.log2(1 + num / (den1 + den2)))
+
+
+class _RefObject:
+    """Attribute bag standing in for a class of the reference's ``modules`` package while unpickling."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {})
+
+
+def load_reference_model(path):
+    """Load a model saved by the reference scripts (``joblib.dump(gmm, '...sav')``, Bussgang_GMM.py:262-264 /
+    Bussgang_MFA.py:125-127) WITHOUT the reference on the path and return the matching estimator of this package
+    (``Gmm_nbit`` or ``Mofa``) with the fitted parameters transplanted (``from_reference``)."""
+    import joblib.numpy_pickle as npk
+
+    from .gmm_cplx_bussgang import Gmm_nbit
+    from .mofa_cplx_bussgang import Mofa
+
+    kinds = {}
+
+    class _Unpickler(npk.NumpyUnpickler):
+        def find_class(self, module, name):
+            if module.startswith('modules.'):
+                cls = kinds.get((module, name))
+                if cls is None:
+                    cls = kinds[(module, name)] = type(name, (_RefObject,), {'_ref_module': module})
+                return cls
+            return super().find_class(module, name)
+
+    with open(path, 'rb') as f:
+        try:
+            obj = _Unpickler(path, f, ensure_native_byte_order=False).load()
+        except TypeError:                                     # older joblib: no ensure_native_byte_order argument
+            f.seek(0)
+            obj = _Unpickler(path, f).load()
+    kind = type(obj).__name__
+    if kind in ('Gmm_nbit', 'Gmm_quant'):
+        return Gmm_nbit.from_reference(obj)
+    if kind == 'Mofa':
+        return Mofa.from_reference(obj)
+    raise TypeError(f'{path}: unsupported reference object {getattr(obj, "_ref_module", "?")}.{kind}')

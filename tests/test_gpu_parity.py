@@ -151,6 +151,22 @@ def test_baselines_golden(qce, golden_baselines, tag):
     assert out.is_cuda and relerr(out.cpu().numpy(), g[tag + '_blmmse_global']) < TOL_TC
 
 
+def test_rate_lower_bound_vs_oracle(qce):
+    """utils.rate_lower_bound (the scripts' post-processing, Bussgang_GMM.py:291-309) against its loop-form restatement."""
+    from quantized_channel_estimation_b200 import uniform_quantizer as uq, utils
+    K, N, B, snr, nb = 4, 16, 500, 10, 2
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, 'uniform', 0.0, seed=31)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    est = m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer=qz)
+    cov = np.einsum('k,kij->ij', w, covs)
+    cy = cov + 10 ** (-snr / 10) * np.eye(N)
+    buss = uq.get_Bussgang_matrix(snr, nb, cy)
+    cq = uq.get_Cr(cy, nb, snr, qz) - buss @ cov @ buss.conj().T
+    ref = orc.rate_lower_bound(est, h, buss, cq)
+    assert abs(utils.rate_lower_bound(est, h, buss, cq) - ref) < 1e-9 * max(1.0, abs(ref))
+    assert abs(utils.rate_lower_bound(torch.from_numpy(est).cuda(), torch.from_numpy(h).cuda(), buss, cq) - ref) < 1e-9 * max(1.0, abs(ref))
+
+
 # ----------------------------------------------------------------------------- estimates vs oracle, larger shapes
 
 def _case(K, N, B, snr, nb, qt, mean_scale, seed):

@@ -156,3 +156,25 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'(import|from)\s+oracle|oracle[./]|qce_oracle', src), os.path.join(dirpath, f)
+
+
+def test_load_reference_model_files():
+    """Models saved by the reference scripts (joblib .sav of modules.gmm_cplx_bussgang.Gmm_nbit / modules.mofa_cplx_bussgang.Mofa,
+    written by tests/golden/make_golden_sav.py with the unmodified classes) load without the reference on the path."""
+    import sys
+    from quantized_channel_estimation_b200 import Gmm_nbit, Mofa, utils
+    assert not any(m == 'modules' or m.startswith('modules.') for m in sys.modules)
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_sav_params.npz'))
+    gmm = utils.load_reference_model(os.path.join(ROOT, 'tests', 'golden', 'ref_gmm.sav'))
+    assert isinstance(gmm, Gmm_nbit)
+    np.testing.assert_array_equal(gmm.means_cplx, g['gmm_means'])
+    np.testing.assert_array_equal(gmm.covs_cplx, g['gmm_covs'])
+    np.testing.assert_array_equal(gmm.gm.weights_, g['w'])
+    assert gmm.params['zero_mean'] is False
+    mfa = utils.load_reference_model(os.path.join(ROOT, 'tests', 'golden', 'ref_mofa.sav'))
+    assert isinstance(mfa, Mofa)
+    np.testing.assert_array_equal(mfa.lambdas, g['mfa_lambdas'])
+    np.testing.assert_array_equal(mfa.psis, g['mfa_psis'])
+    np.testing.assert_array_equal(mfa.covs, g['mfa_covs'])
+    np.testing.assert_array_equal(mfa.amps, g['w'])
+    assert mfa._covs_are_low_rank
