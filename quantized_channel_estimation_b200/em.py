@@ -83,6 +83,27 @@ def _m_step(X, resp, reg_covar, diag, zero_mean):
     return nk, means, covs
 
 
+def _m_step_inv(X, resp, reg_covar, zero_mean, covs_prev, Sigma, F2):
+    """Toeplitz / block-Toeplitz M-step (``estimate_gaussian_covariances_inv``, gmm:792-826; Barton & Fuhrmann's inverse EM):
+    the covariance lives on the diagonal ``Sigma_k`` of the twofold-oversampled DFT domain, ``C_k = F2^H diag(Sigma_k) F2``, and
+    is updated with ``Theta = diag(F2 (C^-1 S C^-1 - C^-1) F2^H)`` of the previous covariance: ``Sigma += Sigma^2 Theta``."""
+    nk = resp.sum(0) + 10 * torch.finfo(resp.dtype).eps
+    means = (resp.T.to(X.dtype) @ X) / nk[:, None]
+    if zero_mean:
+        means = torch.zeros_like(means)
+    K, N = means.shape
+    covs = torch.empty((K, N, N), dtype=X.dtype, device=X.device)
+    eye = torch.eye(N, dtype=X.dtype, device=X.device)
+    Cinv = torch.linalg.pinv(covs_prev, hermitian=True)
+    for k in range(K):
+        diff = X - means[k]
+        S = (diff.T * resp[:, k]) @ diff.conj() / nk[k]
+        theta = ((F2 @ (Cinv[k] @ S @ Cinv[k] - Cinv[k])) * F2.conj()).sum(1).real
+        Sigma[k] = (Sigma[k] + Sigma[k] ** 2 * theta).clamp(min=reg_covar)
+        covs[k] = (F2.conj().T * Sigma[k]) @ F2 + reg_covar * eye
+    return nk, means, covs
+
+
 def _log_prob(X, weights, means, covs, diag):
     """Weighted log-densities ``[B, K]`` of the circularly-symmetric complex Gaussians (gmm:369-435)."""
     B, N = X.shape
@@ -103,7 +124,7 @@ def _log_prob(X, weights, means, covs, diag):
     return out + torch.log(weights)[None]
 
 
-def _em_gmm(X, K, diag, zero_mean, reg_covar, tol, max_iter, n_init, init_params, seed, verbose=0):
+def _em_gmm(X, K, diag, zero_mean, reg_covar, tol, max_iter, n_init, init_params, seed, verbose=0, F2=None):
     dev = X.device
     gen = _generator(seed, dev)
     B = X.shape[0]
@@ -120,13 +141,19 @@ def _em_gmm(X, K, diag, zero_mean, reg_covar, tol, max_iter, n_init, init_params
             raise ValueError("Unimplemented initialization method '%s'" % init_params)
         nk, means, covs = _m_step(X, resp, reg_covar, diag, zero_mean)
         weights = nk / B
+        Sigma = None
+        if F2 is not None:                                              # gmm:600-604: start from the unstructured covariances
+            Sigma = torch.stack([((F2 @ covs[k]) * F2.conj()).sum(1).real for k in range(K)]).clamp(min=reg_covar)
         lower, converged, n_iter = -np.inf, False, 0
         for n_iter in range(1, max_iter + 1):
             prev = lower
             wlp = _log_prob(X, weights, means, covs, diag)              # E-step (gmm:612-650)
             lpn = torch.logsumexp(wlp, 1)
             resp = torch.exp(wlp - lpn[:, None])
-            nk, means, covs = _m_step(X, resp, reg_covar, diag, zero_mean)   # M-step (gmm:659-690)
+            if F2 is None:
+                nk, means, covs = _m_step(X, resp, reg_covar, diag, zero_mean)   # M-step (gmm:659-690)
+            else:
+                nk, means, covs = _m_step_inv(X, resp, reg_covar, zero_mean, covs, Sigma, F2)
             weights = nk / B
             lower = float(lpn.mean())
             if verbose:
@@ -143,7 +170,8 @@ def _em_gmm(X, K, diag, zero_mean, reg_covar, tol, max_iter, n_init, init_params
 
 
 def fit_gmm(model, h, blocks=None, zero_mean=False):
-    """``Gmm_nbit.fit`` (gmm:96-163) for 'full', 'circulant' and 'block-circulant'."""
+    """``Gmm_nbit.fit`` (gmm:96-163): 'full', 'circulant', 'block-circulant' (EM in the DFT domain) and 'toeplitz' / 'block-toeplitz'
+    (inverse EM)."""
     gm = model.gm
     ctype = gm.covariance_type
     dev = _device()
@@ -152,9 +180,19 @@ def fit_gmm(model, h, blocks=None, zero_mean=False):
         raise ValueError('h must be [n_samples, n_antennas]')
     N = X.shape[1]
     model.params['zero_mean'] = bool(zero_mean)
-    if ctype in ('toeplitz', 'block-toeplitz'):
-        raise NotImplementedError(f'Fitting for covariance_type = {ctype} (inverse EM, gmm:787-816) is not implemented yet.')
-    if ctype == 'circulant':
+    F2 = None
+    if ctype in ('toeplitz', 'block-toeplitz'):                         # inverse EM on the oversampled DFT grid (gmm:142-160)
+        if ctype == 'block-toeplitz' and blocks is None:
+            raise ValueError("covariance_type='block-toeplitz' needs blocks=(n1, n2)")
+        dims = (N,) if ctype == 'toeplitz' else tuple(blocks)
+        Fn = np.ones((1, 1), dtype=complex)
+        for n in dims:
+            Fn = np.kron(Fn, np.fft.fft(np.eye(2 * n))[:, :n] / np.sqrt(2 * n))
+        model.F2 = Fn
+        model.params['inv-em'] = True
+        F2 = torch.as_tensor(Fn, dtype=torch.complex128, device=dev)
+        n1, n2 = 1, N
+    elif ctype == 'circulant':
         n1, n2 = 1, N
     elif ctype == 'block-circulant':
         if blocks is None:
@@ -162,13 +200,13 @@ def fit_gmm(model, h, blocks=None, zero_mean=False):
         n1, n2 = blocks
     elif ctype != 'full':
         raise NotImplementedError(f'Fitting for covariance_type = {ctype} is not implemented.')
-    diag = ctype != 'full'
+    diag = ctype in ('circulant', 'block-circulant')
     if diag:
         F = torch.as_tensor(precompute.dft_matrix(n1, n2), dtype=torch.complex128, device=dev)
         X = X @ F.T                                                     # DFT-domain data (gmm:105-106, :123-126)
     lower, weights, means, covs, n_iter, converged = _em_gmm(
         X, int(gm.n_components), diag, bool(zero_mean), float(gm.reg_covar), float(gm.tol), int(gm.max_iter), int(gm.n_init),
-        gm.init_params, gm.random_state, getattr(gm, 'verbose', 0))
+        gm.init_params, gm.random_state, getattr(gm, 'verbose', 0), F2)
     gm.converged_, gm.n_iter_, gm.lower_bound_ = bool(converged), int(n_iter), float(lower)
     w = weights.cpu().numpy()
     if diag:

@@ -21,7 +21,7 @@ def avg_loglik(h, weights, means, covs):
 
 def make_data(tag, B=4000):
     """Samples of a known 3-component mixture; returns ``(h, (weights, means, covs))``."""
-    rng = np.random.default_rng({'full_zm': 1, 'full_mean': 2, 'circ': 3, 'bccb': 4, 'mfa': 5}[tag])
+    rng = np.random.default_rng({'full_zm': 1, 'full_mean': 2, 'circ': 3, 'bccb': 4, 'mfa': 5, 'toep': 6, 'btoep': 7}[tag])
     K = 3
     w = np.array([0.5, 0.3, 0.2])
     if tag in ('full_zm', 'full_mean'):
@@ -32,6 +32,17 @@ def make_data(tag, B=4000):
             C = X @ X.conj().T / (2 * N) * (0.3 + k)
             covs.append(C)
         means = np.zeros((K, N), complex) if tag == 'full_zm' else 1.5 * crandn(rng, K, N)
+    elif tag in ('toep', 'btoep'):
+        N = 8
+
+        def toep(n):            # positive definite Toeplitz matrix from a few spectral lines plus a white floor
+            f, p = rng.random(3), rng.random(3) + 0.2
+            t = (p[None, :] * np.exp(2j * np.pi * f[None, :] * np.arange(n)[:, None])).sum(1)
+            t[0] += 0.2
+            idx = np.arange(n)[None, :] - np.arange(n)[:, None]
+            return np.where(idx >= 0, t[np.abs(idx)], np.conj(t[np.abs(idx)]))
+        covs = [(0.3 + k) * (toep(8) if tag == 'toep' else np.kron(toep(2), toep(4))) for k in range(K)]
+        means = np.zeros((K, N), complex)
     elif tag in ('circ', 'bccb'):
         N = 8
         n1, n2 = (1, 8) if tag == 'circ' else (2, 4)

@@ -27,7 +27,8 @@ from fit_common import avg_loglik, make_data                   # noqa: E402
 
 out = {}
 for tag, ctype, blocks, zm in [('full_zm', 'full', None, True), ('full_mean', 'full', None, False),
-                               ('circ', 'circulant', None, True), ('bccb', 'block-circulant', (2, 4), True)]:
+                               ('circ', 'circulant', None, True), ('bccb', 'block-circulant', (2, 4), True),
+                               ('toep', 'toeplitz', None, True), ('btoep', 'block-toeplitz', (2, 4), True)]:
     h, true = make_data(tag)
     g = Gmm_nbit(n_components=3, covariance_type=ctype, random_state=0, max_iter=200, tol=1e-5)
     g.fit(h, blocks=blocks, zero_mean=zm)
