@@ -28,6 +28,13 @@ constexpr int CT_EP = CT_N + 8;      // pitch (halves) of the |rt|^2 operand row
 constexpr int CT_R_BYTES = 34816;    // operand region: E hi/lo, later log-probabilities | weight hi/lo
 constexpr int CT_XP = CT_N + 8;      // pitch (float2) of one pilot's rt tile: 2112 B = 64 mod 128, so that the float4 updates of
                                      // two pilots (GEMM 2 epilogue) fall into different halves of the 32 banks
+#ifndef CT_TWOSUM_EVERY
+#define CT_TWOSUM_EVERY 4          // K-steps accumulated in the tensor core before the exact (hi, lo) accumulation.
+                                   // Measured at config 3 (rms error of l_k - l_max in nats / worst per-pilot estimate error / ms per
+                                   // 2^20 pilots): 1: 0.9e-5 / 5e-6 / 3.08, 2: 1.1e-5 / 6e-6 / 2.95, 4: 1.4e-5 / 7e-6 / 2.82,
+                                   // 16: 4.1e-5 / 2.3e-5 / 2.71; plain FP32 accumulation of the full 1 / lambda: 17e-5 / 9e-5 / 2.55.
+                                   // Below ~1e-5 nats the FP32 FFT is the floor.
+#endif
 constexpr float CT_WSCALE = 1024.f;  // weights (<= 1) are scaled into the FP16 normal range
 
 struct CircTcArgs {
@@ -35,7 +42,9 @@ struct CircTcArgs {
     int64_t B;
     const uint4* b1;                 // packed 1/lambda fragments  [K/8][16][32]
     const uint4* b2;                 // packed gain fragments      [32][K/16][32]
-    const float2* logc2;             // [K] logc as (hi, lo)
+    const float2* logc2;             // [K] logc - max(logc) as (hi, lo)
+    const float* ilbar;              // [N] mean over the components of 1 / lambda: reference quadratic form per pilot
+    double logc_max;
     float inv_s1, inv_s2;            // 2^-s of the packed operands
     const double2* r;
     double2* h_est;
@@ -118,7 +127,8 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
     __half* Whi = reinterpret_cast<__half*>(R + CT_P * LP * 4);
     __half* Wlo = Whi + CT_P * WP;
     float* invsc = reinterpret_cast<float*>(R + CT_R_BYTES);                       // [32] 1 / per-pilot scale of |rt|^2
-    double* red = reinterpret_cast<double*>(R + CT_R_BYTES + 128);                 // [2]
+    float* qref = invsc + CT_P;                                                    // [32] sum_i |rt_i|^2 mean_k(1 / lambda_k,i)
+    double* red = reinterpret_cast<double*>(R + CT_R_BYTES + 256);                 // [2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t base = (int64_t)blockIdx.x * CT_P;
@@ -171,10 +181,18 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
         float e[16], psum = 0.f;
         #pragma unroll
         for (int c = 0; c < 8; ++c) row[c ^ (ar & 7)] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
+        // The log-probabilities are ~ -N +- tens of nats: rounding them to FP32 would cost 3e-5 nats each.  Only their differences
+        // matter, so everything is kept relative to a per-pilot reference quadratic form q_ref (the mean 1 / lambda over the
+        // components) and to max_k logc_k; the export adds both back in FP64.
+        float qr = 0.f;
         #pragma unroll
-        for (int b = 0; b < 16; ++b) { e[b] = v[b].x * v[b].x + v[b].y * v[b].y; psum += e[b]; }
+        for (int b = 0; b < 16; ++b) { e[b] = v[b].x * v[b].x + v[b].y * v[b].y; psum += e[b]; qr = fmaf(e[b], __ldg(a.ilbar + ar * 16 + b), qr); }
         #pragma unroll
-        for (int off = 8; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);     // the 16 rows of pilot p
+        for (int off = 8; off > 0; off >>= 1) {                                                     // the 16 rows of pilot p
+            psum += __shfl_xor_sync(0xffffffffu, psum, off);
+            qr += __shfl_xor_sync(0xffffffffu, qr, off);
+        }
+        if (ar == 0) qref[p] = qr;
         int ex = 0;
         float sc = 1.f;
         if (psum > 0.f && psum < 3.0e38f) { frexpf(psum, &ex); sc = ldexpf(1.f, 14 - ex); }         // every e * sc < 2^14
@@ -195,20 +213,25 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
     }
     __syncthreads();
 
-    // ---- GEMM 1: q[p][k] = sum_i E[p][i] / lambda[k][i]   (warp: 32 pilots x KNB blocks of 8 components)
+    // ---- GEMM 1: q'[p][k] = sum_i E[p][i] (1 / lambda[k][i] - ilbar[i])   (warp: 32 pilots x KNB blocks of 8 components)
     // The constant fragments stream from L2: they are fetched PF k-steps ahead of their MMAs.
+    // Precision: q is ~N nats and the combination weights need it to ~1e-5 nats, which an FP32 tensor-core accumulator cannot
+    // hold over 48 accumulations (measured 2e-4 nats rms).  So (a) the operand is the DEVIATION of 1 / lambda from its mean over
+    // the components (the common part cancels in the softmax and is evaluated once per pilot, q_ref), and (b) every group of
+    // CT_TWOSUM_EVERY K-steps starts from a zero accumulator and is added to a running (hi, lo) FP32 pair with an exact TwoSum.
     const int g = lane >> 2, t4 = lane & 3;
     {
-        float acc[2][KNB][4];
+        float sum_hi[2][KNB][4], sum_lo[2][KNB][4];
         #pragma unroll
         for (int m = 0; m < 2; ++m)
             #pragma unroll
             for (int n = 0; n < KNB; ++n)
                 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[m][n][c] = 0.f;
+                for (int c = 0; c < 4; ++c) { sum_hi[m][n][c] = 0.f; sum_lo[m][n][c] = 0.f; }
         const uint4* bp = a.b1 + ((size_t)(warp * KNB) * 16) * 32 + lane;
-        constexpr int KS = CT_N / 16, PF = 4;
+        constexpr int KS = CT_N / 16, PF = 4, TS_EVERY = CT_TWOSUM_EVERY;
         uint4 bq[PF][KNB];
+        float acc[2][KNB][4];
         #pragma unroll
         for (int f = 0; f < PF; ++f)
             #pragma unroll
@@ -228,7 +251,15 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
                 bv[n] = bq[ks % PF][n];
                 if (ks + PF < KS) bq[ks % PF][n] = __ldg(bp + ((size_t)n * 16 + ks + PF) * 32);
             }
-            // pass-major order: consecutive MMAs hit different accumulators (the HMMA latency is ~4 issue slots)
+            if (ks % TS_EVERY == 0) {
+                #pragma unroll
+                for (int m = 0; m < 2; ++m)
+                    #pragma unroll
+                    for (int n = 0; n < KNB; ++n)
+                        #pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[m][n][c] = 0.f;
+            }
+            // pass-major order: consecutive MMAs hit different accumulators
             #pragma unroll
             for (int pass = 0; pass < 3; ++pass)
                 #pragma unroll
@@ -236,6 +267,18 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
                     #pragma unroll
                     for (int m = 0; m < 2; ++m)
                         mma16816(acc[m][n], pass == 1 ? al[m] : ah[m], pass == 2 ? bv[n].z : bv[n].x, pass == 2 ? bv[n].w : bv[n].y);
+            if (ks % TS_EVERY == TS_EVERY - 1)
+            #pragma unroll
+            for (int m = 0; m < 2; ++m)
+                #pragma unroll
+                for (int n = 0; n < KNB; ++n)
+                    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {        // (sum_hi, sum_lo) += acc without losing the rounding error (Knuth TwoSum)
+                        const float x = sum_hi[m][n][c], y = acc[m][n][c];
+                        const float t = x + y, bb = t - x;
+                        sum_lo[m][n][c] += (x - (t - bb)) + (y - bb);
+                        sum_hi[m][n][c] = t;
+                    }
         }
         __syncthreads();                       // every warp is done with E: its space becomes the log-probability rows
         #pragma unroll
@@ -247,8 +290,9 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
                 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int p = m * 16 + g + 8 * hh;
-                    const float s = invsc[p] * a.inv_s1;
-                    const float l0 = (lc0.x - acc[m][n][2 * hh] * s) + lc0.y, l1 = (lc1.x - acc[m][n][2 * hh + 1] * s) + lc1.y;
+                    const float s = invsc[p] * a.inv_s1;                               // a power of two: the products are exact
+                    const float l0 = (lc0.x - sum_hi[m][n][2 * hh] * s) + (lc0.y - sum_lo[m][n][2 * hh] * s);
+                    const float l1 = (lc1.x - sum_hi[m][n][2 * hh + 1] * s) + (lc1.y - sum_lo[m][n][2 * hh + 1] * s);
                     *reinterpret_cast<float2*>(lbuf + p * LP + k) = make_float2(l0, l1);
                 }
             }
@@ -257,7 +301,7 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
 
     // ---- combination weights per pilot
     if (a.logp_out) {
-        for (int o = tid; o < nvalid * K; o += NT) a.logp_out[base * K + o] = (double)lbuf[(o / K) * LP + (o % K)];
+        for (int o = tid; o < nvalid * K; o += NT) a.logp_out[base * K + o] = (double)lbuf[(o / K) * LP + (o % K)] + (a.logc_max - (double)qref[o / K]);
         __syncthreads();
     }
     if (a.mode == QCE_MODE_ALL) {
@@ -409,7 +453,9 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
 // Constant operands in mma.m16n8k16 B-fragment order.  Thread (g = lane / 4, t = lane % 4) of block (nb, ks) holds
 // b0 = {B[16 ks + 2t][8 nb + g], B[16 ks + 2t + 1][.]}, b1 = the same 8 rows further; stored as uint4 {b0 hi, b1 hi, b0 lo, b1 lo}.
 // which = 0: B[i][k] = 1 / lambda (source inv_lambda_t [N][K]),  which = 1: B[k][i] = gain (source gain [K][N]).
-__global__ void circ_tc_pack_kernel(const double* __restrict__ src, int rows, int cols, double scale, uint4* __restrict__ out) {
+// sub != nullptr: sub[row] is subtracted first (the 1 / lambda operand is packed as its deviation from the mean over the components).
+__global__ void circ_tc_pack_kernel(const double* __restrict__ src, const float* __restrict__ sub, int rows, int cols, double scale,
+                                    uint4* __restrict__ out) {
     const int nks = rows / 16, nnb = cols / 8;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nnb * nks * 32) return;
@@ -419,7 +465,7 @@ __global__ void circ_tc_pack_kernel(const double* __restrict__ src, int rows, in
     #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int row = ks * 16 + 2 * t + (e & 1) + 8 * (e >> 1);
-        const double x = src[(size_t)row * cols + col] * scale;
+        const double x = (src[(size_t)row * cols + col] - (sub ? (double)sub[row] : 0.0)) * scale;
         hi[e] = __double2half(x);
         lo[e] = __double2half(x - (double)__half2float(hi[e]));
     }
@@ -427,9 +473,17 @@ __global__ void circ_tc_pack_kernel(const double* __restrict__ src, int rows, in
     out[idx] = make_uint4(pack(hi[0], hi[1]), pack(hi[2], hi[3]), pack(lo[0], lo[1]), pack(lo[2], lo[3]));
 }
 
-__global__ void circ_tc_logc_kernel(const double* __restrict__ logc, int K, float2* __restrict__ out) {
+__global__ void circ_tc_logc_kernel(const double* __restrict__ logc, int K, double logc_max, float2* __restrict__ out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < K) { const double l = logc[k]; const float hi = (float)l; out[k] = make_float2(hi, (float)(l - (double)hi)); }
+    if (k < K) { const double l = logc[k] - logc_max; const float hi = (float)l; out[k] = make_float2(hi, (float)(l - (double)hi)); }
+}
+
+__global__ void circ_tc_ilbar_kernel(const double* __restrict__ inv_lambda_t, int N, int K, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) sum += inv_lambda_t[(size_t)i * K + k];
+    out[i] = (float)(sum / K);
 }
 
 double pow2_scale_for(const double* dev, size_t n, cudaStream_t s, qce_status* st) {
@@ -457,8 +511,8 @@ double pow2_scale_for(const double* dev, size_t n, cudaStream_t s, qce_status* s
 bool circ_tc_shape_ok(const qce_circ_model* m) { return m->n1 == 16 && m->n2 == 16 && (m->n_comp == 64 || m->n_comp == 128); }
 
 void circ_tc_free(qce_circ_model* m) {
-    cudaFree(m->tc_b1); cudaFree(m->tc_b2); cudaFree(m->tc_logc2);
-    m->tc_b1 = m->tc_b2 = m->tc_logc2 = nullptr;
+    cudaFree(m->tc_b1); cudaFree(m->tc_b2); cudaFree(m->tc_logc2); cudaFree(m->tc_ilbar);
+    m->tc_b1 = m->tc_b2 = m->tc_logc2 = m->tc_ilbar = nullptr;
     m->tc_ready = false;
 }
 
@@ -477,13 +531,29 @@ qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s) {
         QCE_CUDA_TRY(cudaMalloc(&m->tc_b1, frag_bytes));
         QCE_CUDA_TRY(cudaMalloc(&m->tc_b2, frag_bytes));
         QCE_CUDA_TRY(cudaMalloc(&m->tc_logc2, K * sizeof(float2)));
+        QCE_CUDA_TRY(cudaMalloc(&m->tc_ilbar, N * sizeof(float)));
     }
     const int total = (int)(N * K / 4);
-    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->inv_lambda_t, (int)N, (int)K, s1, (uint4*)m->tc_b1);
+    circ_tc_ilbar_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(m->inv_lambda_t, (int)N, (int)K, (float*)m->tc_ilbar);
+    QCE_CHECK_LAUNCH("circ_tc_ilbar_kernel");
+    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->inv_lambda_t, (const float*)m->tc_ilbar, (int)N, (int)K, s1, (uint4*)m->tc_b1);
     QCE_CHECK_LAUNCH("circ_tc_pack_kernel");
-    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->gain, (int)K, (int)N, s2, (uint4*)m->tc_b2);
+    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->gain, nullptr, (int)K, (int)N, s2, (uint4*)m->tc_b2);
     QCE_CHECK_LAUNCH("circ_tc_pack_kernel");
-    circ_tc_logc_kernel<<<(unsigned)((K + 127) / 128), 128, 0, s>>>(m->logc, (int)K, (float2*)m->tc_logc2);
+    {
+        double* h_logc = (double*)malloc(K * sizeof(double));
+        if (!h_logc || cudaMemcpyAsync(h_logc, m->logc, K * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            free(h_logc);
+            set_error("circulant tensor-core pack: device read failed");
+            return QCE_ERR_CUDA;
+        }
+        double mx = h_logc[0];
+        for (size_t k = 1; k < K; ++k) mx = h_logc[k] > mx ? h_logc[k] : mx;
+        free(h_logc);
+        m->tc_logc_max = mx;
+    }
+    circ_tc_logc_kernel<<<(unsigned)((K + 127) / 128), 128, 0, s>>>(m->logc, (int)K, m->tc_logc_max, (float2*)m->tc_logc2);
     QCE_CHECK_LAUNCH("circ_tc_logc_kernel");
     m->tc_inv_s1 = (float)(1.0 / s1);
     m->tc_inv_s2 = (float)(1.0 / s2);
@@ -493,7 +563,7 @@ qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s) {
 
 template <int KC, int NW>
 static qce_status launch_circ_tc_k(const CircTcArgs& a, cudaStream_t s) {
-    constexpr size_t SMEM = CT_P * CT_XP * sizeof(float2) + CT_R_BYTES + 256;
+    constexpr size_t SMEM = CT_P * CT_XP * sizeof(float2) + CT_R_BYTES + 512;
     static bool attr_set = false;
     if (!attr_set) {
         QCE_CUDA_TRY(cudaFuncSetAttribute(circ_tc_kernel<KC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -511,6 +581,7 @@ qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double*
     CircTcArgs a;
     a.K = m->n_comp; a.B = B;
     a.b1 = (const uint4*)m->tc_b1; a.b2 = (const uint4*)m->tc_b2; a.logc2 = (const float2*)m->tc_logc2;
+    a.ilbar = (const float*)m->tc_ilbar; a.logc_max = m->tc_logc_max;
     a.inv_s1 = m->tc_inv_s1; a.inv_s2 = m->tc_inv_s2;
     a.r = (const double2*)r; a.h_est = (double2*)h_est; a.logp_out = logp_out; a.h_true = (const double2*)h_true; a.acc = acc;
     a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;

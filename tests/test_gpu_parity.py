@@ -262,6 +262,81 @@ def test_linearity_and_batch_invariance_full_size(qce):
     assert float((a + b).abs().max()) < 1e-5 * float(a.abs().max())
 
 
+def _grid_pilots(B, N, levels, scale, seed):
+    """Random pilots on the grid {+-1, +-3, ...} * scale (what a uniform quantiser emits), on the GPU."""
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    idx = torch.randint(0, levels, (B, N, 2), generator=g, device='cuda', dtype=torch.int8)
+    return torch.view_as_complex(((idx.double() * 2 - (levels - 1)) * scale).contiguous()), g
+
+
+def test_full_size_config4_mfa_split_path(qce):
+    """BASELINE config 4 at full size (MFA, N=128, K=64, latent 16, 2-bit uniform; 2^16 pilots): tiling / order invariance of the
+    split tensor-core path, oracle spot check, agreement with the complex128 Woodbury kernel."""
+    K, N, M, B, snr = 64, 128, 16, 1 << 16, 10
+    means, lambdas, psis, amps = orc.random_mfa(K, N, M, seed=0)
+    covs = orc.mofa_covs(lambdas, psis)
+    qz = orc.get_quantizer([snr], 2, 'uniform')[snr]
+    mf = qce.Mofa(K, M, verbose=False).set_parameters(means, lambdas, psis, amps)
+    r, g = _grid_pilots(B, N, 4, qz[1][-1] / 3, seed=4)
+    full = mf.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=2, quantizer=qz)
+    perm = torch.randperm(B, generator=g, device='cuda')
+    part = mf.estimate_from_y(r[perm][:20001].contiguous(), snr, n_summands_or_proba='all', n_bits=2, quantizer=qz)
+    assert torch.equal(part, full[perm][:20001])
+    idx = np.arange(0, B, B // 48)
+    ref = orc.mofa_estimate_from_y(means, covs, amps, r[idx].cpu().numpy(), snr, n_summands_or_proba='all', n_bits=2, quantizer=qz)
+    assert relerr(full[idx].cpu().numpy(), ref) < TOL_TC
+    mf.precision = 'fp64'                                       # Woodbury kernel
+    w64 = mf.estimate_from_y(r[:4096].contiguous(), snr, n_summands_or_proba='all', n_bits=2, quantizer=qz)
+    assert relerr(full[:4096].cpu().numpy(), w64.cpu().numpy()) < TOL_TC
+
+
+def test_full_size_config3_block_circulant(qce):
+    """BASELINE config 3 at full size (block-circulant 16x16, N=256, K=128, 3-bit Lloyd-Max; 2^16 pilots): tiling / order
+    invariance of the FP32-FFT + tensor-core kernel, agreement with the complex128 kernel, dense-oracle spot check."""
+    K, N, B, snr = 128, 256, 1 << 16, 10
+    c, covs, w, F = orc.circulant_gmm(K, 16, 16, seed=0)
+    qz = orc.get_quantizer([snr], 3, 'lloyd')[snr]
+    m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
+    m.set_circulant_parameters(c, w, (16, 16))
+    g = torch.Generator(device='cuda').manual_seed(3)
+    y = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float64)) * 0.8
+    r = qce.quant(y, 3, qz[0], qz[1])
+    full = m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=3, quantizer_type='lloyd', quantizer=qz)
+    perm = torch.randperm(B, generator=g, device='cuda')
+    part = m.estimate_from_y(r[perm][:10007].contiguous(), snr, N, n_summands_or_proba='all', n_bits=3, quantizer_type='lloyd', quantizer=qz)
+    assert torch.equal(part, full[perm][:10007])
+    m.precision = 'fp64'
+    f64 = m.estimate_from_y(r[:8192].contiguous(), snr, N, n_summands_or_proba='all', n_bits=3, quantizer_type='lloyd', quantizer=qz)
+    assert relerr(full[:8192].cpu().numpy(), f64.cpu().numpy()) < TOL_TC
+    idx = np.arange(0, B, B // 16)
+    ref = orc.gmm_estimate_from_y(np.zeros((K, N)), covs, w, r[idx].cpu().numpy(), snr, n_summands_or_proba='all', n_bits=3,
+                                  quantizer_type='lloyd', quantizer=qz)
+    assert relerr(full[idx].cpu().numpy(), ref) < TOL_TC
+
+
+def test_full_size_config5_shape(qce):
+    """BASELINE config 5 shape (N=64, K=256, 1 bit; 2^17 pilots): NMSE accumulators of the fused pipeline do not depend on how the
+    observations are split (the sample-sharded run adds them across ranks), oracle spot check."""
+    from quantized_channel_estimation_b200 import engine, precompute
+    K, N, B, snr = 256, 64, 1 << 17, 5
+    means, covs, w = orc.random_psd_gmm(K, N, seed=0)
+    model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, 1))
+    quant = engine.Quantizer.get(1)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    h = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float32)).contiguous()
+    noise = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float64)).contiguous()
+    est, acc = model.pipeline(quant, h, noise, 10 ** (-snr / 20), 'all', 'auto', want_est=True)
+    parts = torch.zeros(3, dtype=torch.float64, device='cuda')
+    for lo, hi in ((0, 40000), (40000, 40001), (40001, B)):
+        model.pipeline(quant, h[lo:hi].contiguous(), noise[lo:hi].contiguous(), 10 ** (-snr / 20), 'all', 'auto', acc=parts)
+    assert parts[2].item() == acc[2].item() == B
+    np.testing.assert_allclose(parts.cpu().numpy(), acc.cpu().numpy(), rtol=1e-9)
+    idx = np.arange(0, B, B // 32)
+    r = orc.get_observation_nbit(h[idx].cpu().numpy(), snr, noise[idx].cpu().numpy(), None, 1)
+    ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=1)
+    assert relerr(est[idx].cpu().numpy(), ref) < TOL_TC
+
+
 def test_host_and_device_entry_points_agree(qce):
     K, N, B, snr = 8, 32, 300000, 0         # > two staging chunks -> exercises the double-buffered host path
     means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.0, seed=9)
