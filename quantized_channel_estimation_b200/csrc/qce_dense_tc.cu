@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 c_z += c2 - c1;
                 // ---- LMMSE row, weighted accumulation (the first H chunk is already in registers)
                 if (EPI != 1) {
-                    const bool any = __any_sync(0xffffffffu, (EPI == 2) ? (p != 0.f) : (p > 1e-30f));
+                    const bool any = __any_sync(0xffffffffu, (EPI == 2) ? (p != 0.f) : (p > a.skip_thresh));
                     const float2 ph = make_float2(p * hs, p * hs);
                     #pragma unroll
                     for (int ch = 0; ch < NCHH; ++ch) {
@@ -1005,6 +1005,8 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     a.tri = p.triangular ? 1 : 0;
     a.prof = nullptr;
     a.h_stride = 2 * m->n_ant; a.h_col0 = 0; a.count_rows = 1;
+    const char* th = getenv("QCE_TC_SKIP");                 // tuning knob (read per launch); measured: no effect up to 1e-9
+    a.skip_thresh = th ? (float)atof(th) : 1e-30f;
 }
 
 static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,

@@ -46,6 +46,8 @@ struct TcArgs {
     int h_stride;              // floats per component in hoff (2N)
     int h_col0;
     int count_rows;            // add the number of rows to acc[2] (only one of the H-part launches does)
+    float skip_thresh;         // fused 'all' epilogue: a warp skips the LMMSE row of a component whose un-normalised weight is below
+                               // this for all of its 32 pilots (the normaliser is >= 1, so the dropped terms are < skip_thresh each)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
