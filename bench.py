@@ -270,8 +270,8 @@ def main():
     k_ms = ev0.elapsed_time(ev1) / reps
     achieved = FLOP_PER_EST * B / (k_ms * 1e-3) / 1e12
     # DRAM traffic of one 2^20-pilot launch of the dominant kernel from the committed ncu --set full capture
-    # (profiles/r01_tc_v5_ncu_summary.txt: dram read 280.5 MB + write 1108.9 MB; algorithmic: 268 MB tiles + 1074 MB estimates)
-    traffic = 1.389e9 * (B / float(1 << 20)) if tc_used else None
+    # (profiles/r01_tc_final_ncu_summary.txt: dram read 295.9 MB + write 1032.4 MB; algorithmic: 268 MB tiles + 1074 MB estimates)
+    traffic = 1.328e9 * (B / float(1 << 20)) if tc_used else None
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['burst'], 'unit': 'TFLOP/s', 'frac': achieved / pk['burst'],
                 'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)', 'kernel': 'dense_tc_kernel' if tc_used else 'dense_fp64_kernel', 'kernel_ms': k_ms,
                 'peak_source': f"{pk['src']} bf16 burst (kernel timed alone)",
