@@ -182,6 +182,11 @@ qce_status qce_mfa_estimate(qce_mfa_model* m, void* stream, const void* r_dev, i
  * model's own streams; returns after the last chunk has landed in h_est_host (synchronous). */
 qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho,
                              int precision, void* h_est_host);
+/* The same for the circulant / block-circulant and the Woodbury-MFA models (r_host and h_est_host c128 [B][n_ant]). */
+qce_status qce_circ_estimate_host(qce_circ_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho,
+                                  int precision, void* h_est_host);
+qce_status qce_mfa_estimate_host(qce_mfa_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho,
+                                 void* h_est_host);
 
 #ifdef __cplusplus
 }

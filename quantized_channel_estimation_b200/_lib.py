@@ -47,6 +47,9 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     'qce_estimate_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.c_void_p]),
+    'qce_circ_estimate_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
+                                         C.c_void_p]),
+    'qce_mfa_estimate_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

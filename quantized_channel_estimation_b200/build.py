@@ -10,7 +10,7 @@ CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libqce_b200.so')
 EXTRA = os.environ.get('QCE_NVCC_EXTRA', '').split()
 NVCC_FLAGS = EXTRA + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-pthread', '-shared', '-I' + os.path.join(ROOT, 'include'), '-I' + CSRC]
 
 
 def sources():
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}:\n{out}')
     tmp = LIB + '.tmp'
-    out = subprocess.run([nvcc, '-shared', '-o', tmp] + objs + ['-lcudart'], stdout=subprocess.PIPE,
+    out = subprocess.run([nvcc, '-shared', '-o', tmp] + objs + ['-lcudart', '-lpthread'], stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:
         raise RuntimeError('link failed:\n' + out.stdout)

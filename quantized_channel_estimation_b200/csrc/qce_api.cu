@@ -3,6 +3,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "qce_common.cuh"
 
@@ -32,6 +34,27 @@ struct HostStaging {            // qce_estimate_host: double-buffered pinned + d
     size_t in_bytes = 0, out_bytes = 0;
 };
 HostStaging g_staging;
+
+// Pageable caller buffers are staged through pinned memory by the calling thread; one memcpy stream moves ~8 GB/s, far below
+// PCIe, so large copies are split over a few threads.
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = bytes >> 22;                                  // one thread per 4 MiB
+    const size_t cap = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
+    if (nt > cap) nt = cap;
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    const size_t piece = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < nt; ++i) {
+        const size_t off = i * piece;
+        if (off >= bytes) break;
+        const size_t len = (off + piece < bytes) ? piece : bytes - off;
+        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    memcpy(dst, src, piece < bytes ? piece : bytes);
+    for (auto& t : th) t.join();
+}
+std::mutex g_staging_mu;          // one host-path call at a time (the slots are shared by all models)
 }  // namespace
 
 extern "C" {
@@ -363,13 +386,16 @@ qce_status qce_estimate_formatted(qce_model* m, void* stream, int64_t B, void* h
     return tc_estimate_formatted(m, (cudaStream_t)stream, B, (double*)h_est, h_true, 0, acc);
 }
 
-qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
-                             void* h_est_host) {
-    if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
-    const size_t in_row = (size_t)m->n_obs * 16, out_row = (size_t)m->n_ant * 16;
-    // process-wide staging: NSLOT slots, each 32 MiB of pilots / estimates (pinned host + device), grown on demand
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
+}  // extern "C"
+
+// Host-buffer estimate, shared by the dense / circulant / MFA entry points: r_host c128 [B][n_in] -> h_est_host c128 [B][n_out].
+// NSLOT chunks are in flight: H2D copy, kernel(s) and D2H copy of a chunk run on the slot's own stream, so that both copy engines
+// stay busy back to back.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly;
+// pageable ones go through the pinned staging slots.  `run(stream, dev_in, rows, dev_out)` enqueues the estimate of one chunk.
+template <typename Run>
+static qce_status estimate_host_impl(size_t n_in, size_t n_out, const void* r_host, int64_t B, void* h_est_host, Run run) {
+    const size_t in_row = n_in * 16, out_row = n_out * 16;
+    std::lock_guard<std::mutex> lock(g_staging_mu);
     HostStaging* hs = &g_staging;
     const size_t slot_bytes = (size_t)32 << 20;
     constexpr int NSLOT = HostStaging::NSLOT;
@@ -399,8 +425,6 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
     // parameters were packed on the caller's stream: make them visible to the private streams
     QCE_CUDA_TRY(cudaDeviceSynchronize());
     const int64_t nchunks = (B + chunk - 1) / chunk;
-    // page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly;
-    // pageable ones go through the model's pinned staging slots
     auto is_pinned = [](const void* p) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -413,7 +437,7 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
         if (pending_b0[slot] < 0) return QCE_OK;
         QCE_CUDA_TRY(cudaEventSynchronize(hs->done[slot]));
         if (!out_pinned)
-            memcpy((char*)h_est_host + (size_t)pending_b0[slot] * out_row, hs->pin_out[slot], (size_t)pending_nb[slot] * out_row);
+            parallel_memcpy((char*)h_est_host + (size_t)pending_b0[slot] * out_row, hs->pin_out[slot], (size_t)pending_nb[slot] * out_row);
         pending_b0[slot] = -1;
         return QCE_OK;
     };
@@ -423,11 +447,10 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
         if (st) return st;
         const int64_t b0 = c * chunk, nb = (B - b0) < chunk ? (B - b0) : chunk;
         const char* src = (const char*)r_host + (size_t)b0 * in_row;
-        if (!in_pinned) { memcpy(hs->pin_in[slot], src, (size_t)nb * in_row); src = (const char*)hs->pin_in[slot]; }
+        if (!in_pinned) { parallel_memcpy(hs->pin_in[slot], src, (size_t)nb * in_row); src = (const char*)hs->pin_in[slot]; }
         cudaStream_t s = hs->streams[slot];
         QCE_CUDA_TRY(cudaMemcpyAsync(hs->dev_in[slot], src, (size_t)nb * in_row, cudaMemcpyHostToDevice, s));
-        st = estimate_impl(m, s, (const double*)hs->dev_in[slot], nb, mode, n_top, rho, precision,
-                           (double*)hs->dev_out[slot], nullptr, nullptr, 0, nullptr);
+        st = run(s, (const double*)hs->dev_in[slot], nb, (double*)hs->dev_out[slot]);
         if (st) return st;
         void* dst = out_pinned ? (void*)((char*)h_est_host + (size_t)b0 * out_row) : hs->pin_out[slot];
         QCE_CUDA_TRY(cudaMemcpyAsync(dst, hs->dev_out[slot], (size_t)nb * out_row, cudaMemcpyDeviceToHost, s));
@@ -439,6 +462,34 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
         if (st) return st;
     }
     return QCE_OK;
+}
+
+extern "C" {
+
+qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
+                             void* h_est_host) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
+    return estimate_host_impl((size_t)m->n_obs, (size_t)m->n_ant, r_host, B, h_est_host,
+                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
+                                  return estimate_impl(m, s, din, nb, mode, n_top, rho, precision, dout, nullptr, nullptr, 0, nullptr);
+                              });
+}
+
+qce_status qce_circ_estimate_host(qce_circ_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
+                                  void* h_est_host) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_circ_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
+    return estimate_host_impl((size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
+                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
+                                  return qce_circ_estimate_prec(m, (void*)s, din, nb, mode, n_top, rho, precision, dout, nullptr, nullptr, nullptr);
+                              });
+}
+
+qce_status qce_mfa_estimate_host(qce_mfa_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, void* h_est_host) {
+    if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_mfa_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
+    return estimate_host_impl((size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
+                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
+                                  return qce_mfa_estimate(m, (void*)s, din, nb, mode, n_top, rho, dout, nullptr, nullptr, nullptr);
+                              });
 }
 
 }  // extern "C"

@@ -277,8 +277,26 @@ class CircModel:
         _lib.check(lib.qce_circ_estimate_prec(self.handle, *head, _lib.PREC_FP64, *tail))
 
     def estimate_host(self, r, n_summands_or_proba='all', precision='auto'):
-        rt = torch.from_numpy(np.ascontiguousarray(np.asarray(r, dtype=np.complex128))).to(self.device)
-        return self.estimate(rt, n_summands_or_proba, precision).cpu().numpy()
+        """r: numpy c128 [B, n_ant] (host) -> numpy c128 [B, n_ant]; chunked, overlapped copies inside the library."""
+        mode, n_top, rho = parse_mode(n_summands_or_proba)
+        r = np.ascontiguousarray(np.asarray(r, dtype=np.complex128))
+        if r.ndim != 2 or r.shape[1] != self.n_obs:
+            raise ValueError(f'y must be [B, {self.n_obs}]')
+        out = np.empty((r.shape[0], self.n_ant), dtype=np.complex128)
+        with torch.cuda.device(self.device):
+            self._run_host(precision, r.ctypes.data_as(C.c_void_p), r.shape[0], mode, n_top, rho, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def _run_host(self, precision, r_ptr, B, mode, n_top, rho, out_ptr):
+        lib = _lib.load()
+        if precision not in ('fp64', 'tc', 'auto'):
+            raise ValueError(f'unknown precision {precision!r}')
+        if precision != 'fp64':
+            st = lib.qce_circ_estimate_host(self.handle, r_ptr, B, mode, n_top, rho, _lib.PREC_TC, out_ptr)
+            if not (st == _lib.ERR_UNSUPPORTED and precision == 'auto'):
+                _lib.check(st)
+                return
+        _lib.check(lib.qce_circ_estimate_host(self.handle, r_ptr, B, mode, n_top, rho, _lib.PREC_FP64, out_ptr))
 
 
 class MfaModel(CircModel):
@@ -309,3 +327,8 @@ class MfaModel(CircModel):
         if precision not in ('fp64', 'tc', 'auto'):
             raise ValueError(f'unknown precision {precision!r}')
         _lib.check(_lib.load().qce_mfa_estimate(self.handle, *head, *tail))
+
+    def _run_host(self, precision, r_ptr, B, mode, n_top, rho, out_ptr):
+        if precision not in ('fp64', 'tc', 'auto'):
+            raise ValueError(f'unknown precision {precision!r}')
+        _lib.check(_lib.load().qce_mfa_estimate_host(self.handle, r_ptr, B, mode, n_top, rho, out_ptr))
