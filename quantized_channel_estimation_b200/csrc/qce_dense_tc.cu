@@ -61,6 +61,9 @@ struct TcCfg {
     static constexpr int TRI16 = NZ > 0 ? 16 : 0;                   // CG=2 image: K-step ks skips the first 16 ks (Z) rows
     static constexpr int A_COPY_BYTES = TILE_M * KD * 2;
     static constexpr int A_TILE_BYTES = AC * A_COPY_BYTES;
+    // resident pilot tiles per CTA: two (their epilogues ping-pong), or one when the (hi, lo) tile pairs of the large shapes would
+    // not leave room for the operand ring (the second epilogue warpgroup then idles and the accumulator is not double-buffered)
+    static constexpr int NTILES = (AC == 2 && KD > 128) ? 1 : TILES;
     static constexpr int KSPS = KD / 32;                            // K-steps (of 16) per staged chunk = half the K range
     // CG=1: a chunk is one K-half of the stacked hi (or lo) image, 4 chunks per component.
     // CG=2: a chunk is this CTA's share of the whole hi (or lo) image (triangular layout), 2 chunks per component.
@@ -68,11 +71,11 @@ struct TcCfg {
     static constexpr int CB0 = tc2_chunk_bytes(NT, TRI16, KSPS, 0), CB1 = tc2_chunk_bytes(NT, TRI16, KSPS, 1);
     static constexpr int STAGE_BYTES = (CG == 2) ? (CB0 + CB1) : NT * (KD / 2) * 2;
     static constexpr int CTRL_BYTES = 1024;
-    static constexpr int STAGES_FIT = (SMEM_LIMIT - TILES * A_TILE_BYTES - CTRL_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_FIT = (SMEM_LIMIT - NTILES * A_TILE_BYTES - CTRL_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
-    static constexpr int SMEM_BYTES = TILES * A_TILE_BYTES + STAGES * STAGE_BYTES + CTRL_BYTES;
+    static constexpr int SMEM_BYTES = NTILES * A_TILE_BYTES + STAGES * STAGE_BYTES + CTRL_BYTES;
     static constexpr int COMP_HALFS = 2 * NT * KD;                  // CG=1: halfs per component image: hi then lo
-    static constexpr int TMEM_COLS_USED = TILES * NT;
+    static constexpr int TMEM_COLS_USED = NTILES * NT;
     static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
                                      : TMEM_COLS_USED <= 256 ? 256 : 512;
     static_assert(STAGES >= (ORDER == 0 ? NCHUNK + 1 : 2), "tile-major schedule keeps the chunks of a component resident plus one prefetch");
@@ -141,13 +144,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     constexpr int S = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;
-    unsigned char* sB = smem + TILES * Cfg::A_TILE_BYTES;
+    constexpr int NTILES = Cfg::NTILES;
+    unsigned char* sB = smem + NTILES * Cfg::A_TILE_BYTES;
     TcCtrl* ctrl = reinterpret_cast<TcCtrl*>(sB + S * Cfg::STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work unit: CG * TILES tiles (256 pilots per CTA); the cluster (CG CTAs) walks the units round-robin
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
-    const int64_t n_units = (a.B + CG * TILES * TILE_M - 1) / (CG * TILES * TILE_M);
+    const int64_t n_units = (a.B + CG * NTILES * TILE_M - 1) / (CG * NTILES * TILE_M);
     const int64_t unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
     // the SM-pair variant is only launched for triangular Linv (the common, Cholesky case): its offsets are compile-time
     const int tri16 = (CG == 2) ? Cfg::TRI16 : (a.tri ? 16 : 0);
@@ -207,11 +211,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
                 mbar_wait(smem_u32(&ctrl->a_free), fph ^ 1);      // all MMAs of the previous unit have read the tiles
                 fph ^= 1;
-                mbar_expect_tx(smem_u32(&ctrl->a_full), TILES * Cfg::A_TILE_BYTES);
+                mbar_expect_tx(smem_u32(&ctrl->a_full), NTILES * Cfg::A_TILE_BYTES);
                 #pragma unroll
-                for (int t = 0; t < TILES; ++t)
+                for (int t = 0; t < NTILES; ++t)
                     bulk_g2s(smem_u32(sA + t * Cfg::A_TILE_BYTES),
-                             reinterpret_cast<const unsigned char*>(a.a_img) + (size_t)((unit * CG + rank) * TILES + t) * Cfg::A_TILE_BYTES,
+                             reinterpret_cast<const unsigned char*>(a.a_img) + (size_t)((unit * CG + rank) * NTILES + t) * Cfg::A_TILE_BYTES,
                              Cfg::A_TILE_BYTES, smem_u32(&ctrl->a_full));
             }
         } else if (warp == 1 && rank == 0) {
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 for (int k = 0; k < a.K; ++k) {
                     if (ORDER == 0) {
                     #pragma unroll
-                    for (int t = 0; t < TILES; ++t) {
+                    for (int t = 0; t < NTILES; ++t) {
                         // the first MMA overwrites the accumulator: the epilogue must have drained component k-1
                         long long c0 = QCE_CLK();
                         if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
@@ -257,12 +261,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                                 w_full += QCE_CLK() - c0;
                             }
                             tc_issue_chunk<Cfg, CG>(q, d_tile, a_lo_t, b_addr0 + stage * (Cfg::STAGE_BYTES >> 4), tri16, elected);
-                            if (t == TILES - 1 && elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->empty[stage])); else tc_commit(smem_u32(&ctrl->empty[stage])); }
+                            if (t == NTILES - 1 && elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->empty[stage])); else tc_commit(smem_u32(&ctrl->empty[stage])); }
                             if (++stage == S) { stage = 0; phase ^= 1; }
                         }
                         if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->acc_full[t])); else tc_commit(smem_u32(&ctrl->acc_full[t])); }
                         __syncwarp();
-                        if (t == TILES - 1) { stage0 = stage; phase0 = phase; }
+                        if (t == NTILES - 1) { stage0 = stage; phase0 = phase; }
                     }
                     } else {
                     // chunk-major: a chunk feeds both tiles and is released at once
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         tc_fence_after();
                         w_full += QCE_CLK() - c0;
                         #pragma unroll
-                        for (int t = 0; t < TILES; ++t) {
+                        for (int t = 0; t < NTILES; ++t) {
                             if (q == 0) {
                                 c0 = QCE_CLK();
                                 if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
@@ -326,8 +330,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         double err = 0.0, pw = 0.0, cnt = 0.0;     // cnt also gates the atomics (rows handled by this thread)
         long long w_acc = 0, c_z = 0, c_h = 0, c_pro = 0, c_ld = 0;
 
-        for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
-            const int64_t tile_base = ((unit * CG + rank) * TILES + t) * TILE_M;
+        for (int64_t unit = unit0; unit < n_units && t < NTILES; unit += unit_step) {
+            const int64_t tile_base = ((unit * CG + rank) * NTILES + t) * TILE_M;
             long long c0 = QCE_CLK();
             bool row_bad = false;
             if (tile_base + row < a.B) row_bad = __ldg(a.bad + tile_base + row) != 0;
@@ -848,7 +852,7 @@ static bool tc_split_shape(int No, int N, int* parts, int* part_cols) {
 bool tc_supported(const qce_model* m, int mode) {
     if (!(m->data_scale >= 0.0)) return false;
     int parts = 0, pc = 0;
-    if (tc_split_shape(m->n_obs, m->n_ant, &parts, &pc)) return m->data_scale > 0.0 && (!m->tc.ready || m->tc.triangular);
+    if (tc_split_shape(m->n_obs, m->n_ant, &parts, &pc)) return !m->tc.ready || m->tc.triangular;
     if (m->data_scale == 0.0 && m->tc.ready && !m->tc.triangular) return false;      // off-grid pilots: SM-pair variant only
     // the modes other than the fused 'all' need the SM-pair variant (triangular whitening factor)
     if (mode != QCE_MODE_ALL && m->tc.ready && !m->tc.triangular) return false;
@@ -945,7 +949,7 @@ static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t n_units = (a.B + CG * TILES * TILE_M - 1) / (CG * TILES * TILE_M);
+    const int64_t n_units = (a.B + CG * Cfg::NTILES * TILE_M - 1) / (CG * Cfg::NTILES * TILE_M);
     const int64_t max_clusters = sms / CG;
     const unsigned grid = (unsigned)((n_units < max_clusters ? n_units : max_clusters) * CG);
     cudaLaunchConfig_t cfg{};
@@ -986,8 +990,7 @@ static qce_status launch_split_ac(const TcArgs& a, bool offs, int epi, cudaStrea
 template <int KDC, int NCHH>
 static qce_status launch_split(const TcArgs& a, bool offs, int epi, bool split_a, cudaStream_t s) {
     if constexpr (KDC > 4) {
-        if (split_a) { set_error("tensor-core kernel: pilots off the integer grid are supported up to 64 observations"); return QCE_ERR_UNSUPPORTED; }
-        return launch_split_ac<KDC, NCHH, 1, 1>(a, offs, epi, s);
+        return split_a ? launch_split_ac<KDC, NCHH, 1, 2>(a, offs, epi, s) : launch_split_ac<KDC, NCHH, 1, 1>(a, offs, epi, s);
     } else {
         return split_a ? launch_split_ac<KDC, NCHH, 0, 2>(a, offs, epi, s) : launch_split_ac<KDC, NCHH, 0, 1>(a, offs, epi, s);
     }

@@ -76,9 +76,8 @@ class Mofa:
                     A.shape == (self.D, self.D) and np.array_equal(A, np.eye(self.D)) and self._covs_are_low_rank)
         # pilots on an integer grid and a tensor-core shape: the dense tcgen05 kernels beat the complex128 Woodbury kernel
         # (config 4: 55 M vs 0.9 M estimates/s) although they do 4x the flops
-        # (off-grid pilots -- Lloyd-Max labels, unquantised data -- take three tensor passes and need N <= 64)
-        if woodbury and self.precision != 'fp64' and engine.tc_shape_ok(A.shape[0], self.D) and \
-                (precompute.data_scale_for(snr_dB, np.inf if nb == 'inf' else nb, quantizer_type) > 0 or self.D <= 64):
+        # (off-grid pilots -- Lloyd-Max labels, unquantised data -- take three tensor passes)
+        if woodbury and self.precision != 'fp64' and engine.tc_shape_ok(A.shape[0], self.D):
             woodbury = False
         if woodbury:
             key = ('woodbury', float(snr_dB), nb, quantizer_type if nb != 'inf' else None, tables, id(self.means), id(self.lambdas),

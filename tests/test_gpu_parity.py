@@ -459,9 +459,9 @@ def test_mfa_woodbury_vs_dense_oracle(qce, K, N, M, nb, qt, ms):
     # 'auto': pilots on a uniform grid and a tensor-core shape go to the dense tcgen05 kernels, everything else stays Woodbury
     m.precision = 'auto'
     from quantized_channel_estimation_b200.engine import tc_shape_ok
-    on_grid = (qt == 'uniform' and np.isfinite(nb)) or N <= 64       # off-grid pilots: split FP16 pilot tiles, N <= 64
-    assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), DenseModel if (on_grid and tc_shape_ok(N, N)) else MfaModel)
-    if on_grid and tc_shape_ok(N, N):
+    # every tensor-core shape (off-grid pilots -- Lloyd-Max labels, unquantised data -- as FP16 (hi, lo) tile pairs)
+    assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), DenseModel if tc_shape_ok(N, N) else MfaModel)
+    if tc_shape_ok(N, N):
         ref = orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
         est = m.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
         assert relerr(est, ref) < TOL_TC
@@ -578,6 +578,8 @@ def test_tc_split_path_mfa_config4_shape(qce):
     (10, 64, 400, 10, 3, 'lloyd', 0.1),          # Lloyd-Max labels are not on an integer grid
     (7, 32, 300, 0, 2, 'lloyd', 0.0),
     (6, 64, 260, 15, np.inf, 'uniform', 0.2),    # unquantised pilots
+    (5, 128, 390, 10, 3, 'lloyd', 0.1),          # large shape: one resident (hi, lo) tile pair per CTA, split launches
+    (4, 96, 131, 5, np.inf, 'uniform', 0.0),
 ])
 def test_tc_off_grid_pilots_three_pass(qce, K, N, B, snr, nb, qt, ms):
     """Pilots that are not integer multiples of a step are staged as FP16 (hi, lo) tile pairs: three tensor passes."""

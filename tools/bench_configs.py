@@ -82,6 +82,12 @@ def main():
         out.append(dict(config=f'C4 MFA N=128 K=64 M=16 2-bit uniform mode={mode}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
                         path='dense tc split', tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9,
                         tflops_woodbury_equiv=(32 * 64 * 128 * 16 + 8 * 64 * 16 * 16) * r.shape[0] / ms / 1e9))
+    # C4 shape with a 3-bit Lloyd-Max quantiser: pilots off the integer grid -> (hi, lo) tile pairs, three passes, one tile per CTA
+    qzl = qce.get_quantizer([snr], 3, 'lloyd')[snr]
+    r = pilots(1 << 18, 128, 3, qzl)
+    ms = timeit(lambda: mf.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=3, quantizer_type='lloyd', quantizer=qzl))
+    out.append(dict(config='C4 shape, MFA N=128 K=64 M=16 3-bit Lloyd-Max', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
+                    path='dense tc split, off-grid pilots', tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9))
     # GMM full, 1 bit, N=128, K=64 (same kernels)
     means, covs, w = orc.random_psd_gmm(64, 128, seed=0)
     m = qce.Gmm_nbit(n_components=64).set_parameters(means, covs, w, detect_structure=False)
