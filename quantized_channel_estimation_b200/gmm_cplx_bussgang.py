@@ -64,6 +64,7 @@ class Gmm_nbit:
         self.blocks = None                 # (n1, n2) when every covariance is F^H diag(c) F with F = F_n1 (x) F_n2
         self.use_structure = True          # use the DFT-domain kernel when blocks is set, A = I and the means vanish
         self._cache = _PreparedCache()
+        self._last = None                  # handle prepared by the last estimate_from_y (for predict_proba_cplx(X))
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -164,23 +165,33 @@ class Gmm_nbit:
         host<->device copies are chunked and overlapped inside the library)."""
         if A is None:
             A = np.eye(n_antennas, dtype=complex)
-        model = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
+        model = self._last = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
         if isinstance(y, torch.Tensor):
             if y.is_cuda:
                 return model.estimate(y, n_summands_or_proba, self.precision)
             return torch.from_numpy(model.estimate_host(y.numpy(), n_summands_or_proba, self.precision))
         return model.estimate_host(y, n_summands_or_proba, self.precision)
 
-    def weighted_log_prob(self, y, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
-        """``_estimate_weighted_log_prob`` of the prepared mixture (reference :369-386): ``[B, K]`` float64."""
-        if A is None:
-            A = np.eye(self.means_cplx.shape[1], dtype=complex)
-        model = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
+    def weighted_log_prob(self, y, snr_dB=None, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+        """``_estimate_weighted_log_prob`` of the prepared mixture (reference :369-386): ``[B, K]`` float64.  With ``snr_dB=None``
+        the setting prepared by the most recent ``estimate_from_y`` is used -- the reference's calling convention, whose
+        ``predict_proba_cplx(X)`` reads the state ``_prepare_for_prediction`` left in ``self.gm``."""
+        if snr_dB is None:
+            if self._last is None:
+                raise RuntimeError('Gmm_nbit: call estimate_from_y first (or pass snr_dB, n_bits, ...), like the reference, whose '
+                                   'predict_proba_cplx uses the state left by _prepare_for_prediction')
+            model = self._last
+        else:
+            if A is None:
+                A = np.eye(self.means_cplx.shape[1], dtype=complex)
+            model = self._last = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
         yt = y if isinstance(y, torch.Tensor) and y.is_cuda else torch.as_tensor(np.asarray(y)).cuda()
         _, lp = model.estimate(yt, 'all', 'fp64', want_logp=True)
         return lp if isinstance(y, torch.Tensor) and y.is_cuda else lp.cpu().numpy()
 
-    def predict_proba_cplx(self, y, snr_dB, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+    _estimate_weighted_log_prob = weighted_log_prob
+
+    def predict_proba_cplx(self, y, snr_dB=None, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
         """Responsibilities ``p(k | r)`` of the prepared mixture (reference :351-367)."""
         lp = self.weighted_log_prob(y, snr_dB, A, n_bits, quantizer_type, quantizer)
         if isinstance(lp, torch.Tensor):
@@ -188,3 +199,8 @@ class Gmm_nbit:
         m = lp.max(axis=1, keepdims=True)
         e = np.exp(lp - m)
         return e / e.sum(axis=1, keepdims=True)
+
+    def _predict_cplx(self, y, snr_dB=None, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
+        """Hard labels: argmax of the weighted log-probabilities (reference :335-349)."""
+        lp = self.weighted_log_prob(y, snr_dB, A, n_bits, quantizer_type, quantizer)
+        return lp.argmax(dim=1) if isinstance(lp, torch.Tensor) else lp.argmax(axis=1)

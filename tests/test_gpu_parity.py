@@ -109,6 +109,9 @@ def test_gmm_golden_fp64(qce, golden_gmm, tag):
     np.testing.assert_allclose(lp, g[f'{tag}_wlp'], rtol=1e-11)
     np.testing.assert_allclose(m.predict_proba_cplx(g[f'{tag}_r'], float(g[f'{tag}_snr']), g[f'{tag}_A'], _nb(g, tag),
                                                     str(g[f'{tag}_qtype']), qz), g[f'{tag}_proba'], rtol=1e-9, atol=1e-300)
+    # the reference's calling convention: predict_proba_cplx(X) / _predict_cplx(X) use the setting of the last estimate_from_y
+    np.testing.assert_allclose(m.predict_proba_cplx(g[f'{tag}_r']), g[f'{tag}_proba'], rtol=1e-9, atol=1e-300)
+    assert np.array_equal(m._predict_cplx(g[f'{tag}_r']), np.argmax(g[f'{tag}_proba'], axis=1))
 
 
 @pytest.mark.parametrize('tag', MFA_TAGS)
