@@ -1088,24 +1088,42 @@ qce_status tc_format(qce_model* m, cudaStream_t s, const double* r, int64_t B) {
 static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, int64_t B, int mode, int n_top, double rho, double* h_est,
                                double* logp_out, const void* h_true, int h_true_c64, double* acc) {
     if (m->n_comp > 1024) { set_error("tensor-core mode selection supports K <= 1024"); return QCE_ERR_UNSUPPORTED; }
-    qce_status st = tc_scratch_aux(ts, (size_t)B, (size_t)m->n_comp);
-    if (st) return st;
     if (!m->tc.image_z) { set_error("tensor-core mode selection needs a lower-triangular whitening factor"); return QCE_ERR_UNSUPPORTED; }
-    st = tc_run_split(m, ts, s, B, 1, 0, nullptr, nullptr, 0, nullptr);
+    // The log-probability / weight scratch is [rows][K]: walk the batch in chunks of whole work units so that it stays below
+    // 2^27 entries (1 GiB + 0.5 GiB) however large the batch is.
+    const int64_t unit_rows = 4 * TILE_M;
+    int64_t chunk = (((int64_t)1 << 27) / m->n_comp) / unit_rows * unit_rows;
+    if (const char* ce = getenv("QCE_TC_MODE_CHUNK")) chunk = atoll(ce) / unit_rows * unit_rows;      // test hook
+    if (chunk < unit_rows) chunk = unit_rows;
+    if (chunk > B) chunk = B;
+    qce_status st = tc_scratch_aux(ts, (size_t)chunk, (size_t)m->n_comp);
     if (st) return st;
     const bool want_est = h_est || acc;
-    {
-        const unsigned grid = (unsigned)((B + 7) / 8);
-        float* wts = want_est ? (float*)ts->wts : nullptr;
-        if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags, wts, logp_out);
-        else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags, wts, logp_out);
-        else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)ts->lp2, B, m->n_comp, mode, n_top, rho, m->flags, wts, logp_out);
-    }
-    QCE_CHECK_LAUNCH("tc_select_kernel");
-    if (!want_est) return QCE_OK;
-    for (int part = 0; part < m->tc.h_parts; ++part) {
-        st = tc_run_split(m, ts, s, B, 2, part, h_est, h_true, h_true_c64, acc);
+    const size_t tile_bytes = (size_t)TILE_M * 2 * m->n_obs * sizeof(__half) * (m->tc.split_a ? 2 : 1);
+    const size_t true_row = (size_t)m->n_ant * (h_true_c64 ? 8 : 16);
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = (B - b0) < chunk ? (B - b0) : chunk;
+        TileScratch v = *ts;                                   // view of this chunk's tiles (b0 is a multiple of the tile size)
+        v.img = (unsigned char*)ts->img + (size_t)(b0 / TILE_M) * tile_bytes;
+        v.bad = (unsigned char*)ts->bad + b0;
+        double* he = h_est ? h_est + (size_t)b0 * m->n_ant * 2 : nullptr;
+        double* lo = logp_out ? logp_out + (size_t)b0 * m->n_comp : nullptr;
+        const void* ht = h_true ? (const void*)((const char*)h_true + (size_t)b0 * true_row) : nullptr;
+        st = tc_run_split(m, &v, s, nb, 1, 0, nullptr, nullptr, 0, nullptr);
         if (st) return st;
+        {
+            const unsigned grid = (unsigned)((nb + 7) / 8);
+            float* wts = want_est ? (float*)v.wts : nullptr;
+            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo);
+            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo);
+            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo);
+        }
+        QCE_CHECK_LAUNCH("tc_select_kernel");
+        if (!want_est) continue;
+        for (int part = 0; part < m->tc.h_parts; ++part) {
+            st = tc_run_split(m, &v, s, nb, 2, part, he, ht, h_true_c64, acc);
+            if (st) return st;
+        }
     }
     return QCE_OK;
 }

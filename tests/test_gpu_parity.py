@@ -606,6 +606,27 @@ def test_tc_off_grid_pilots_three_pass(qce, K, N, B, snr, nb, qt, ms):
         assert acc.cpu().numpy()[2] == B
 
 
+def test_tc_mode_path_is_chunked(qce):
+    """The log-probability / weight scratch of the three-launch path is bounded: large batches are walked in chunks of whole work
+    units (QCE_TC_MODE_CHUNK shrinks the chunk for this test); results must not depend on the chunking."""
+    import os
+    K, N, B, snr = 5, 32, 1700, 5
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.1, seed=77)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    rt = torch.from_numpy(r).cuda()
+    model = m._prepared(np.eye(N), snr, 1, 'uniform', None)
+    ref = {mode: model.estimate(rt, mode, 'tc', want_logp=True, h_true=torch.from_numpy(h).cuda()) for mode in (1, 3, 0.9)}
+    os.environ['QCE_TC_MODE_CHUNK'] = '512'
+    try:
+        for mode, (e0, l0, a0) in ref.items():
+            e1, l1, a1 = model.estimate(rt, mode, 'tc', want_logp=True, h_true=torch.from_numpy(h).cuda())
+            assert torch.equal(e0, e1) and torch.equal(l0, l1)
+            np.testing.assert_allclose(a0.cpu().numpy(), a1.cpu().numpy(), rtol=1e-12)
+    finally:
+        del os.environ['QCE_TC_MODE_CHUNK']
+
+
 def test_tc_single_component_and_many_components(qce):
     for K, N in ((1, 64), (130, 16)):
         means, covs, w, h, noise, qz, r = _case(K, N, 300, 10, 1, 'uniform', 0.0, seed=K)
