@@ -7,8 +7,9 @@ does, and raises if the library or the device is missing (no CPU fallback).
 """
 from . import estimators, lloyd_max_quantizer, uniform_quantizer, utils  # noqa: F401
 from .gmm_cplx_bussgang import Gmm_nbit  # noqa: F401
+from .gmm_cplx_quant import Gmm_quant  # noqa: F401
 from .mofa_cplx_bussgang import Mofa  # noqa: F401
 from .utils import get_observation_nbit, get_quantizer, quant  # noqa: F401
 
-__all__ = ['Gmm_nbit', 'Mofa', 'quant', 'get_observation_nbit', 'get_quantizer', 'utils', 'uniform_quantizer',
+__all__ = ['Gmm_nbit', 'Gmm_quant', 'Mofa', 'quant', 'get_observation_nbit', 'get_quantizer', 'utils', 'uniform_quantizer',
            'lloyd_max_quantizer', 'estimators']

@@ -170,7 +170,10 @@ def load_reference_model(path):
             f.seek(0)
             obj = _Unpickler(path, f).load()
     kind = type(obj).__name__
-    if kind in ('Gmm_nbit', 'Gmm_quant'):
+    if kind == 'Gmm_quant':
+        from .gmm_cplx_quant import Gmm_quant
+        return Gmm_quant.from_reference(obj)
+    if kind == 'Gmm_nbit':
         return Gmm_nbit.from_reference(obj)
     if kind == 'Mofa':
         return Mofa.from_reference(obj)

@@ -178,3 +178,16 @@ def test_load_reference_model_files():
     np.testing.assert_array_equal(mfa.covs, g['mfa_covs'])
     np.testing.assert_array_equal(mfa.amps, g['w'])
     assert mfa._covs_are_low_rank
+
+
+def test_gmm_quant_is_an_inference_alias():
+    from quantized_channel_estimation_b200 import Gmm_nbit, Gmm_quant
+    g = Gmm_quant(n_components=2, covariance_type='full')
+    assert isinstance(g, Gmm_nbit) and Gmm_quant.estimate_from_y is Gmm_nbit.estimate_from_y
+    with pytest.raises(NotImplementedError):
+        g.fit(np.ones((4, 2), complex), 1, 0.1, None, 'uniform')
+    ref = type('Ref', (), {})()
+    ref.means_cplx, ref.covs_cplx = np.zeros((2, 3), complex), np.stack([np.eye(3, dtype=complex)] * 2)
+    ref.gm, ref.params = type('GM', (), {'weights_': np.array([0.4, 0.6])})(), {'zero_mean': True}
+    t = Gmm_quant.from_reference(ref)
+    assert isinstance(t, Gmm_quant) and t.params['zero_mean'] is True and t.gm.weights_[1] == 0.6
