@@ -92,8 +92,8 @@ class ClockSampler:
 
 
 def make_params():
-    from oracle import qce_oracle as orc            # seeded synthetic generators only (SURVEY.md section 8d P-rand)
-    return orc.random_psd_gmm(N_COMP, N_ANT, seed=0)
+    from quantized_channel_estimation_b200 import synthetic      # seeded synthetic generators (SURVEY.md section 8d P-rand)
+    return synthetic.random_psd_gmm(N_COMP, N_ANT, seed=0)
 
 
 def cpu_port_rate(means, covs, w, n_obs, snr=10, seed=123):

@@ -191,3 +191,20 @@ def test_gmm_quant_is_an_inference_alias():
     ref.gm, ref.params = type('GM', (), {'weights_': np.array([0.4, 0.6])})(), {'zero_mean': True}
     t = Gmm_quant.from_reference(ref)
     assert isinstance(t, Gmm_quant) and t.params['zero_mean'] is True and t.gm.weights_[1] == 0.6
+
+
+def test_package_synthetic_generators_match_the_oracle_copies():
+    """bench.py / tools/ build their workloads with quantized_channel_estimation_b200.synthetic (product side never imports the
+    oracle); the tests use the oracle's own generators: same arrays, seed for seed."""
+    from oracle import qce_oracle as orc
+    from quantized_channel_estimation_b200 import synthetic
+    for a, b in zip(synthetic.random_psd_gmm(3, 8, seed=4, mean_scale=0.2), orc.random_psd_gmm(3, 8, seed=4, mean_scale=0.2)):
+        assert np.array_equal(a, b)
+    for a, b in zip(synthetic.random_mfa(3, 8, 2, seed=5), orc.random_mfa(3, 8, 2, seed=5)):
+        assert np.array_equal(a, b)
+    for a, b in zip(synthetic.circulant_gmm(3, 2, 4, seed=6), orc.circulant_gmm(3, 2, 4, seed=6)):
+        assert np.array_equal(a, b)
+    assert synthetic.circulant_gmm(3, 2, 4, seed=6, dense=False)[1] is None
+    means, covs, w = orc.random_psd_gmm(3, 8, seed=4)
+    for a, b in zip(synthetic.sample_gmm_channels(means, covs, w, 50, seed=7), orc.sample_gmm_channels(means, covs, w, 50, seed=7)):
+        assert np.array_equal(a, b)

@@ -10,8 +10,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import qce_oracle as orc                      # seeded synthetic parameter generators only
 import quantized_channel_estimation_b200 as qce
+from quantized_channel_estimation_b200 import synthetic
 
 
 def timeit(fn, reps=3):
@@ -36,27 +36,27 @@ def main():
     out = []
     snr = 10
     # C1: GMM full, 1 bit, N=32, K=16
-    means, covs, w = orc.random_psd_gmm(16, 32, seed=0)
+    means, covs, w = synthetic.random_psd_gmm(16, 32, seed=0)
     m = qce.Gmm_nbit(n_components=16).set_parameters(means, covs, w, detect_structure=False)
     r = pilots(1 << 20, 32, 1, (None, None))
     ms = timeit(lambda: m.estimate_from_y(r, snr, 32, n_summands_or_proba='all'))
     out.append(dict(config='C1 GMM full 1-bit N=32 K=16', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='tc'))
     # C5 shape: GMM full, 1 bit, N=64, K=256
-    means, covs, w = orc.random_psd_gmm(256, 64, seed=0)
+    means, covs, w = synthetic.random_psd_gmm(256, 64, seed=0)
     m = qce.Gmm_nbit(n_components=256).set_parameters(means, covs, w, detect_structure=False)
     r = pilots(1 << 19, 64, 1, (None, None))
     ms = timeit(lambda: m.estimate_from_y(r, snr, 64, n_summands_or_proba='all'))
     out.append(dict(config='C5 GMM full 1-bit N=64 K=256', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='tc',
                     tflops_algorithmic=16 * 256 * 64 * 64 * r.shape[0] / ms / 1e9))
     # C2 other modes on the tensor-core path
-    means, covs, w = orc.random_psd_gmm(64, 64, seed=0)
+    means, covs, w = synthetic.random_psd_gmm(64, 64, seed=0)
     m = qce.Gmm_nbit(n_components=64).set_parameters(means, covs, w, detect_structure=False)
     r = pilots(1 << 19, 64, 1, (None, None))
     for mode in (1, 4, 0.9):
         ms = timeit(lambda: m.estimate_from_y(r, snr, 64, n_summands_or_proba=mode))
         out.append(dict(config=f'C2 GMM full 1-bit N=64 K=64 mode={mode}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='tc 3-launch'))
     # C3: block-circulant 16x16, 3-bit Lloyd, N=256, K=128
-    c, _, w, _ = orc.circulant_gmm(128, 16, 16, seed=0)
+    c, _, w, _ = synthetic.circulant_gmm(128, 16, 16, seed=0)
     qz = qce.get_quantizer([snr], 3, 'lloyd')[snr]
     m = qce.Gmm_nbit(n_components=128, covariance_type='block-circulant')
     m.covs_cplx = None
@@ -66,7 +66,7 @@ def main():
     out.append(dict(config='C3 GMM block-circulant 16x16 3-bit Lloyd N=256 K=128', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
                     path='circ tc (fp32 fft + split-fp16 mma)', gbytes_per_s=32 * 256 * r.shape[0] / ms / 1e6))
     # C4: MFA N=128, K=64, latent 16, 2-bit uniform (dense path, as the reference computes it)
-    means, lambdas, psis, amps = orc.random_mfa(64, 128, 16, seed=0)
+    means, lambdas, psis, amps = synthetic.random_mfa(64, 128, 16, seed=0)
     qz = qce.get_quantizer([snr], 2, 'uniform')[snr]
     mf = qce.Mofa(64, 16, verbose=False).set_parameters(means, lambdas, psis, amps)
     mf.precision = 'fp64'                                 # complex128: the Woodbury kernel
@@ -89,7 +89,7 @@ def main():
     out.append(dict(config='C4 shape, MFA N=128 K=64 M=16 3-bit Lloyd-Max', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
                     path='dense tc split, off-grid pilots', tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9))
     # GMM full, 1 bit, N=128, K=64 (same kernels)
-    means, covs, w = orc.random_psd_gmm(64, 128, seed=0)
+    means, covs, w = synthetic.random_psd_gmm(64, 128, seed=0)
     m = qce.Gmm_nbit(n_components=64).set_parameters(means, covs, w, detect_structure=False)
     m.precision = 'tc'
     r = pilots(1 << 19, 128, 1, (None, None))

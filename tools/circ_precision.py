@@ -1,10 +1,12 @@
+#!/usr/bin/env python
+"""Per-pilot error statistics of circ_tc_kernel against the complex128 circ_kernel at config 3 (same pilots, same parameters)."""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
-from oracle import qce_oracle as orc
 import quantized_channel_estimation_b200 as qce
+from quantized_channel_estimation_b200 import synthetic
 K, N, B, snr = 128, 256, 4096, 10
-c, covs, w, F = orc.circulant_gmm(K, 16, 16, seed=0)
-qz = orc.get_quantizer([snr], 3, 'lloyd')[snr]
+c, covs, w, F = synthetic.circulant_gmm(K, 16, 16, seed=0, dense=False)
+qz = qce.get_quantizer([snr], 3, 'lloyd')[snr]
 m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
 m.set_circulant_parameters(c, w, (16, 16))
 g = torch.Generator(device='cuda').manual_seed(3)

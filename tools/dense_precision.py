@@ -10,9 +10,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import qce_oracle as orc                      # seeded synthetic parameter generator only
 import quantized_channel_estimation_b200 as qce
-from quantized_channel_estimation_b200 import engine, precompute
+from quantized_channel_estimation_b200 import engine, precompute, synthetic
 
 
 def stats(tag, model, r):
@@ -32,10 +31,10 @@ def main():
     for tag, K, N, snr, nb, qt in (('C2 N=64 K=64 1-bit 10dB', 64, 64, 10, 1, 'uniform'), ('C2 -10dB', 64, 64, -10, 1, 'uniform'),
                                    ('C2 30dB', 64, 64, 30, 1, 'uniform'), ('N=128 K=64 2-bit split path', 64, 128, 10, 2, 'uniform'),
                                    ('N=64 K=32 3-bit Lloyd (off-grid)', 32, 64, 10, 3, 'lloyd')):
-        means, covs, w = orc.random_psd_gmm(K, N, seed=0)
-        h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=1)
-        qz = orc.get_quantizer([snr], nb, qt)[snr]
-        r = torch.from_numpy(orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])).cuda()
+        means, covs, w = synthetic.random_psd_gmm(K, N, seed=0)
+        h, noise, _ = synthetic.sample_gmm_channels(means, covs, w, B, seed=1)
+        qz = qce.get_quantizer([snr], nb, qt)[snr]
+        r = qce.get_observation_nbit(torch.from_numpy(h).cuda(), snr, n_bits=nb, thresholds=qz[0], cluster=qz[1], noise=torch.from_numpy(noise).cuda())
         model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, nb, qt, qz))
         stats(tag, model, r)
 

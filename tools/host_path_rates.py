@@ -10,8 +10,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import qce_oracle as orc                      # seeded synthetic parameter generator only
 import quantized_channel_estimation_b200 as qce
+from quantized_channel_estimation_b200 import synthetic
 
 
 def rate(fn, B, N, reps=3):
@@ -27,7 +27,7 @@ def main():
     snr = 10
     # config 2: dense GMM, 1 bit, N = 64, K = 64
     K, N, B = 64, 64, 1 << 19
-    means, covs, w = orc.random_psd_gmm(K, N, seed=0)
+    means, covs, w = synthetic.random_psd_gmm(K, N, seed=0)
     m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
     g = torch.Generator(device='cuda').manual_seed(0)
     bits = torch.randint(0, 2, (B, N, 2), generator=g, device='cuda', dtype=torch.int8)
@@ -39,7 +39,7 @@ def main():
     print(json.dumps(dict(case='C2 dense, pinned input (output array still pageable)', **rate(lambda: m.estimate_from_y(rp.numpy(), snr, N, n_summands_or_proba='all'), B, N))), flush=True)
     # config 3: block-circulant, 3-bit Lloyd-Max, N = 256, K = 128
     K, N, B = 128, 256, 1 << 17
-    c, _, w, _ = orc.circulant_gmm(K, 16, 16, seed=0)
+    c, _, w, _ = synthetic.circulant_gmm(K, 16, 16, seed=0)
     qz = qce.get_quantizer([snr], 3, 'lloyd')[snr]
     mc = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
     mc.set_circulant_parameters(c, w, (16, 16))

@@ -8,15 +8,15 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import qce_oracle as orc                      # seeded synthetic parameter generator only
 import quantized_channel_estimation_b200 as qce
+from quantized_channel_estimation_b200 import synthetic
 from bench_configs import pilots, timeit
 
 
 def main():
     snr, K = 10, int(os.environ.get('K', 128))
     B = 1 << int(os.environ.get('LOG2B', 19))
-    c, _, w, _ = orc.circulant_gmm(K, 16, 16, seed=0)
+    c, _, w, _ = synthetic.circulant_gmm(K, 16, 16, seed=0)
     qz = qce.get_quantizer([snr], 3, 'lloyd')[snr]
     m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
     m.set_circulant_parameters(c, w, (16, 16))

@@ -11,9 +11,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import qce_oracle as orc                      # seeded synthetic parameter generator only
 import quantized_channel_estimation_b200 as qce
-from quantized_channel_estimation_b200 import _lib, engine, precompute
+from quantized_channel_estimation_b200 import _lib, engine, precompute, synthetic
 from bench_configs import timeit
 
 
@@ -21,14 +20,14 @@ def main():
     K, N = int(os.environ.get('K', 64)), 64
     B = 1 << int(os.environ.get('LOG2B', 20))
     snrs = [int(x) for x in os.environ.get('SNRS', '-10,10,30').split(',')]
-    means, covs, w = orc.random_psd_gmm(K, N, seed=0)
-    h, noise, _ = orc.sample_gmm_channels(means, covs, w, 1 << 14, seed=1)
+    means, covs, w = synthetic.random_psd_gmm(K, N, seed=0)
+    h, noise, _ = synthetic.sample_gmm_channels(means, covs, w, 1 << 14, seed=1)
     lib = _lib.load()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     out = torch.empty((B, N), dtype=torch.complex128, device='cuda')
     ab = [x for x in os.environ.get('AB', 'SKIP=1e-12').split(';') if x]
     for snr in snrs:
-        r = torch.from_numpy(orc.get_observation_nbit(h, snr, noise, None, 1)).cuda().repeat(B >> 14, 1).contiguous()
+        r = qce.get_observation_nbit(torch.from_numpy(h).cuda(), snr, n_bits=1, noise=torch.from_numpy(noise).cuda()).repeat(B >> 14, 1).contiguous()
         model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, 1))
         _lib.check(lib.qce_format_pilots(model.handle, stream, C.c_void_p(r.data_ptr()), B))
         run = lambda: _lib.check(lib.qce_estimate_formatted(model.handle, stream, B, C.c_void_p(out.data_ptr()), None, None))

@@ -9,15 +9,15 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import qce_oracle as orc                      # seeded synthetic parameter generator only
 import quantized_channel_estimation_b200 as qce
+from quantized_channel_estimation_b200 import synthetic
 from bench_configs import pilots, timeit
 
 
 def main():
     snr, K, N = 10, int(os.environ.get('K', 64)), int(os.environ.get('N', 128))
     B = 1 << int(os.environ.get('LOG2B', 19))
-    means, covs, w = orc.random_psd_gmm(K, N, seed=0)
+    means, covs, w = synthetic.random_psd_gmm(K, N, seed=0)
     m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
     m.precision = 'tc'
     r = pilots(B, N, 1, (None, None))

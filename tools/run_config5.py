@@ -23,8 +23,8 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import qce_oracle as orc                      # seeded synthetic parameter generator only
 import quantized_channel_estimation_b200 as qce
+from quantized_channel_estimation_b200 import synthetic
 from quantized_channel_estimation_b200 import engine, montecarlo
 
 N_ANT, N_COMP, CHUNK = 64, 256, 1 << 20
@@ -61,7 +61,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    means, covs, w = orc.random_psd_gmm(N_COMP, N_ANT, seed=0)
+    means, covs, w = synthetic.random_psd_gmm(N_COMP, N_ANT, seed=0)
     gmm = qce.Gmm_nbit(n_components=N_COMP, covariance_type='full').set_parameters(means, covs, w, zero_mean=True, detect_structure=False)
     eye = np.eye(N_ANT, dtype=complex)
     models = [gmm._prepared(eye, s, 1, 'uniform', None) for s in SNRS]
