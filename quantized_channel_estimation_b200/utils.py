@@ -110,6 +110,16 @@ def get_pilot_matrix(n_antennas, n_pilots=1, pilots=None):
     return np.kron(x[:, None], np.eye(n_antennas)).astype(complex)
 
 
+def toeplitz(c, r=None):
+    """Toeplitz matrix with first column ``c`` and first row ``r`` (``conj(c)`` if omitted) -- the helper of the reference
+    (modules/utils.py:115-165, a copy of ``scipy.linalg.toeplitz``) the scripts use as ``toeplitz(t).T`` for channel covariances."""
+    c = np.asarray(c).ravel()
+    r = np.conjugate(c) if r is None else np.asarray(r).ravel()
+    vals = np.concatenate((c[::-1], r[1:]))
+    idx = (len(c) - 1) + np.arange(len(r))[None, :] - np.arange(len(c))[:, None]
+    return vals[idx]
+
+
 def mse(h_est, h):
     """The scripts' NMSE: ``sum |h_est - h|^2 / h.size`` (reference :617-618, Bussgang_GMM.py:289)."""
     if isinstance(h_est, torch.Tensor) or isinstance(h, torch.Tensor):

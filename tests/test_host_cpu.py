@@ -208,3 +208,13 @@ def test_package_synthetic_generators_match_the_oracle_copies():
     means, covs, w = orc.random_psd_gmm(3, 8, seed=4)
     for a, b in zip(synthetic.sample_gmm_channels(means, covs, w, 50, seed=7), orc.sample_gmm_channels(means, covs, w, 50, seed=7)):
         assert np.array_equal(a, b)
+
+
+def test_toeplitz_helper_matches_scipy():
+    import scipy.linalg
+    from quantized_channel_estimation_b200 import utils
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal(6) + 1j * rng.standard_normal(6)
+    r = rng.standard_normal(4) + 1j * rng.standard_normal(4)
+    assert np.array_equal(utils.toeplitz(c), scipy.linalg.toeplitz(c))
+    assert np.array_equal(utils.toeplitz(c, r), scipy.linalg.toeplitz(c, r))
