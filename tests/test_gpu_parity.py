@@ -546,19 +546,23 @@ def test_tc_split_path_large_antenna_counts(qce, K, N, B, snr, nb, ms):
     np.testing.assert_allclose(acc[1], np.sum(np.abs(h) ** 2), rtol=1e-5)
 
 
-def test_tc_split_path_two_pilots(qce):
-    """A = kron(x, I): n_obs = 2 N = 128 observations of 64 antennas (one row block of 128 columns)."""
-    K, N, B, snr = 5, 64, 400, 5
-    means, covs, w = orc.random_psd_gmm(K, N, seed=21, mean_scale=0.1)
+@pytest.mark.parametrize('N,nb,qt', [(64, 1, 'uniform'), (32, 1, 'uniform'), (16, 2, 'uniform'), (32, 3, 'lloyd'), (64, 2, 'lloyd')])
+def test_tc_two_pilots(qce, N, nb, qt):
+    """A = kron(x, I): n_obs = 2 N observations of N antennas.  N = 64: split path (one row block of 128 columns); N = 32 / 16: the
+    fused kernel with Z twice as wide as H; Lloyd-Max rows: off-grid pilots as (hi, lo) tile pairs on both."""
+    K, B, snr = 5, 400, 5
+    means, covs, w = orc.random_psd_gmm(K, N, seed=21 + N, mean_scale=0.1)
     h, _, _ = orc.sample_gmm_channels(means, covs, w, B, seed=22)
     A = np.kron(np.array([[1.0], [1j]]), np.eye(N))
     noise = orc.crandn(B, 2 * N, rng=np.random.default_rng(23))
-    r = orc.get_observation_nbit(h, snr, noise, A, 1)
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    r = orc.get_observation_nbit(h, snr, noise, A, nb, qz[0], qz[1])
     m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
     m.precision = 'tc'
     rt = torch.from_numpy(r).cuda()
-    _check_modes(lambda mode: m.estimate_from_y(rt, snr, N, A=A, n_summands_or_proba=mode).cpu().numpy(),
-                 lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, snr, A=A, n_summands_or_proba=mode, n_bits=1), B)
+    _check_modes(lambda mode: m.estimate_from_y(rt, snr, N, A=A, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz).cpu().numpy(),
+                 lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, snr, A=A, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
+                                                      quantizer=qz), B)
 
 
 def test_tc_split_path_mfa_config4_shape(qce):
