@@ -632,13 +632,15 @@ def test_tc_mode_path_is_chunked(qce):
 
 
 def test_tc_single_component_and_many_components(qce):
-    for K, N in ((1, 64), (130, 16)):
-        means, covs, w, h, noise, qz, r = _case(K, N, 300, 10, 1, 'uniform', 0.0, seed=K)
+    """K = 1, and K = 130 / 300: the selection kernel holds 2, 8 or 32 entries per lane depending on K."""
+    for K, N in ((1, 64), (130, 16), (300, 16)):
+        B = 300
+        means, covs, w, h, noise, qz, r = _case(K, N, B, 10, 1, 'uniform', 0.0, seed=K)
         m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
         m.precision = 'tc'
-        ref = orc.gmm_estimate_from_y(means, covs, w, r, 10, n_summands_or_proba='all', n_bits=1)
-        est = m.estimate_from_y(torch.from_numpy(r).cuda(), 10, N, n_summands_or_proba='all').cpu().numpy()
-        assert relerr(est, ref) < TOL_TC
+        rt = torch.from_numpy(r).cuda()
+        _check_modes(lambda mode: m.estimate_from_y(rt, 10, N, n_summands_or_proba=mode).cpu().numpy(),
+                     lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, 10, n_summands_or_proba=mode, n_bits=1), B)
 
 
 def test_tc_off_grid_pilots_come_back_nan(qce):
