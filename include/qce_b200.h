@@ -157,7 +157,7 @@ qce_status qce_circ_model_set_params(qce_circ_model* m, void* stream, const doub
 qce_status qce_circ_estimate(qce_circ_model* m, void* stream, const void* r_dev, int64_t B, int mode, int n_top, double rho,
                              void* h_est_dev, double* logp_out_dev, const void* h_true_dev, double* acc_dev);
 /* The same with a precision selector.  QCE_PREC_FP64: the complex128 kernel above.  QCE_PREC_TC: FP32 radix-4 FFTs and
- * split-FP16 tensor-core contractions (16 x 16 blocks, K = 64 or 128; any real-valued pilots; estimates within ~1e-6 of the
+ * split-FP16 tensor-core contractions (16 x 16 blocks or plain circulant of length 256, K = 64 or 128; any real-valued pilots; estimates within ~1e-6 of the
  * complex128 path), QCE_ERR_UNSUPPORTED for other shapes. */
 qce_status qce_circ_estimate_prec(qce_circ_model* m, void* stream, const void* r_dev, int64_t B, int mode, int n_top, double rho,
                                   int precision, void* h_est_dev, double* logp_out_dev, const void* h_true_dev, double* acc_dev);

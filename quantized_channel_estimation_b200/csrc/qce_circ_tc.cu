@@ -44,6 +44,7 @@ struct CircTcArgs {
     const uint4* b2;                 // packed gain fragments      [32][K/16][32]
     const float2* logc2;             // [K] logc - max(logc) as (hi, lo)
     const float* ilbar;              // [N] mean over the components of 1 / lambda: reference quadratic form per pilot
+    const float2* tw256;             // plain circulant (one 256-point DFT = 16 x 16 Cooley-Tukey): e^{-2 pi i m / 256}, else null
     double logc_max;
     float inv_s1, inv_s2;            // 2^-s of the packed operands
     const double2* r;
@@ -164,6 +165,13 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
             for (int ar = 0; ar < 16; ++ar) v[ar] = make_float2(0.f, 0.f);
         }
         fft16<false>(v);
+        if (a.tw256) {                         // plain circulant: twiddle W_256^(n2 k1) between the two radix-16 stages
+            #pragma unroll
+            for (int ar = 1; ar < 16; ++ar) {
+                const float2 w = __ldg(a.tw256 + ((b * ar) & 255));
+                v[ar] = make_float2(v[ar].x * w.x - v[ar].y * w.y, v[ar].x * w.y + v[ar].y * w.x);
+            }
+        }
         #pragma unroll
         for (int ar = 0; ar < 16; ++ar) X[xidx(p, ar, b)] = v[ar];
     }
@@ -418,6 +426,13 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
             float2 v[16];
             #pragma unroll
             for (int ar = 0; ar < 16; ++ar) v[ar] = X[xidx(p, ar, b)];
+            if (a.tw256) {
+                #pragma unroll
+                for (int ar = 1; ar < 16; ++ar) {
+                    const float2 w = __ldg(a.tw256 + ((b * ar) & 255));
+                    v[ar] = make_float2(v[ar].x * w.x + v[ar].y * w.y, v[ar].y * w.x - v[ar].x * w.y);
+                }
+            }
             fft16<true>(v);
             if (p < nvalid) {
                 const size_t o = (size_t)(base + p) * CT_N + b;
@@ -454,8 +469,12 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
 // b0 = {B[16 ks + 2t][8 nb + g], B[16 ks + 2t + 1][.]}, b1 = the same 8 rows further; stored as uint4 {b0 hi, b1 hi, b0 lo, b1 lo}.
 // which = 0: B[i][k] = 1 / lambda (source inv_lambda_t [N][K]),  which = 1: B[k][i] = gain (source gain [K][N]).
 // sub != nullptr: sub[row] is subtracted first (the 1 / lambda operand is packed as its deviation from the mean over the components).
+// one_d: the bin axis (rows of 1 / lambda, columns of the gains) is stored in the order the two-stage 256-point FFT leaves it:
+// position s = 16 k1 + k2 holds frequency k1 + 16 k2.
+__device__ __forceinline__ int circ_bin_of(int s, int one_d) { return one_d ? (s >> 4) + 16 * (s & 15) : s; }
+
 __global__ void circ_tc_pack_kernel(const double* __restrict__ src, const float* __restrict__ sub, int rows, int cols, double scale,
-                                    uint4* __restrict__ out) {
+                                    uint4* __restrict__ out, int perm_rows, int perm_cols) {
     const int nks = rows / 16, nnb = cols / 8;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nnb * nks * 32) return;
@@ -465,7 +484,7 @@ __global__ void circ_tc_pack_kernel(const double* __restrict__ src, const float*
     #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int row = ks * 16 + 2 * t + (e & 1) + 8 * (e >> 1);
-        const double x = (src[(size_t)row * cols + col] - (sub ? (double)sub[row] : 0.0)) * scale;
+        const double x = (src[(size_t)circ_bin_of(row, perm_rows) * cols + circ_bin_of(col, perm_cols)] - (sub ? (double)sub[row] : 0.0)) * scale;
         hi[e] = __double2half(x);
         lo[e] = __double2half(x - (double)__half2float(hi[e]));
     }
@@ -478,12 +497,19 @@ __global__ void circ_tc_logc_kernel(const double* __restrict__ logc, int K, doub
     if (k < K) { const double l = logc[k] - logc_max; const float hi = (float)l; out[k] = make_float2(hi, (float)(l - (double)hi)); }
 }
 
-__global__ void circ_tc_ilbar_kernel(const double* __restrict__ inv_lambda_t, int N, int K, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void circ_tc_ilbar_kernel(const double* __restrict__ inv_lambda_t, int N, int K, int one_d, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // storage position
     if (i >= N) return;
     double sum = 0.0;
-    for (int k = 0; k < K; ++k) sum += inv_lambda_t[(size_t)i * K + k];
+    for (int k = 0; k < K; ++k) sum += inv_lambda_t[(size_t)circ_bin_of(i, one_d) * K + k];
     out[i] = (float)(sum / K);
+}
+
+__global__ void circ_tc_twiddle_kernel(float2* __restrict__ out) {
+    const int m = threadIdx.x;
+    double sn, cs;
+    sincospi(-2.0 * m / 256.0, &sn, &cs);
+    out[m] = make_float2((float)cs, (float)sn);
 }
 
 double pow2_scale_for(const double* dev, size_t n, cudaStream_t s, qce_status* st) {
@@ -508,11 +534,13 @@ double pow2_scale_for(const double* dev, size_t n, cudaStream_t s, qce_status* s
 
 }  // namespace
 
-bool circ_tc_shape_ok(const qce_circ_model* m) { return m->n1 == 16 && m->n2 == 16 && (m->n_comp == 64 || m->n_comp == 128); }
+bool circ_tc_shape_ok(const qce_circ_model* m) {     // block-circulant 16 x 16, or plain circulant of length 256 (one two-stage FFT)
+    return ((m->n1 == 16 && m->n2 == 16) || (m->n1 == 1 && m->n2 == 256)) && (m->n_comp == 64 || m->n_comp == 128);
+}
 
 void circ_tc_free(qce_circ_model* m) {
-    cudaFree(m->tc_b1); cudaFree(m->tc_b2); cudaFree(m->tc_logc2); cudaFree(m->tc_ilbar);
-    m->tc_b1 = m->tc_b2 = m->tc_logc2 = m->tc_ilbar = nullptr;
+    cudaFree(m->tc_b1); cudaFree(m->tc_b2); cudaFree(m->tc_logc2); cudaFree(m->tc_ilbar); cudaFree(m->tc_tw);
+    m->tc_b1 = m->tc_b2 = m->tc_logc2 = m->tc_ilbar = m->tc_tw = nullptr;
     m->tc_ready = false;
 }
 
@@ -533,12 +561,18 @@ qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s) {
         QCE_CUDA_TRY(cudaMalloc(&m->tc_logc2, K * sizeof(float2)));
         QCE_CUDA_TRY(cudaMalloc(&m->tc_ilbar, N * sizeof(float)));
     }
+    const int one_d = m->n1 == 1;
+    if (one_d && !m->tc_tw) {
+        QCE_CUDA_TRY(cudaMalloc(&m->tc_tw, 256 * sizeof(float2)));
+        circ_tc_twiddle_kernel<<<1, 256, 0, s>>>((float2*)m->tc_tw);
+        QCE_CHECK_LAUNCH("circ_tc_twiddle_kernel");
+    }
     const int total = (int)(N * K / 4);
-    circ_tc_ilbar_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(m->inv_lambda_t, (int)N, (int)K, (float*)m->tc_ilbar);
+    circ_tc_ilbar_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(m->inv_lambda_t, (int)N, (int)K, one_d, (float*)m->tc_ilbar);
     QCE_CHECK_LAUNCH("circ_tc_ilbar_kernel");
-    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->inv_lambda_t, (const float*)m->tc_ilbar, (int)N, (int)K, s1, (uint4*)m->tc_b1);
+    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->inv_lambda_t, (const float*)m->tc_ilbar, (int)N, (int)K, s1, (uint4*)m->tc_b1, one_d, 0);
     QCE_CHECK_LAUNCH("circ_tc_pack_kernel");
-    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->gain, nullptr, (int)K, (int)N, s2, (uint4*)m->tc_b2);
+    circ_tc_pack_kernel<<<(total + 255) / 256, 256, 0, s>>>(m->gain, nullptr, (int)K, (int)N, s2, (uint4*)m->tc_b2, 0, one_d);
     QCE_CHECK_LAUNCH("circ_tc_pack_kernel");
     {
         double* h_logc = (double*)malloc(K * sizeof(double));
@@ -582,6 +616,7 @@ qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double*
     a.K = m->n_comp; a.B = B;
     a.b1 = (const uint4*)m->tc_b1; a.b2 = (const uint4*)m->tc_b2; a.logc2 = (const float2*)m->tc_logc2;
     a.ilbar = (const float*)m->tc_ilbar; a.logc_max = m->tc_logc_max;
+    a.tw256 = (m->n1 == 1) ? (const float2*)m->tc_tw : nullptr;
     a.inv_s1 = m->tc_inv_s1; a.inv_s2 = m->tc_inv_s2;
     a.r = (const double2*)r; a.h_est = (double2*)h_est; a.logp_out = logp_out; a.h_true = (const double2*)h_true; a.acc = acc;
     a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;

@@ -391,15 +391,16 @@ def test_circulant_kernel_vs_dense_oracle(qce, n1, n2, K, nb, qt, tol):
     assert relerr(m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz), dense) < max(tol, 1e-5)
 
 
-@pytest.mark.parametrize('K,nb,qt,B', [
-    (128, 3, 'lloyd', 150),          # config 3: 256 antennas, 16x16 blocks, 3-bit Lloyd-Max, K = 128 (ragged batch)
-    (64, 1, 'uniform', 97),
-    (64, np.inf, 'uniform', 33),     # unquantised pilots: no grid assumption in this kernel
+@pytest.mark.parametrize('K,nb,qt,B,n1,n2', [
+    (128, 3, 'lloyd', 150, 16, 16),          # config 3: 256 antennas, 16x16 blocks, 3-bit Lloyd-Max, K = 128 (ragged batch)
+    (64, 1, 'uniform', 97, 16, 16),
+    (64, np.inf, 'uniform', 33, 16, 16),     # unquantised pilots: no grid assumption in this kernel
+    (128, 3, 'lloyd', 140, 1, 256),          # config 3, plain circulant: one 256-point DFT as a two-stage 16 x 16 FFT with twiddles
+    (64, 2, 'uniform', 70, 1, 256),
 ])
-def test_circulant_tc_kernel_vs_dense_oracle(qce, K, nb, qt, B):
+def test_circulant_tc_kernel_vs_dense_oracle(qce, K, nb, qt, B, n1, n2):
     """FP32-FFT + split-FP16 tensor-core version of the DFT-domain kernel against the oracle's dense path."""
     from quantized_channel_estimation_b200.engine import CircModel
-    n1 = n2 = 16
     N, snr = 256, 8
     c, covs, w, F = orc.circulant_gmm(K, n1, n2, seed=K)
     h, noise, _ = orc.sample_gmm_channels(np.zeros((K, N), complex), covs, w, B, seed=5)

@@ -65,6 +65,13 @@ def main():
     ms = timeit(lambda: m.estimate_from_y(r, snr, 256, n_summands_or_proba='all', n_bits=3, quantizer_type='lloyd', quantizer=qz))
     out.append(dict(config='C3 GMM block-circulant 16x16 3-bit Lloyd N=256 K=128', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
                     path='circ tc (fp32 fft + split-fp16 mma)', gbytes_per_s=32 * 256 * r.shape[0] / ms / 1e6))
+    # C3, plain 'circulant' variant: one 256-point DFT (two-stage 16 x 16 FFT with twiddles), same kernel
+    c1, _, w1, _ = synthetic.circulant_gmm(128, 1, 256, seed=0, dense=False)
+    m1 = qce.Gmm_nbit(n_components=128, covariance_type='circulant')
+    m1.set_circulant_parameters(c1, w1, (1, 256))
+    ms = timeit(lambda: m1.estimate_from_y(r, snr, 256, n_summands_or_proba='all', n_bits=3, quantizer_type='lloyd', quantizer=qz))
+    out.append(dict(config='C3 GMM circulant 3-bit Lloyd N=256 K=128', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
+                    path='circ tc (fp32 fft + split-fp16 mma)', gbytes_per_s=32 * 256 * r.shape[0] / ms / 1e6))
     # C4: MFA N=128, K=64, latent 16, 2-bit uniform (dense path, as the reference computes it)
     means, lambdas, psis, amps = synthetic.random_mfa(64, 128, 16, seed=0)
     qz = qce.get_quantizer([snr], 2, 'uniform')[snr]
