@@ -632,6 +632,23 @@ def test_tc_mode_path_is_chunked(qce):
         del os.environ['QCE_TC_MODE_CHUNK']
 
 
+@pytest.mark.parametrize('scale,snr,nb', [(1e4, 0, 1), (1e-4, 0, 1), (1.0, 40, 1), (1e3, 20, 2), (1.0, -30, 2)])
+def test_tc_parameter_scales_and_extreme_snr(qce, scale, snr, nb):
+    """Channel power far from one and extreme SNRs: the power-of-two normalisation of the FP16 operand images and the FP32 (hi, lo)
+    log-probabilities must hold the tensor-core path on the oracle."""
+    K, N, B = 7, 32, 300
+    means, covs, w = orc.random_psd_gmm(K, N, seed=91, mean_scale=0.1)
+    means, covs = means * np.sqrt(scale), covs * scale
+    h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=92)
+    qz = orc.get_quantizer([snr], nb, 'uniform')[snr]
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    rt = torch.from_numpy(r).cuda()
+    _check_modes(lambda mode: m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer=qz).cpu().numpy(),
+                 lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer=qz), B)
+
+
 def test_tc_single_component_and_many_components(qce):
     """K = 1, and K = 130 / 300: the selection kernel holds 2, 8 or 32 entries per lane depending on K."""
     for K, N in ((1, 64), (130, 16), (300, 16)):
