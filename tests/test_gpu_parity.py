@@ -432,6 +432,28 @@ def test_circulant_tc_kernel_vs_dense_oracle(qce, K, nb, qt, B, n1, n2):
     np.testing.assert_allclose(acc[1], np.sum(np.abs(h) ** 2), rtol=1e-4)
 
 
+@pytest.mark.parametrize('scale,snr,nb,qt', [(1e3, 10, 3, 'lloyd'), (1e-3, 0, 2, 'uniform'), (1.0, 35, 1, 'uniform'), (1.0, -20, 3, 'lloyd')])
+def test_circulant_tc_kernel_scales_and_extreme_snr(qce, scale, snr, nb, qt):
+    """Per-pilot scaling of |rt|^2, global scaling of the parameter fragments and the compensated log-likelihood accumulation under
+    channel powers far from one and extreme SNRs; against the complex128 kernel on the same pilots."""
+    K, N, B = 64, 256, 200
+    c, _, w, _ = orc.circulant_gmm(K, 16, 16, seed=17)
+    c = c * scale
+    m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
+    m.set_circulant_parameters(c, w, (16, 16))
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    g = torch.Generator(device='cuda').manual_seed(18)
+    y = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float64)) * float(np.sqrt(scale + 10 ** (-snr / 10)))
+    r = qce.quant(y, nb, qz[0], qz[1])
+    model = m._prepared(np.eye(N), snr, nb, qt, qz)
+    e_tc, lp_tc = model.estimate(r, 'all', 'tc', want_logp=True)
+    e_64, lp_64 = model.estimate(r, 'all', 'fp64', want_logp=True)
+    assert torch.isfinite(torch.view_as_real(e_tc)).all()
+    per = (e_tc - e_64).norm(dim=1) / e_64.norm(dim=1).clamp(min=1e-300)
+    assert float((e_tc - e_64).norm() / e_64.norm()) < TOL_TC and float(per.max()) < 1e-4, (float(per.max()),)
+    assert float((lp_tc - lp_64).abs().max()) < 5e-3 * max(1.0, float(lp_64.abs().max()) / 300)
+
+
 # ----------------------------------------------------------------------------- MFA Woodbury kernel
 
 @pytest.mark.parametrize('K,N,M,nb,qt,ms', [
