@@ -93,6 +93,7 @@ struct TcCtrl {
     uint64_t a_full, a_free;
     uint32_t tmem_base;
     uint32_t pad;
+    uint64_t fmt_done;       // PRO: the eight epilogue warps have written their shares of the next work unit's pilot tiles
 };
 static_assert(sizeof(TcCtrl) <= 1024, "control block");
 
@@ -134,10 +135,103 @@ __device__ __forceinline__ void tc_issue_chunk(const int q, const uint32_t d_til
     }
 }
 
+// In-kernel prologue (PRO): observe (A = I) + quantise + format the pilots straight into the tile image the bulk copies read, same
+// arithmetic as tc_format_kernel<true, ., false>.  One ITEM = one 128-byte core matrix = 8 pilots x 4 complex, one element per lane;
+// item i of a work unit of NTILES tiles: pair = i / kbs -> (tile, 8-row block), K-core kb = i % kbs.  The loads of an item are issued
+// early (fmt_load) and consumed late (fmt_store) so that their latency hides behind the epilogue work in between.  Rows that are not
+// on the grid are flagged by an atomicOr on the (zero-initialised) flag bytes.
+struct FmtItem { double2 h, w; float2 hf; };
+
+template <bool H_C64>
+__device__ __forceinline__ void fmt_load(const TcArgs& a, int64_t first_tile, int KD, int item, int lane, FmtItem& it) {
+    const int kbs = KD / 8, No = KD / 2;
+    const int pair = item / kbs, kb = item - pair * kbs;
+    const int64_t g = (first_tile + pair / (TILE_M / 8)) * TILE_M + (pair % (TILE_M / 8)) * 8 + (lane & 7);
+    const size_t e = (size_t)(g < a.B ? g : 0) * No + kb * 4 + (lane >> 3);
+    // volatile asm: the compiler must not sink these loads down to their use (it does, to save registers, and then every component
+    // of the epilogue eats a full memory latency)
+    if (H_C64) asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(it.hf.x), "=f"(it.hf.y) : "l"(reinterpret_cast<const float2*>(a.obs_h) + e));
+    else asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(it.h.x), "=d"(it.h.y) : "l"(reinterpret_cast<const double2*>(a.obs_h) + e));
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(it.w.x), "=d"(it.w.y) : "l"(a.obs_noise + e));
+}
+
+// double -> float through the integer pipe (round half up on the magnitude; FP32-normal range, else the hardware conversion): the
+// FP64 / conversion pipes crawl while the tensor pipe is saturated, and this runs inside the estimate kernel's epilogue warps
+__device__ __forceinline__ float fmt_d2f(const double x) {
+    const uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
+    const uint32_t e = (hi >> 20) & 0x7ffu;
+    if (e - 897u < 253u) return __uint_as_float(((hi & 0x80000000u) | ((e - 896u) << 23) | ((hi & 0xfffffu) << 3) | (lo >> 29)) + ((lo >> 28) & 1u));
+    return (float)x;
+}
+
+// sign(h + s n) exactly as the float64 reference computes it (1-bit quantiser).  The rounded double sum has the sign of the exact sum
+// h + fl(s n); an FP32 evaluation decides it whenever |y| is not within 2^-19 of cancellation (relative to |h| + |s n|, 30x the FP32
+// error bound), which leaves ~1e-6 of the elements (and every NaN / infinity) to the FP64 path.
+__device__ __forceinline__ float fmt_sign1(const double h, const float hf, const double n, const double s, const float sf) {
+    const float p = sf * fmt_d2f(n);
+    const float y = hf + p;
+    if (fabsf(y) > 1.9e-6f * (fabsf(hf) + fabsf(p))) return y > 0.f ? 1.f : -1.f;      // false for NaN
+    const double yd = __dadd_rn(h, __dmul_rn(s, n));
+    return (yd > 0.0) ? 1.f : ((yd < 0.0) ? -1.f : ((yd == 0.0) ? 0.f : __int_as_float(0x7fc00000)));
+}
+
+template <bool H_C64>
+__device__ __forceinline__ void fmt_store(const TcArgs& a, int64_t first_tile, int KD, int item, int lane, const FmtItem& it) {
+    const int kbs = KD / 8;
+    const int pair = item / kbs, kb = item - pair * kbs;
+    const int64_t tile = first_tile + pair / (TILE_M / 8);
+    const int mb = pair % (TILE_M / 8);
+    const int64_t g = tile * TILE_M + mb * 8 + (lane & 7);
+    float qr = 0.f, qi = 0.f;
+    if (g < a.B) {       // 1-bit quantiser (the host launches the fused prologue for n_bits = 1 only)
+        const float sf = (float)a.obs_noise_scale_f;
+        if (H_C64) {
+            qr = fmt_sign1((double)it.hf.x, it.hf.x, it.w.x, a.obs_noise_scale, sf);
+            qi = fmt_sign1((double)it.hf.y, it.hf.y, it.w.y, a.obs_noise_scale, sf);
+        } else {
+            qr = fmt_sign1(it.h.x, fmt_d2f(it.h.x), it.w.x, a.obs_noise_scale, sf);
+            qi = fmt_sign1(it.h.y, fmt_d2f(it.h.y), it.w.y, a.obs_noise_scale, sf);
+        }
+    }
+    if (!(qr == qr && qi == qi)) {     // NaN data: flag the row (its estimate becomes NaN)
+        const int64_t fr = tile * TILE_M + mb * 8 + (lane & 7);      // (the flag buffer is padded to whole units)
+        atomicOr(reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(a.bad)) + (fr >> 2), 1u << (8 * (int)(fr & 3)));
+        qr = qi = 0.f;
+    }
+    unsigned char* tile_img = reinterpret_cast<unsigned char*>(const_cast<__half*>(a.a_img)) + (size_t)tile * TILE_M * KD * 2;
+    *reinterpret_cast<__half2*>(tile_img + (size_t)(kb * (TILE_M / 8) + mb) * 128 + (lane & 7) * 16 + (lane >> 3) * 4) = __floats2half2_rn(qr, qi);
+}
+
+// pull the (h, noise) rows of one work unit of this CTA into L2 (two bulk prefetches): the small per-item loads of the in-kernel
+// formatter then hit L2 instead of fetching DRAM in 32-byte pieces spread over the whole unit (measured: 2x read amplification)
+__device__ __forceinline__ void fmt_prefetch_unit(const TcArgs& a, int64_t first_tile, int ntiles, int KD) {
+    const int No = KD / 2;
+    const int64_t r0 = first_tile * TILE_M;
+    if (r0 >= a.B) return;
+    const int64_t rows = (a.B - r0) < (int64_t)ntiles * TILE_M ? (a.B - r0) : (int64_t)ntiles * TILE_M;
+    const size_t hsz = a.obs_h_c64 ? 8 : 16;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)a.obs_h + (size_t)r0 * No * hsz), "r"((uint32_t)(rows * No * hsz)) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)a.obs_noise + (size_t)r0 * No * 16), "r"((uint32_t)(rows * No * 16)) : "memory");
+}
+
+// a whole share of a work unit at once (the first unit of a CTA, formatted by the eight epilogue warps before the pipeline starts)
+template <bool H_C64>
+__device__ __forceinline__ void fmt_items(const TcArgs& a, int64_t first_tile, int KD, int item0, int n_items, int lane) {
+    for (int i = 0; i < n_items; i += 4) {
+        FmtItem it[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) if (i + j < n_items) fmt_load<H_C64>(a, first_tile, KD, item0 + i + j, lane, it[j]);
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) if (i + j < n_items) fmt_store<H_C64>(a, first_tile, KD, item0 + i + j, lane, it[j]);
+    }
+}
+
 // EPI selects the epilogue: 0 = fused 'all' estimate (online softmax), 1 = export the weighted log-probabilities l_k only,
 // 2 = combine with given per-pilot weights (the top-1 / top-n / cumulative-probability modes run 1 -> select -> 2)
 // KDC = n_obs / 16 (reduction length 32 KDC); NCHZ = 0 (no whitening columns: an H-part launch) or KDC; NCHH = H columns / 32
-template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC>
+// PRO = true: fused prologue -- no formatter launch, the kernel builds its own pilot tiles from (h, noise): the epilogue warps format
+// the first work unit of the CTA, warp 2 every further one while the tensor pipe works on the previous.
+template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC, bool PRO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
     using Cfg = TcCfg<32 * KDC, NZ, NH, CG, ORDER, AC>;
@@ -166,6 +260,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         }
         mbar_init(smem_u32(&ctrl->a_full), full_count);
         mbar_init(smem_u32(&ctrl->a_free), 1);
+        mbar_init(smem_u32(&ctrl->fmt_done), 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -207,10 +302,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             }
         } else if (warp == 3 && lane == 0) {
             // ===================== pilot-tile producer: the two pre-formatted 128-pilot tiles of each unit, one bulk copy each
-            uint32_t fph = 0;
+            uint32_t fph = 0, n_done = 0;
             for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
                 mbar_wait(smem_u32(&ctrl->a_free), fph ^ 1);      // all MMAs of the previous unit have read the tiles
                 fph ^= 1;
+                if (PRO) {     // the tiles of this unit must have been written (generic proxy) before the bulk copy (async proxy) reads them
+                    mbar_wait(smem_u32(&ctrl->fmt_done), n_done & 1u);      // (a spin on a shared-memory counter here starved the epilogue
+                    ++n_done;                                               //  warps that share this warp's scheduler)
+                    __threadfence();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
                 mbar_expect_tx(smem_u32(&ctrl->a_full), NTILES * Cfg::A_TILE_BYTES);
                 #pragma unroll
                 for (int t = 0; t < NTILES; ++t)
@@ -327,15 +428,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         const uint32_t th = tz + NZ;
         uint32_t fph = 0;
         const int N = a.N;
+        // PRO: items of a work unit per epilogue warp, and how they are spread over the components of the previous unit
+        constexpr int FMT_IPW = NTILES * (TILE_M / 8) * (Cfg::KD / 8) / 8;
+        const int fmt_slot = warp - 4;
+        const int fmt_every = a.K / FMT_IPW;      // one item every fmt_every components (the host only launches PRO when FMT_IPW divides K)
+        if (PRO && unit0 < n_units) {      // the eight epilogue warps share the first work unit of this CTA
+            if (a.obs_h_c64) fmt_items<true>(a, (unit0 * CG + rank) * NTILES, Cfg::KD, fmt_slot * FMT_IPW, FMT_IPW, lane);
+            else fmt_items<false>(a, (unit0 * CG + rank) * NTILES, Cfg::KD, fmt_slot * FMT_IPW, FMT_IPW, lane);
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctrl->fmt_done));
+        }
         double err = 0.0, pw = 0.0, cnt = 0.0;     // cnt also gates the atomics (rows handled by this thread)
         long long w_acc = 0, c_z = 0, c_h = 0, c_pro = 0, c_ld = 0;
 
         for (int64_t unit = unit0; unit < n_units && t < NTILES; unit += unit_step) {
             const int64_t tile_base = ((unit * CG + rank) * NTILES + t) * TILE_M;
             long long c0 = QCE_CLK();
-            bool row_bad = false;
-            if (tile_base + row < a.B) row_bad = __ldg(a.bad + tile_base + row) != 0;
-            c_pro += QCE_CLK() - c0;
 
             float2 acc[NH > 0 ? NH / 2 : 1];           // the estimate row, (re, im) pairs: packed FFMA2 arithmetic
             #pragma unroll
@@ -347,7 +457,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             float2 lc_n = __ldg(a.logc2);
             const int64_t grow = (tile_base + row < a.B) ? tile_base + row : 0;     // rows past the end read row 0, never write
             float w_n = (EPI == 2) ? __ldg(a.w_in + grow * a.K) : 0.f;
+            const bool fmt_next = PRO && (unit + unit_step < n_units);
+            const int64_t fmt_tile0 = ((unit + unit_step) * CG + rank) * NTILES;
+            if (fmt_next && fmt_slot == 0 && lane == 0) fmt_prefetch_unit(a, fmt_tile0, NTILES, Cfg::KD);
             for (int k = 0; k < a.K; ++k) {
+                // PRO: this warp's share of the NEXT unit's pilot tiles: loads issued here, consumed after the accumulator is released
+                FmtItem fit;
+                const bool fmt_now = fmt_next && (k % fmt_every == 0);
+                const int fmt_item = fmt_slot * FMT_IPW + k / fmt_every;
+                if (PRO && fmt_now) {
+                    if (a.obs_h_c64) fmt_load<true>(a, fmt_tile0, Cfg::KD, fmt_item, lane, fit); else fmt_load<false>(a, fmt_tile0, Cfg::KD, fmt_item, lane, fit);
+                }
                 // per-component scalars were fetched one iteration ahead (their L2 latency would otherwise sit on the
                 // critical path between "accumulator ready" and "accumulator released")
                 const float zs = zs_n, hs = hs_n;
@@ -462,13 +582,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 if (lane == 0) {        // one arrival per warp on the LEADER's barrier
                     if (CG == 2) mbar_arrive_cluster(smem_u32(&ctrl->acc_empty[t]), 0); else mbar_arrive(smem_u32(&ctrl->acc_empty[t]));
                 }
+                if (PRO && fmt_now) { if (a.obs_h_c64) fmt_store<true>(a, fmt_tile0, Cfg::KD, fmt_item, lane, fit); else fmt_store<false>(a, fmt_tile0, Cfg::KD, fmt_item, lane, fit); }
                 c_h += QCE_CLK() - c2;
+            }
+            if (fmt_next) {             // this warp's share of the next unit is written: publish it to the tile producer
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctrl->fmt_done));
             }
 
             // ---- finalise: normalise, write the estimate row, NMSE accumulators (FP32 per row: FP64 stalls behind the
             // tensor pipe; the per-row sums enter the FP64 accumulators once)
             const int64_t g = tile_base + row;
             if (EPI != 1 && g < a.B) {
+                // (read here, after the last component: with the fused prologue the flags are written by other warps of this kernel)
+                const bool row_bad = (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) != 0;
                 const float invs = row_bad ? __int_as_float(0x7fc00000) : (EPI == 2 ? 1.f : 1.f / ssum);
                 if (a.h_est) {
                     double2* out = a.h_est + g * N + (a.h_col0 >> 1);
@@ -937,11 +1066,11 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
     return QCE_OK;
 }
 
-template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC = 1>
+template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC = 1, bool PRO = false>
 static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
     using Cfg = TcCfg<32 * KDC, 32 * NCHZ, 32 * NCHH, CG, ORDER, AC>;
     static bool attr_set = false;
-    auto kern = dense_tc_kernel<KDC, NCHZ, NCHH, OFFS, CG, EPI, ORDER, AC>;
+    auto kern = dense_tc_kernel<KDC, NCHZ, NCHH, OFFS, CG, EPI, ORDER, AC, PRO>;
     if (!attr_set) {
         QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
@@ -1164,6 +1293,28 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
     TileScratch* ts = nullptr;
     qce_status st = tc_scratch(m, s, B, &ts);
     if (st) return st;
+    // Fused prologue (QCE_TC_FUSE=1): ONE launch observes, quantises, formats and estimates (mode 'all', fused shapes, 1-bit pilots,
+    // SM-pair variant, K a multiple of the items per warp): the epilogue warps build the NEXT work unit's tiles one core matrix per
+    // component.  Bit-identical results, but no faster than the formatter launch + estimate launch pair (4.78 vs 4.79 ms per 2^20
+    // pilots): the kernel is power-limited, so the formatter's energy costs the same time inside it as outside.  Default: the pair.
+    {
+        const char* fe = getenv("QCE_TC_FUSE");
+        const bool want = fe && atoi(fe) == 1;
+        const int cz = m->n_obs / 16, ch = m->n_ant / 16;
+        const int ipw = 2 * 16 * (2 * m->n_obs / 8) / 8;            // items of a work unit per epilogue warp (see FMT_IPW)
+        const bool k_ok = m->n_comp >= ipw && m->n_comp % ipw == 0;      // one item per warp every K / ipw components
+        if (want && k_ok && qt->n_bits == 1 && mode == QCE_MODE_ALL && !m->tc.split && !m->tc.split_a && m->tc.triangular && cz == ch && (cz == 4 || cz == 2)) {
+            QCE_CUDA_TRY(cudaMemsetAsync(ts->bad, 0, ts->bad_bytes, s));      // off-grid rows are flagged with atomicOr
+            TcArgs a;
+            tc_fill_args(m, ts, B, h_est, h, h_is_c64, acc, &a);
+            a.obs_h = h; a.obs_noise = (const double2*)noise; a.obs_noise_scale = noise_scale; a.obs_noise_scale_f = (float)noise_scale; a.obs_inv_scale = 1.0 / m->tc.eff_scale;
+            a.obs_h_c64 = h_is_c64; a.obs_bits = qt->n_bits; a.obs_n_thr = qt->n_thr; a.obs_thr = qt->thr; a.obs_labels = qt->labels;
+            ts->owner = m; ts->rows = B;
+            const bool offs = m->tc.has_offsets;
+            if (cz == 4) return offs ? launch_cfg<4, 4, 4, true, 2, 0, 0, 1, true>(a, s) : launch_cfg<4, 4, 4, false, 2, 0, 0, 1, true>(a, s);
+            return offs ? launch_cfg<2, 2, 2, true, 2, 0, 0, 1, true>(a, s) : launch_cfg<2, 2, 2, false, 2, 0, 0, 1, true>(a, s);
+        }
+    }
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
     const size_t smem = (qt->n_bits > 1) ? (size_t)(2 * qt->n_thr + 1) * sizeof(double) : 0;
     const unsigned grid = (unsigned)(tiles * (TILE_M / 8));

@@ -46,6 +46,14 @@ struct TcArgs {
     int h_stride;              // floats per component in hoff (2N)
     int h_col0;
     int count_rows;            // add the number of rows to acc[2] (only one of the H-part launches does)
+    // fused prologue (PRO kernels): the kernel observes + quantises + formats its own pilot tiles into a_img / bad
+    const void* obs_h;         // [B][No] c64 / c128 channels
+    const double2* obs_noise;  // [B][No] c128
+    double obs_noise_scale, obs_inv_scale;
+    float obs_noise_scale_f;
+    int obs_h_c64, obs_bits, obs_n_thr;
+    const double* obs_thr;     // device quantiser tables (b > 1)
+    const double* obs_labels;
     float skip_thresh;         // fused 'all' epilogue: a warp skips the LMMSE row of a component whose un-normalised weight is below
                                // this for all of its 32 pilots (the normaliser is >= 1, so the dropped terms are < skip_thresh each)
 };

@@ -671,6 +671,43 @@ def test_tc_parameter_scales_and_extreme_snr(qce, scale, snr, nb):
                  lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer=qz), B)
 
 
+@pytest.mark.parametrize('K,N,c64', [(64, 64, True), (128, 64, False), (32, 32, True)])
+def test_tc_fused_prologue_variant(qce, K, N, c64):
+    """QCE_TC_FUSE=1: the estimate kernel builds its own pilot tiles (observe + 1-bit quantise + format in the epilogue warps, FP32
+    sign decision with an exact FP64 fallback near cancellation); results must be identical to the formatter + estimate launch pair,
+    including NaN rows and a ragged tail over several work units per CTA."""
+    import os
+    from quantized_channel_estimation_b200 import engine, precompute
+    B, snr = 148 * 512 * 2 + 777, 5
+    means, covs, w = orc.random_psd_gmm(K, N, seed=K + N, mean_scale=0.1)
+    model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, 1))
+    quant = engine.Quantizer.get(1)
+    g = torch.Generator(device='cuda').manual_seed(12)
+    h = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float32 if c64 else torch.float64)).contiguous()
+    noise = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float64)).contiguous()
+    noise[5, 3] = complex(float('nan'), 0.0)
+    h[B - 2, 0] = 0.0
+    noise[B - 2, 0] = 0.0                          # y = 0 exactly: np.sign gives 0, both paths must carry the value 0 (FP64 fallback)
+    est0, acc0 = model.pipeline(quant, h, noise, 10 ** (-snr / 20), 'all', 'tc', want_est=True)
+    os.environ['QCE_TC_FUSE'] = '1'
+    try:
+        l0 = _launches()
+        est1, acc1 = model.pipeline(quant, h, noise, 10 ** (-snr / 20), 'all', 'tc', want_est=True)
+        assert _launches() - l0 == 1                # one kernel launch
+    finally:
+        del os.environ['QCE_TC_FUSE']
+    ok = ~torch.isnan(est0.real).any(dim=1)
+    assert bool(torch.isnan(est0[5].real).all()) and bool(torch.isnan(est1[5].real).all())
+    assert torch.equal(torch.isnan(est0.real), torch.isnan(est1.real))
+    assert torch.equal(est0[ok], est1[ok])
+    assert acc0[2].item() == acc1[2].item() == B
+
+
+def _launches():
+    from quantized_channel_estimation_b200 import _lib
+    return _lib.launch_count()
+
+
 def test_tc_single_component_and_many_components(qce):
     """K = 1, and K = 130 / 300: the selection kernel holds 2, 8 or 32 entries per lane depending on K."""
     for K, N in ((1, 64), (130, 16), (300, 16)):
