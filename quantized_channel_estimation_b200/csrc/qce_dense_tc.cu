@@ -753,8 +753,10 @@ __global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const dou
 // ------------------------------------------------------------------------------------------------ pilot tiles
 // HBM-bound formatter: pilots -> exact FP16 integers m = r / data_scale, written as 128-pilot tiles in the canonical
 // K-major core-matrix layout the MMA A-descriptor expects (core (mb, kb) at ((kb * 16) + mb) * 128 B), so that the
-// estimate kernel stages a tile with ONE contiguous bulk copy.  One CTA per (tile, 8-row block): its 8 warps sweep the
-// K cores, i.e. the CTA reads 8 full pilot rows (coalesced 64 B segments) and every warp writes one 128 B core matrix.
+// estimate kernel stages a tile with ONE contiguous bulk copy.  One CTA per (tile, 8-row block): warp w reads pilot row w of
+// the block in full (lane-contiguous elements: whole 128-byte lines per warp-load -- a first version in which every warp-load touched
+// 8 rows x 32..64 B ran at 98 % L1TEX throughput and 59 % of DRAM), the formatted halves go through a 2..4 KB shared-memory
+// image of the block's core matrices, and every warp then writes whole 128-byte core matrices.
 // OBSERVE = true fuses get_observation_nbit + quant (modules/utils.py:241-251, :189-203) in front: y = h + s*n with
 // two roundings, then the same sign / digitize decisions as quantize_kernel (bit-exact), then the level's grid index.
 // SPLIT = true: arbitrary real data, written as the FP16 pair (hi, lo) of m = r / eff_scale into two consecutive tile images.
@@ -762,70 +764,90 @@ template <bool OBSERVE, bool H_C64, bool SPLIT>
 __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__ src, const double2* __restrict__ noise, double noise_scale,
                                                         QuantTables qt, int64_t B, int No, double inv_data_scale,
                                                         __half* __restrict__ img, unsigned char* __restrict__ bad) {
-    extern __shared__ double s_tab[];              // thr[n_thr] then labels[n_thr + 1] (OBSERVE, b > 1)
+    extern __shared__ __align__(16) unsigned char s_dyn[];   // [copies][kbs][8 rows][16 B] core matrices of this block, then thr / labels (f64)
     __shared__ int s_bad[8];
     const int KD = 2 * No, kbs = KD / 8;
     const int64_t tile = blockIdx.x / (TILE_M / 8);
     const int mb = blockIdx.x % (TILE_M / 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int COPIES = SPLIT ? 2 : 1;
+    unsigned char* s_img = s_dyn;
+    double* s_tab = reinterpret_cast<double*>(s_dyn + (size_t)COPIES * kbs * 128);
     if (OBSERVE && qt.n_bits > 1) {
         for (int i = threadIdx.x; i < 2 * qt.n_thr + 1; i += blockDim.x) s_tab[i] = (i < qt.n_thr) ? qt.thr[i] : qt.labels[i - qt.n_thr];
     }
     if (threadIdx.x < 8) s_bad[threadIdx.x] = 0;
     __syncthreads();
-    const int rr = mb * 8 + (lane & 7);
-    const int64_t g = tile * TILE_M + rr;
-    const float inv = (float)inv_data_scale;
-    __half* tile_img = img + (size_t)tile * TILE_M * KD * (SPLIT ? 2 : 1);
+    const int64_t g = tile * TILE_M + mb * 8 + warp;           // this warp's pilot
     int my_bad = 0;
-    for (int kb = warp; kb < kbs; kb += 8) {
-        const int j = kb * 4 + (lane >> 3);
-        double2 v = make_double2(0.0, 0.0);
-        if (g < B) {
-            if (OBSERVE) {
-                double2 h;
-                if (H_C64) { const float2 hf = reinterpret_cast<const float2*>(src)[g * No + j]; h = make_double2((double)hf.x, (double)hf.y); }
-                else h = reinterpret_cast<const double2*>(src)[g * No + j];
-                const double2 w = noise[g * No + j];
-                const double yx = __dadd_rn(h.x, __dmul_rn(noise_scale, w.x)), yy = __dadd_rn(h.y, __dmul_rn(noise_scale, w.y));
+    for (int j0 = 0; j0 < No; j0 += 64) {                       // complex elements j0 + lane and j0 + 32 + lane of the row: every
+        double2 v[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};     // warp-load covers 256 / 512 contiguous bytes
+        const int ja = j0 + lane, jb = j0 + 32 + lane;
+        const bool oa = g < B && ja < No, ob = g < B && jb < No;
+        if (OBSERVE) {
+            double2 h[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)}, w[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+            if (H_C64) {
+                if (oa) { const float2 hf = __ldcs(reinterpret_cast<const float2*>(src) + g * No + ja); h[0] = make_double2((double)hf.x, (double)hf.y); }
+                if (ob) { const float2 hf = __ldcs(reinterpret_cast<const float2*>(src) + g * No + jb); h[1] = make_double2((double)hf.x, (double)hf.y); }
+            } else {
+                if (oa) h[0] = __ldcs(reinterpret_cast<const double2*>(src) + g * No + ja);
+                if (ob) h[1] = __ldcs(reinterpret_cast<const double2*>(src) + g * No + jb);
+            }
+            if (oa) w[0] = __ldcs(noise + g * No + ja);
+            if (ob) w[1] = __ldcs(noise + g * No + jb);
+            #pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!(u ? ob : oa)) continue;
+                const double yx = __dadd_rn(h[u].x, __dmul_rn(noise_scale, w[u].x)), yy = __dadd_rn(h[u].y, __dmul_rn(noise_scale, w[u].y));
                 if (qt.n_bits == 1) {        // value on the grid is sign(y) (x 1/sqrt(2) = data_scale)
-                    v.x = (yx > 0.0) ? 1.0 : ((yx < 0.0) ? -1.0 : ((yx == 0.0) ? 0.0 : yx));
-                    v.y = (yy > 0.0) ? 1.0 : ((yy < 0.0) ? -1.0 : ((yy == 0.0) ? 0.0 : yy));
+                    v[u].x = (yx > 0.0) ? 1.0 : ((yx < 0.0) ? -1.0 : ((yx == 0.0) ? 0.0 : yx));
+                    v[u].y = (yy > 0.0) ? 1.0 : ((yy < 0.0) ? -1.0 : ((yy == 0.0) ? 0.0 : yy));
                 } else {
                     const double* thr = s_tab;
                     const double* lab = s_tab + qt.n_thr;
                     int ir = qt.n_thr, ii = qt.n_thr;
                     if (yx == yx) { int lo = 0, hi = qt.n_thr; while (lo < hi) { int mid = (lo + hi) >> 1; if (thr[mid] <= yx) lo = mid + 1; else hi = mid; } ir = lo; }
                     if (yy == yy) { int lo = 0, hi = qt.n_thr; while (lo < hi) { int mid = (lo + hi) >> 1; if (thr[mid] <= yy) lo = mid + 1; else hi = mid; } ii = lo; }
-                    v.x = lab[ir] * inv_data_scale;
-                    v.y = lab[ii] * inv_data_scale;
+                    v[u].x = lab[ir] * inv_data_scale;
+                    v[u].y = lab[ii] * inv_data_scale;
                 }
+            }
+        } else {
+            if (oa) { v[0] = __ldcs(reinterpret_cast<const double2*>(src) + g * No + ja); v[0].x *= inv_data_scale; v[0].y *= inv_data_scale; }
+            if (ob) { v[1] = __ldcs(reinterpret_cast<const double2*>(src) + g * No + jb); v[1].x *= inv_data_scale; v[1].y *= inv_data_scale; }
+        }
+        // complex j sits in K-core kb = j / 4 at byte (row % 8) * 16 + (j % 4) * 4 of the core
+        #pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = u ? jb : ja;
+            if (j >= No) continue;
+            const int s_off = (j >> 2) * 128 + warp * 16 + (j & 3) * 4;
+            if (SPLIT) {
+                if (!(fabs(v[u].x) <= 60000.0 && fabs(v[u].y) <= 60000.0)) { my_bad = 1; v[u] = make_double2(0.0, 0.0); }     // out of FP16 range / NaN
+                const __half hr = __double2half(v[u].x), hi_ = __double2half(v[u].y);
+                *reinterpret_cast<__half2*>(s_img + s_off) = __halves2half2(hr, hi_);
+                *reinterpret_cast<__half2*>(s_img + kbs * 128 + s_off) =
+                    __halves2half2(__double2half(v[u].x - (double)__half2float(hr)), __double2half(v[u].y - (double)__half2float(hi_)));
             } else {
-                v = __ldg(reinterpret_cast<const double2*>(src) + g * No + j);
-                v.x *= inv_data_scale;
-                v.y *= inv_data_scale;
+                const float mr = (float)v[u].x, mi = (float)v[u].y;
+                const float qr = rintf(mr), qi = rintf(mi);
+                // off-grid / out-of-range / NaN data cannot be represented exactly: flag the row (its estimate becomes NaN)
+                if (!(fabsf(mr - qr) <= 1e-4f * fmaxf(1.f, fabsf(qr)) && fabsf(mi - qi) <= 1e-4f * fmaxf(1.f, fabsf(qi)) &&
+                      fabsf(qr) <= 2048.f && fabsf(qi) <= 2048.f))
+                    my_bad = 1;
+                *reinterpret_cast<__half2*>(s_img + s_off) = __floats2half2_rn(qr, qi);
             }
         }
-        const size_t core_off = (size_t)(kb * (TILE_M / 8) + mb) * 128 + (lane & 7) * 16 + (lane >> 3) * 4;
-        if (SPLIT) {
-            if (!(fabs(v.x) <= 60000.0 && fabs(v.y) <= 60000.0)) { my_bad = 1; v = make_double2(0.0, 0.0); }     // out of FP16 range / NaN
-            const __half hr = __double2half(v.x), hi_ = __double2half(v.y);
-            const __half lr = __double2half(v.x - (double)__half2float(hr)), li = __double2half(v.y - (double)__half2float(hi_));
-            *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img) + core_off) = __halves2half2(hr, hi_);
-            *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img + (size_t)TILE_M * KD) + core_off) = __halves2half2(lr, li);
-            continue;
-        }
-        const float mr = (float)v.x, mi = (float)v.y;
-        const float qr = rintf(mr), qi = rintf(mi);
-        // off-grid / out-of-range / NaN data cannot be represented exactly: flag the row (its estimate becomes NaN)
-        if (!(fabsf(mr - qr) <= 1e-4f * fmaxf(1.f, fabsf(qr)) && fabsf(mi - qi) <= 1e-4f * fmaxf(1.f, fabsf(qi)) &&
-              fabsf(qr) <= 2048.f && fabsf(qi) <= 2048.f))
-            my_bad = 1;
-        *reinterpret_cast<__half2*>(reinterpret_cast<unsigned char*>(tile_img) + core_off) = __floats2half2_rn(qr, qi);
-        (void)inv;
     }
-    if (my_bad) s_bad[lane & 7] = 1;
+    if (__any_sync(0xffffffffu, my_bad) && lane == 0) s_bad[warp] = 1;
     __syncthreads();
+    // whole core matrices out: core (mb, kb) of copy c at tile image + c * TILE_M * KD halves + (kb * 16 + mb) * 128 B
+    unsigned char* tile_img = reinterpret_cast<unsigned char*>(img + (size_t)tile * TILE_M * KD * COPIES);
+    for (int c = warp; c < COPIES * kbs; c += 8) {
+        const int copy = c / kbs, kb = c - copy * kbs;
+        *reinterpret_cast<uint32_t*>(tile_img + (size_t)copy * TILE_M * KD * 2 + (size_t)(kb * (TILE_M / 8) + mb) * 128 + lane * 4) =
+            *reinterpret_cast<const uint32_t*>(s_img + c * 128 + lane * 4);
+    }
     if (threadIdx.x < 8) bad[tile * TILE_M + mb * 8 + threadIdx.x] = (unsigned char)s_bad[threadIdx.x];
 }
 
@@ -1197,10 +1219,10 @@ static qce_status tc_format_into(qce_model* m, cudaStream_t s, const double* r, 
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
     QuantTables none{};
     if (m->tc.split_a)
-        tc_format_kernel<false, false, true><<<(unsigned)(tiles * (TILE_M / 8)), 256, 0, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
+        tc_format_kernel<false, false, true><<<(unsigned)(tiles * (TILE_M / 8)), 256, 2 * (size_t)(2 * m->n_obs / 8) * 128, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
                                                                                             (__half*)ts->img, (unsigned char*)ts->bad);
     else
-        tc_format_kernel<false, false, false><<<(unsigned)(tiles * (TILE_M / 8)), 256, 0, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
+        tc_format_kernel<false, false, false><<<(unsigned)(tiles * (TILE_M / 8)), 256, (size_t)(2 * m->n_obs / 8) * 128, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
                                                                                              (__half*)ts->img, (unsigned char*)ts->bad);
     QCE_CHECK_LAUNCH("tc_format_kernel");
     ts->owner = m; ts->rows = B;
@@ -1316,7 +1338,7 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
         }
     }
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
-    const size_t smem = (qt->n_bits > 1) ? (size_t)(2 * qt->n_thr + 1) * sizeof(double) : 0;
+    const size_t smem = (size_t)(m->tc.split_a ? 2 : 1) * (2 * m->n_obs / 8) * 128 + ((qt->n_bits > 1) ? (size_t)(2 * qt->n_thr + 1) * sizeof(double) : 0);
     const unsigned grid = (unsigned)(tiles * (TILE_M / 8));
     const double inv_scale = 1.0 / m->tc.eff_scale;
 #define QCE_FMT(C64, SPL) tc_format_kernel<true, C64, SPL><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, inv_scale, \
