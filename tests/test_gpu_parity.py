@@ -779,3 +779,78 @@ def test_tc_single_cta_variant_env(qce):
     assert out.returncode == 0, out.stderr[-2000:]
     err = float([l for l in out.stdout.splitlines() if l.startswith('RELERR')][0].split()[1])
     assert err < TOL_TC
+
+
+@pytest.mark.gpu
+def test_c_abi_error_behaviour(qce):
+    """The C ABI reports misuse through its status codes and ``qce_last_error_string`` (include/qce_b200.h:34-40) instead of
+    crashing, and an empty batch is a valid no-op -- the reference's numpy code returns an empty array for it."""
+    import ctypes as C
+    from quantized_channel_estimation_b200 import _lib
+    lib = _lib.require_device()
+    INVALID, UNSUPPORTED = -1, -3
+    err = lambda: lib.qce_last_error_string().decode()
+    h = C.c_void_p()
+    assert lib.qce_model_create(0, 8, 4, 0, C.byref(h)) == INVALID and 'shape' in err()
+    assert lib.qce_model_create(8, 8, 4, 0, None) == INVALID
+    assert lib.qce_quantizer_create(0, None, None, C.byref(h)) == INVALID and 'n_bits' in err()
+    assert lib.qce_quantizer_create(2, None, None, C.byref(h)) == INVALID and 'tables' in err()
+    thr = (C.c_double * 3)(0.5, -0.5, 1.0)                   # not ascending
+    lab = (C.c_double * 4)(-1.5, -0.5, 0.5, 1.5)
+    assert lib.qce_quantizer_create(2, thr, lab, C.byref(h)) == INVALID and 'ascend' in err()
+
+    m = C.c_void_p()
+    assert lib.qce_model_create(20, 20, 5, 0, C.byref(m)) == 0
+    try:
+        r = torch.zeros((4, 20), dtype=torch.complex128, device='cuda')
+        out = torch.empty_like(r)
+        # a model without parameters refuses to estimate
+        assert lib.qce_estimate(m, None, r.data_ptr(), 4, 0, 0, 0.0, 0, out.data_ptr(), None, None, None) == INVALID
+        assert 'no parameters' in err()
+        assert lib.qce_model_set_params(m, None, None, None, None, None, None, 0.0) == INVALID
+        K, N = 5, 20
+        eye = torch.eye(N, dtype=torch.complex128, device='cuda').repeat(K, 1, 1).contiguous()
+        z = torch.zeros((K, N), dtype=torch.complex128, device='cuda')
+        lc = torch.zeros(K, dtype=torch.float64, device='cuda')
+        assert lib.qce_model_set_params(m, None, eye.data_ptr(), eye.data_ptr(), z.data_ptr(), z.data_ptr(), lc.data_ptr(),
+                                        -1.0) == INVALID
+        assert lib.qce_model_set_params(m, None, eye.data_ptr(), eye.data_ptr(), z.data_ptr(), z.data_ptr(), lc.data_ptr(),
+                                        0.0) == 0
+        args = lambda B, mode, ntop, rho, prec, rp=r.data_ptr(): (m, None, rp, B, mode, ntop, rho, prec, out.data_ptr(), None,
+                                                                   None, None)
+        assert lib.qce_estimate(*args(-1, 0, 0, 0.0, 0)) == INVALID
+        assert lib.qce_estimate(*args(4, 0, 0, 0.0, 0, rp=None)) == INVALID
+        assert lib.qce_estimate(*args(4, 7, 0, 0.0, 0)) == INVALID and 'unknown mode' in err()
+        assert lib.qce_estimate(*args(4, _lib.MODE_TOPN, 0, 0.0, 0)) == INVALID and 'n_top' in err()
+        assert lib.qce_estimate(*args(4, _lib.MODE_CUMPROB, 0, float('nan'), 0)) == INVALID and 'NaN' in err()
+        assert lib.qce_estimate(*args(4, 0, 0, 0.0, 9)) == INVALID and 'precision' in err()
+        # N = 20 is not a tensor-core shape: asking for that kernel explicitly is refused, never silently rerouted
+        assert lib.qce_estimate(*args(4, 0, 0, 0.0, _lib.PREC_TC)) == UNSUPPORTED and 'tensor-core' in err()
+        assert lib.qce_format_pilots(m, None, r.data_ptr(), 4) == UNSUPPORTED
+        # empty batch: OK, nothing written
+        out.fill_(7.0)
+        assert lib.qce_estimate(*args(0, 0, 0, 0.0, 0, rp=None)) == 0
+        torch.cuda.synchronize()
+        assert bool((out == 7.0).all())
+        # and a valid call still works afterwards (identity filters, equal weights -> h = r)
+        r2 = torch.randn((4, 20), dtype=torch.complex128, device='cuda')
+        assert lib.qce_estimate(*args(4, 0, 0, 0.0, 0, rp=r2.data_ptr())) == 0
+        torch.cuda.synchronize()
+        assert torch.allclose(out, r2, rtol=1e-12, atol=1e-12)
+        host_in = np.zeros((4, 20), dtype=np.complex128)
+        assert lib.qce_estimate_host(m, None, 4, 0, 0, 0.0, 0, host_in.ctypes.data) == INVALID
+        assert lib.qce_estimate_host(m, host_in.ctypes.data, 0, 0, 0, 0.0, 0, None) == 0
+    finally:
+        lib.qce_model_destroy(m)
+    # pipeline needs a square pilot matrix (A = I)
+    m2 = C.c_void_p()
+    assert lib.qce_model_create(8, 16, 2, 0, C.byref(m2)) == 0
+    try:
+        q = C.c_void_p()
+        assert lib.qce_quantizer_create(1, None, None, C.byref(q)) == 0
+        x = torch.zeros((2, 16), dtype=torch.complex128, device='cuda')
+        assert lib.qce_pipeline(m2, q, None, x.data_ptr(), 0, x.data_ptr(), 1.0, 2, 0, 0, 0.0, 0, None, None) == INVALID
+        assert 'n_obs == n_ant' in err()
+        lib.qce_quantizer_destroy(q)
+    finally:
+        lib.qce_model_destroy(m2)
