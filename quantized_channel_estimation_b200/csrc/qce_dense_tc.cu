@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work unit: CG * TILES tiles (256 pilots per CTA); the cluster (CG CTAs) walks the units round-robin
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
-    const int64_t n_units = (a.B + CG * NTILES * TILE_M - 1) / (CG * NTILES * TILE_M);
+    int64_t n_units = (a.B + CG * NTILES * TILE_M - 1) / (CG * NTILES * TILE_M);
+    const bool bucket = (EPI == 2) && a.unit_comp != nullptr;      // one component per work unit (bucketed top-1)
+    if (bucket) n_units = __ldg(a.n_units_dev);
     const int64_t unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
     // the SM-pair variant is only launched for triangular Linv (the common, Cholesky case): its offsets are compile-time
     const int tri16 = (CG == 2) ? Cfg::TRI16 : (a.tri ? 16 : 0);
@@ -288,7 +290,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             const unsigned char* img = (CG == 2) ? a.image2 + (size_t)rank * COMP_BYTES : reinterpret_cast<const unsigned char*>(a.image);
             constexpr size_t COMP_STRIDE = COMP_BYTES * CG;      // CG=2: [k][rank]
             for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
-                for (int k = 0; k < a.K; ++k) {
+                int kb = 0, ke = a.K;
+                if (bucket) { kb = __ldg(a.unit_comp + unit); ke = kb + 1; }
+                for (int k = kb; k < ke; ++k) {
                     const unsigned char* comp = img + (size_t)k * COMP_STRIDE;
                     #pragma unroll
                     for (int q = 0; q < Cfg::NCHUNK; ++q) {
@@ -339,7 +343,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 a_phase ^= 1;
                 tc_fence_after();
                 w_a += QCE_CLK() - ca;
-                for (int k = 0; k < a.K; ++k) {
+                const int nk = bucket ? 1 : a.K;
+                for (int k = 0; k < nk; ++k) {
                     if (ORDER == 0) {
                     #pragma unroll
                     for (int t = 0; t < NTILES; ++t) {
@@ -408,7 +413,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 mbar_wait(smem_u32(&ctrl->a_full), a_phase);
                 a_phase ^= 1;
                 mbar_arrive_cluster(smem_u32(&ctrl->a_full), 0);
-                for (int k = 0; k < a.K; ++k) {
+                const int nk = bucket ? 1 : a.K;
+                for (int k = 0; k < nk; ++k) {
                     #pragma unroll
                     for (int q = 0; q < Cfg::NCHUNK; ++q) {
                         mbar_wait(smem_u32(&ctrl->full[stage]), phase);
@@ -453,14 +459,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             float mref_hi = 0.f, mref_lo = 0.f;
             float ssum = 0.f;
 
-            float zs_n = __ldg(a.zscale), hs_n = __ldg(a.hscale);
-            float2 lc_n = __ldg(a.logc2);
-            const int64_t grow = (tile_base + row < a.B) ? tile_base + row : 0;     // rows past the end read row 0, never write
-            float w_n = (EPI == 2) ? __ldg(a.w_in + grow * a.K) : 0.f;
+            // the pilot this thread handles, and the components of this unit
+            int64_t src = tile_base + row;
+            bool valid = src < a.B;
+            int kb = 0, ke = a.K;
+            if (bucket) {
+                kb = __ldg(a.unit_comp + unit); ke = kb + 1;
+                src = __ldg(a.perm + tile_base + row);
+                valid = src >= 0;
+            }
+            float zs_n = __ldg(a.zscale + kb), hs_n = __ldg(a.hscale + kb);
+            float2 lc_n = __ldg(a.logc2 + kb);
+            const int64_t grow = valid ? src : 0;     // rows past the end read row 0, never write
+            float w_n = (EPI == 2) ? (bucket ? (valid ? 1.f : 0.f) : __ldg(a.w_in + grow * a.K)) : 0.f;
             const bool fmt_next = PRO && (unit + unit_step < n_units);
             const int64_t fmt_tile0 = ((unit + unit_step) * CG + rank) * NTILES;
             if (fmt_next && fmt_slot == 0 && lane == 0) fmt_prefetch_unit(a, fmt_tile0, NTILES, Cfg::KD);
-            for (int k = 0; k < a.K; ++k) {
+            for (int k = kb; k < ke; ++k) {
                 // PRO: this warp's share of the NEXT unit's pilot tiles: loads issued here, consumed after the accumulator is released
                 FmtItem fit;
                 const bool fmt_now = fmt_next && (k % fmt_every == 0);
@@ -473,7 +488,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 const float zs = zs_n, hs = hs_n;
                 const float2 lc = lc_n;
                 const float w_k = w_n;
-                if (k + 1 < a.K) {
+                if (k + 1 < ke) {
                     zs_n = __ldg(a.zscale + k + 1); hs_n = __ldg(a.hscale + k + 1); lc_n = __ldg(a.logc2 + k + 1);
                     if (EPI == 2) w_n = __ldg(a.w_in + grow * a.K + k + 1);
                 }
@@ -594,8 +609,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
 
             // ---- finalise: normalise, write the estimate row, NMSE accumulators (FP32 per row: FP64 stalls behind the
             // tensor pipe; the per-row sums enter the FP64 accumulators once)
-            const int64_t g = tile_base + row;
-            if (EPI != 1 && g < a.B) {
+            const int64_t g = src;
+            if (EPI != 1 && valid) {
                 // (read here, after the last component: with the fused prologue the flags are written by other warps of this kernel)
                 const bool row_bad = (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) != 0;
                 const float invs = row_bad ? __int_as_float(0x7fc00000) : (EPI == 2 ? 1.f : 1.f / ssum);
@@ -858,7 +873,8 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
 // K <= 1024 (32 values per lane).  Also exports l as float64 when asked.
 template <int PER>      // entries per lane: K <= 32 PER
 __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho,
-                                                        int flags, float* __restrict__ w_out, double* __restrict__ logp_out) {
+                                                        int flags, float* __restrict__ w_out, double* __restrict__ logp_out,
+                                                        int* __restrict__ top_out) {
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -886,9 +902,13 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
         const int oa = __shfl_xor_sync(0xffffffffu, amax, off);
         if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
     }
-    if (!w_out) return;
+    if (!w_out && !top_out) return;
     if (mode == QCE_MODE_TOP1) {
         if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
+        if (top_out) {      // bucketed combination: the label instead of a one-hot weight row
+            if (lane == 0) top_out[b] = amax;
+            return;
+        }
         #pragma unroll
         for (int i = 0; i < PER; ++i)
             if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = (k == amax) ? 1.f : 0.f; }
@@ -941,6 +961,73 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
         if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = ((sel >> i) & 1u) ? (float)(l[i] / cum) : 0.f; }
 }
 
+// ------------------------------------------------------------------------------------------------ bucketed top-1 combination
+// Top-1 needs ONE LMMSE row block per pilot, not K: regroup the pilots by their selected component into buckets padded to whole
+// work units, so that the combine launch runs a single component per unit (1/K of the tensor work of the weighted launch).
+// Bucket sizes: block-level histogram in shared memory, one global atomic per (block, non-empty bucket) -- per-pilot global atomics
+// on K addresses serialise in L2.
+__global__ void __launch_bounds__(1024) tc_bucket_count_kernel(const int* __restrict__ top, int64_t B, int K, int* __restrict__ cnt) {
+    __shared__ int s_cnt[1024];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) atomicAdd(&s_cnt[top[b]], 1);
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) if (s_cnt[k]) atomicAdd(cnt + k, s_cnt[k]);
+}
+
+// cnt[K] -> off[K] first slot of each bucket, unit_comp[u], n_units; cursor[K] zeroed.
+__global__ void __launch_bounds__(1024) tc_bucket_scan_kernel(const int* __restrict__ cnt, int K, int unit_rows, int* __restrict__ off,
+                                                              int* __restrict__ cursor, int* __restrict__ unit_comp, int* __restrict__ n_units) {
+    __shared__ int s_first[1024];        // first unit of bucket k
+    if (threadIdx.x == 0) {
+        int u = 0;
+        for (int k = 0; k < K; ++k) { s_first[k] = u; u += (cnt[k] + unit_rows - 1) / unit_rows; }
+        *n_units = u;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int u0 = s_first[k], nu = (cnt[k] + unit_rows - 1) / unit_rows;
+        off[k] = u0 * unit_rows;
+        cursor[k] = 0;
+        for (int u = 0; u < nu; ++u) unit_comp[u0 + u] = k;
+    }
+}
+
+// slot of every pilot inside its bucket (order within a bucket is irrelevant: pilots are independent): rank within the block from
+// a shared-memory histogram, one global atomic per (block, non-empty bucket) reserves the block's range
+__global__ void __launch_bounds__(1024) tc_bucket_place_kernel(const int* __restrict__ top, int64_t B, int K, const int* __restrict__ off,
+                                                               int* __restrict__ cursor, int* __restrict__ perm) {
+    __shared__ int s_cnt[1024];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = 0, local = 0;
+    if (b < B) { k = top[b]; local = atomicAdd(&s_cnt[k], 1); }
+    __syncthreads();
+    for (int j = threadIdx.x; j < K; j += blockDim.x) { const int c = s_cnt[j]; s_cnt[j] = c ? off[j] + atomicAdd(cursor + j, c) : 0; }
+    __syncthreads();
+    if (b < B) perm[s_cnt[k] + local] = (int)b;
+}
+
+// pilot tiles in bucket order: one block per destination tile, a thread moves the 16-byte K-core pieces of one pilot row
+// (row r of a tile keeps its piece of core column kb at byte (kb * 16) * 128 + r * 16 of each copy)
+__global__ void __launch_bounds__(256) tc_bucket_gather_kernel(const unsigned char* __restrict__ img, const int* __restrict__ perm,
+                                                               const int* __restrict__ n_units, int tiles_per_unit, int kbs, int copies,
+                                                               unsigned char* __restrict__ img2) {
+    const int64_t tile = blockIdx.x;
+    if (tile >= (int64_t)__ldg(n_units) * tiles_per_unit) return;
+    const int r = threadIdx.x & (TILE_M - 1);
+    const size_t tile_bytes = (size_t)copies * kbs * TILE_M * 16;
+    const int src = __ldg(perm + tile * TILE_M + r);
+    const unsigned char* from = img + (size_t)(src >= 0 ? src / TILE_M : 0) * tile_bytes + (size_t)(src >= 0 ? src % TILE_M : 0) * 16;
+    unsigned char* to = img2 + (size_t)tile * tile_bytes + (size_t)r * 16;
+    for (int c = threadIdx.x / TILE_M; c < copies * kbs; c += 256 / TILE_M) {
+        const uint4 v = src >= 0 ? __ldg(reinterpret_cast<const uint4*>(from + (size_t)c * TILE_M * 16)) : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(to + (size_t)c * TILE_M * 16) = v;
+    }
+}
+
 static std::mutex g_scratch_mu;
 static std::map<cudaStream_t, TileScratch> g_scratch;
 
@@ -981,6 +1068,23 @@ static qce_status tc_scratch_aux(TileScratch* t, size_t rows, size_t K) {
         t->wts = nullptr; t->wts_bytes = 0;
         QCE_CUDA_TRY(cudaMalloc(&t->wts, need_w));
         t->wts_bytes = need_w;
+    }
+    return QCE_OK;
+}
+
+static qce_status tc_scratch_bucket(TileScratch* t, size_t img2_bytes, size_t idx_ints) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    if (img2_bytes > t->img2_bytes) {
+        if (t->img2) QCE_CUDA_TRY(cudaFree(t->img2));
+        t->img2 = nullptr; t->img2_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t->img2, img2_bytes));
+        t->img2_bytes = img2_bytes;
+    }
+    if (idx_ints * sizeof(int) > t->bidx_bytes) {
+        if (t->bidx) QCE_CUDA_TRY(cudaFree(t->bidx));
+        t->bidx = nullptr; t->bidx_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t->bidx, idx_ints * sizeof(int)));
+        t->bidx_bytes = idx_ints * sizeof(int);
     }
     return QCE_OK;
 }
@@ -1161,13 +1265,16 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     a.h_stride = 2 * m->n_ant; a.h_col0 = 0; a.count_rows = 1;
     const char* th = getenv("QCE_TC_SKIP");                 // tuning knob (read per launch); measured: no effect up to 1e-9
     a.skip_thresh = th ? (float)atof(th) : 1e-30f;
+    a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr;
 }
 
 static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,
-                               const void* h_true, int h_true_c64, double* acc) {
+                               const void* h_true, int h_true_c64, double* acc, const int* unit_comp = nullptr, const int* perm = nullptr,
+                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr) {
     const TcParams& p = m->tc;
     TcArgs a;
     tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
+    if (unit_comp) { a.unit_comp = unit_comp; a.perm = perm; a.n_units_dev = n_units_dev; a.a_img = (const __half*)bucket_img; }
     a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
     a.h_col0 = part * p.part_cols;
     a.count_rows = part == 0;
@@ -1252,6 +1359,19 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
     const bool want_est = h_est || acc;
     const size_t tile_bytes = (size_t)TILE_M * 2 * m->n_obs * sizeof(__half) * (m->tc.split_a ? 2 : 1);
     const size_t true_row = (size_t)m->n_ant * (h_true_c64 ? 8 : 16);
+    // top-1: regroup the pilots by selected component and run ONE component per work unit (QCE_TC_BUCKET=0: weighted launch instead)
+    const int tiles_per_unit = 2 * ((m->tc.split_a && 2 * m->n_obs > 128) ? 1 : TILES);      // CG * Cfg::NTILES of the split launches
+    const int bucket_rows = tiles_per_unit * TILE_M;
+    const bool bucket_env = !(getenv("QCE_TC_BUCKET") && atoi(getenv("QCE_TC_BUCKET")) == 0);      // read per call (A/B runs, parity test)
+    const bool bucketed = bucket_env && want_est && mode == QCE_MODE_TOP1 && m->n_comp >= 4 && chunk >= 4 * (int64_t)bucket_rows;
+    const int64_t cap_units = chunk / bucket_rows + m->n_comp + 1, cap_rows = cap_units * bucket_rows;
+    int *b_top = nullptr, *b_perm = nullptr, *b_ucomp = nullptr, *b_cnt = nullptr, *b_off = nullptr, *b_cur = nullptr, *b_nu = nullptr;
+    if (bucketed) {
+        st = tc_scratch_bucket(ts, (size_t)(cap_rows / TILE_M + 4) * tile_bytes, (size_t)(chunk + cap_rows + cap_units + 3 * m->n_comp + 1));
+        if (st) return st;
+        b_top = (int*)ts->bidx; b_perm = b_top + chunk; b_ucomp = b_perm + cap_rows; b_cnt = b_ucomp + cap_units;
+        b_off = b_cnt + m->n_comp; b_cur = b_off + m->n_comp; b_nu = b_cur + m->n_comp;
+    }
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0) < chunk ? (B - b0) : chunk;
         TileScratch v = *ts;                                   // view of this chunk's tiles (b0 is a multiple of the tile size)
@@ -1264,13 +1384,30 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         if (st) return st;
         {
             const unsigned grid = (unsigned)((nb + 7) / 8);
-            float* wts = want_est ? (float*)v.wts : nullptr;
-            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo);
-            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo);
-            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo);
+            float* wts = (want_est && !bucketed) ? (float*)v.wts : nullptr;
+            if (bucketed) {
+                QCE_CUDA_TRY(cudaMemsetAsync(b_cnt, 0, m->n_comp * sizeof(int), s));
+                QCE_CUDA_TRY(cudaMemsetAsync(b_perm, 0xFF, (size_t)cap_rows * sizeof(int), s));        // -1 = padding slot
+            }
+            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
+            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
+            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
         }
         QCE_CHECK_LAUNCH("tc_select_kernel");
         if (!want_est) continue;
+        if (bucketed) {
+            tc_bucket_count_kernel<<<(unsigned)((nb + 1023) / 1024), 1024, 0, s>>>(b_top, nb, m->n_comp, b_cnt);
+            tc_bucket_scan_kernel<<<1, 1024, 0, s>>>(b_cnt, m->n_comp, bucket_rows, b_off, b_cur, b_ucomp, b_nu);
+            tc_bucket_place_kernel<<<(unsigned)((nb + 1023) / 1024), 1024, 0, s>>>(b_top, nb, m->n_comp, b_off, b_cur, b_perm);
+            tc_bucket_gather_kernel<<<(unsigned)(cap_rows / TILE_M), 256, 0, s>>>((const unsigned char*)v.img, b_perm, b_nu, tiles_per_unit,
+                                                                                  2 * m->n_obs / 8, m->tc.split_a ? 2 : 1, (unsigned char*)ts->img2);
+            QCE_CHECK_LAUNCH("tc_bucket kernels");
+            for (int part = 0; part < m->tc.h_parts; ++part) {
+                st = tc_run_split(m, &v, s, cap_rows, 2, part, he, ht, h_true_c64, acc, b_ucomp, b_perm, b_nu, ts->img2);
+                if (st) return st;
+            }
+            continue;
+        }
         for (int part = 0; part < m->tc.h_parts; ++part) {
             st = tc_run_split(m, &v, s, nb, 2, part, he, ht, h_true_c64, acc);
             if (st) return st;

@@ -56,6 +56,11 @@ struct TcArgs {
     const double* obs_labels;
     float skip_thresh;         // fused 'all' epilogue: a warp skips the LMMSE row of a component whose un-normalised weight is below
                                // this for all of its 32 pilots (the normaliser is >= 1, so the dropped terms are < skip_thresh each)
+    // bucketed top-1 combination (EPI=2, all three null otherwise): the pilots were regrouped by their selected component, work
+    // unit u holds pilots of component unit_comp[u] only and runs that ONE component; slot -> pilot through perm (-1 = padding)
+    const int* unit_comp;      // [*n_units_dev]
+    const int* perm;           // [B] (B = slot capacity of the launch)
+    const int* n_units_dev;    // number of work units actually filled (device-side: the bucket sizes are data)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -182,6 +187,9 @@ struct TileScratch {
     void* lp2 = nullptr;                   // [rows][K] float2 log-probabilities (modes other than fused 'all')
     void* wts = nullptr;                   // [rows][K] float weights
     size_t img_bytes = 0, bad_bytes = 0, lp2_bytes = 0, wts_bytes = 0;
+    void* img2 = nullptr;                  // bucketed top-1: pilot tiles regrouped by selected component
+    void* bidx = nullptr;                  // int32: top[rows] | perm[slots] | unit_comp[units] | cnt[K] off[K] cursor[K] n_units
+    size_t img2_bytes = 0, bidx_bytes = 0;
     const qce_model* owner = nullptr;      // model whose pilots are currently formatted here
     int64_t rows = 0;
 };

@@ -854,3 +854,51 @@ def test_c_abi_error_behaviour(qce):
         lib.qce_quantizer_destroy(q)
     finally:
         lib.qce_model_destroy(m2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('K,N,B,snr,nb,qt,ms,kind', [
+    (64, 64, 6000, 10, 1, 'uniform', 0.0, 'gmm'),       # config-2 shape, fused-shape model on the per-purpose launches
+    (5, 32, 2500, 0, 2, 'uniform', 0.1, 'gmm'),         # means: offsets in the combine epilogue; some buckets nearly empty
+    (9, 128, 4200, 10, 2, 'uniform', 0.0, 'gmm'),       # split shape: two LMMSE row blocks per pilot
+    (6, 128, 2100, 5, 3, 'lloyd', 0.1, 'gmm'),          # off-grid pilots: (hi, lo) tile pairs, one tile per CTA
+    (8, 64, 3000, 10, 1, 'uniform', 0.0, 'mfa'),        # MFA: argmax of exp(l) (label 0 on underflow)
+])
+def test_tc_top1_bucketed_combination(qce, K, N, B, snr, nb, qt, ms, kind):
+    """Top-1 on large batches regroups the pilots by selected component and runs ONE component per work unit (1/K of the combine
+    work).  Must equal the weighted three-launch path bit for bit (QCE_TC_BUCKET=0), NaN rows and NMSE accumulators included, and
+    match the oracle."""
+    import os
+    if kind == 'gmm':
+        means, covs, w = orc.random_psd_gmm(K, N, seed=K + N, mean_scale=ms)
+        h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=K)
+        m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+        oracle = lambda r, qz: orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=1, n_bits=nb, quantizer_type=qt,
+                                                       quantizer=qz)
+    else:
+        means, lam, psi, w = orc.random_mfa(K, N, 4, seed=K + N)
+        covs = orc.mofa_covs(lam, psi)
+        h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=K)
+        m = qce.Mofa(K, 4, verbose=False).set_parameters(means, lam, psi, w)
+        oracle = lambda r, qz: orc.mofa_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=1, n_bits=nb, quantizer_type=qt,
+                                                        quantizer=qz)
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    r[17, 3] = np.nan                                     # a row the tensor path cannot represent: NaN estimate, still counted
+    m.precision = 'tc'
+    model = m._prepared(np.eye(N), snr, nb, qt, qz)
+    rt, ht = torch.from_numpy(r).cuda(), torch.from_numpy(h).cuda()
+    e1, l1, a1 = model.estimate(rt, 1, 'tc', want_logp=True, h_true=ht)
+    os.environ['QCE_TC_BUCKET'] = '0'
+    try:
+        e0, l0, a0 = model.estimate(rt, 1, 'tc', want_logp=True, h_true=ht)
+    finally:
+        del os.environ['QCE_TC_BUCKET']
+    ok = torch.ones(B, dtype=torch.bool, device='cuda'); ok[17] = False
+    assert torch.equal(e0[ok], e1[ok]) and torch.equal(l0[ok], l1[ok])
+    assert bool(torch.isnan(e1[17]).all()) and bool(torch.isnan(e0[17]).all())
+    assert a1.cpu().numpy()[2] == B
+    good = np.ones(B, dtype=bool); good[17] = False
+    ref = oracle(r[good], qz)
+    per = np.linalg.norm(e1.cpu().numpy()[good] - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert np.mean(per > TOL_TC) < 0.01, np.mean(per > TOL_TC)          # near-ties may pick the other component under FP32
