@@ -231,6 +231,11 @@ __device__ __forceinline__ void fmt_items(const TcArgs& a, int64_t first_tile, i
 // KDC = n_obs / 16 (reduction length 32 KDC); NCHZ = 0 (no whitening columns: an H-part launch) or KDC; NCHH = H columns / 32
 // PRO = true: fused prologue -- no formatter launch, the kernel builds its own pilot tiles from (h, noise): the epilogue warps format
 // the first work unit of the CTA, warp 2 every further one while the tensor pipe works on the previous.
+// hi_a + lo_a > hi_b + lo_b, exactly (the FP64 sums of FP32 pairs are exact)
+__device__ __noinline__ bool pair_greater_f64(float hi_a, float lo_a, float hi_b, float lo_b) {
+    return ((double)hi_a + (double)lo_a) > ((double)hi_b + (double)lo_b);
+}
+
 template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC, bool PRO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
@@ -458,6 +463,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             for (int j = 0; j < NH / 2; ++j) acc[j] = make_float2(0.f, 0.f);
             float mref_hi = 0.f, mref_lo = 0.f;
             float ssum = 0.f;
+            float best_hi = -INFINITY, best_lo = 0.f;  // EPI=1 label mode: running maximum of l_k as an FP32 pair
+            int best_k = 0;
 
             // the pilot this thread handles, and the components of this unit
             int64_t src = tile_base + row;
@@ -544,7 +551,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 const float bq = l_hi - lc.x;
                 const float l_lo = ((lc.x - (l_hi - bq)) + (-q_hi - bq)) + (lc.y - q_lo);
                 if (EPI == 1) {
-                    if (tile_base + row < a.B) a.lp_out[(tile_base + row) * a.K + k] = make_float2(l_hi, l_lo);
+                    if (a.top_out) {
+                        // top-1 label only.  tc_select_kernel compares the FP64 sums hi + lo; the same decision in FP32 (FP64
+                        // arithmetic next to the saturated tensor pipe cost 18 % of this launch): the difference of the pairs,
+                        // with the exact FP64 comparison only where its rounding error could change the sign
+                        const float d_hi = l_hi - best_hi, d_lo = l_lo - best_lo;
+                        const float d = d_hi + d_lo;
+                        const bool safe = fabsf(d) > 4.8e-7f * (fabsf(d_hi) + fabsf(d_lo));               // 2^-21 > the 3 x 2^-24 rounding bound
+                        bool better = d > 0.f;
+                        // ties, NaN, infinities, the first component: rare, and behind a warp-uniform branch and a call so that the
+                        // compiler cannot turn the FP64 comparison into unconditional arithmetic + select
+                        if (__any_sync(0xffffffffu, !safe)) { if (!safe) better = pair_greater_f64(l_hi, l_lo, best_hi, best_lo); }
+                        if (better) { best_hi = l_hi; best_lo = l_lo; best_k = k; }
+                    } else if (tile_base + row < a.B) a.lp_out[(tile_base + row) * a.K + k] = make_float2(l_hi, l_lo);
                     p = 0.f;
                 } else {
                 // ---- lazily rescaled online softmax (reference maximum moves only on jumps > 8)
@@ -610,6 +629,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             // ---- finalise: normalise, write the estimate row, NMSE accumulators (FP32 per row: FP64 stalls behind the
             // tensor pipe; the per-row sums enter the FP64 accumulators once)
             const int64_t g = src;
+            if (EPI == 1 && a.top_out && valid) {
+                if ((a.top_flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp((double)best_hi + (double)best_lo) == 0.0) best_k = 0;
+                a.top_out[g] = best_k;
+            }
             if (EPI != 1 && valid) {
                 // (read here, after the last component: with the fused prologue the flags are written by other warps of this kernel)
                 const bool row_bad = (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) != 0;
@@ -1266,15 +1289,17 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     const char* th = getenv("QCE_TC_SKIP");                 // tuning knob (read per launch); measured: no effect up to 1e-9
     a.skip_thresh = th ? (float)atof(th) : 1e-30f;
     a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr;
+    a.top_out = nullptr; a.top_flags = m->flags;
 }
 
 static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,
                                const void* h_true, int h_true_c64, double* acc, const int* unit_comp = nullptr, const int* perm = nullptr,
-                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr) {
+                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr) {
     const TcParams& p = m->tc;
     TcArgs a;
     tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
     if (unit_comp) { a.unit_comp = unit_comp; a.perm = perm; a.n_units_dev = n_units_dev; a.a_img = (const __half*)bucket_img; }
+    a.top_out = top_out;
     a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
     a.h_col0 = part * p.part_cols;
     a.count_rows = part == 0;
@@ -1380,15 +1405,17 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         double* he = h_est ? h_est + (size_t)b0 * m->n_ant * 2 : nullptr;
         double* lo = logp_out ? logp_out + (size_t)b0 * m->n_comp : nullptr;
         const void* ht = h_true ? (const void*)((const char*)h_true + (size_t)b0 * true_row) : nullptr;
-        st = tc_run_split(m, &v, s, nb, 1, 0, nullptr, nullptr, 0, nullptr);
+        // top-1 without log-probability export: the whitening launch keeps the running argmax itself (no [rows][K] export, no selection launch)
+        const bool label_in_kernel = bucketed && !logp_out;
+        st = tc_run_split(m, &v, s, nb, 1, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, label_in_kernel ? b_top : nullptr);
         if (st) return st;
-        {
+        if (bucketed) {
+            QCE_CUDA_TRY(cudaMemsetAsync(b_cnt, 0, m->n_comp * sizeof(int), s));
+            QCE_CUDA_TRY(cudaMemsetAsync(b_perm, 0xFF, (size_t)cap_rows * sizeof(int), s));        // -1 = padding slot
+        }
+        if (!label_in_kernel) {
             const unsigned grid = (unsigned)((nb + 7) / 8);
             float* wts = (want_est && !bucketed) ? (float*)v.wts : nullptr;
-            if (bucketed) {
-                QCE_CUDA_TRY(cudaMemsetAsync(b_cnt, 0, m->n_comp * sizeof(int), s));
-                QCE_CUDA_TRY(cudaMemsetAsync(b_perm, 0xFF, (size_t)cap_rows * sizeof(int), s));        // -1 = padding slot
-            }
             if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
             else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
             else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);

@@ -61,6 +61,10 @@ struct TcArgs {
     const int* unit_comp;      // [*n_units_dev]
     const int* perm;           // [B] (B = slot capacity of the launch)
     const int* n_units_dev;    // number of work units actually filled (device-side: the bucket sizes are data)
+    // EPI=1 with top_out != null: running argmax of l_k in the epilogue thread instead of the log-probability export (top-1 label
+    // with tc_select_kernel's semantics: first index among equal maxima; QCE_FLAG_TOP1_EXP_ARGMAX in top_flags: label 0 on underflow)
+    int* top_out;              // [B]
+    int top_flags;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers

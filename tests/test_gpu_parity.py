@@ -889,6 +889,7 @@ def test_tc_top1_bucketed_combination(qce, K, N, B, snr, nb, qt, ms, kind):
     model = m._prepared(np.eye(N), snr, nb, qt, qz)
     rt, ht = torch.from_numpy(r).cuda(), torch.from_numpy(h).cuda()
     e1, l1, a1 = model.estimate(rt, 1, 'tc', want_logp=True, h_true=ht)
+    e2, a2 = model.estimate(rt, 1, 'tc', h_true=ht)       # no log-probability export: the whitening launch keeps the argmax itself
     os.environ['QCE_TC_BUCKET'] = '0'
     try:
         e0, l0, a0 = model.estimate(rt, 1, 'tc', want_logp=True, h_true=ht)
@@ -896,8 +897,9 @@ def test_tc_top1_bucketed_combination(qce, K, N, B, snr, nb, qt, ms, kind):
         del os.environ['QCE_TC_BUCKET']
     ok = torch.ones(B, dtype=torch.bool, device='cuda'); ok[17] = False
     assert torch.equal(e0[ok], e1[ok]) and torch.equal(l0[ok], l1[ok])
-    assert bool(torch.isnan(e1[17]).all()) and bool(torch.isnan(e0[17]).all())
-    assert a1.cpu().numpy()[2] == B
+    assert torch.equal(e1[ok], e2[ok])
+    assert bool(torch.isnan(e1[17]).all()) and bool(torch.isnan(e0[17]).all()) and bool(torch.isnan(e2[17]).all())
+    assert a1.cpu().numpy()[2] == B and a2.cpu().numpy()[2] == B
     good = np.ones(B, dtype=bool); good[17] = False
     ref = oracle(r[good], qz)
     per = np.linalg.norm(e1.cpu().numpy()[good] - ref, axis=1) / np.linalg.norm(ref, axis=1)
