@@ -54,7 +54,7 @@ def main():
     r = pilots(1 << 19, 64, 1, (None, None))
     for mode in (1, 4, 0.9):
         ms = timeit(lambda: m.estimate_from_y(r, snr, 64, n_summands_or_proba=mode))
-        out.append(dict(config=f'C2 GMM full 1-bit N=64 K=64 mode={mode}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='tc 3-launch'))
+        out.append(dict(config=f'C2 GMM full 1-bit N=64 K=64 mode={mode}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='tc bucketed top-1' if mode == 1 else 'tc 3-launch'))
     # C3: block-circulant 16x16, 3-bit Lloyd, N=256, K=128
     c, _, w, _ = synthetic.circulant_gmm(128, 16, 16, seed=0)
     qz = qce.get_quantizer([snr], 3, 'lloyd')[snr]
