@@ -904,3 +904,36 @@ def test_tc_top1_bucketed_combination(qce, K, N, B, snr, nb, qt, ms, kind):
     ref = oracle(r[good], qz)
     per = np.linalg.norm(e1.cpu().numpy()[good] - ref, axis=1) / np.linalg.norm(ref, axis=1)
     assert np.mean(per > TOL_TC) < 0.01, np.mean(per > TOL_TC)          # near-ties may pick the other component under FP32
+
+
+@pytest.mark.gpu
+def test_tc_top1_bucketed_full_size_chunks(qce):
+    """Config-2 size (2^19 pilots, K = 64, N = 64, 1 bit): the bucketed top-1 path over several chunks (bucket scratch reused, ragged
+    last chunk) equals the weighted three-launch path bit for bit, and every pilot is written exactly once."""
+    import os
+    from quantized_channel_estimation_b200 import synthetic
+    K, N, B, snr = 64, 64, (1 << 19) - 77, 10
+    means, covs, w = synthetic.random_psd_gmm(K, N, seed=0)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    model = m._prepared(np.eye(N), snr, 1, 'uniform', None)
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    bits = torch.randint(0, 2, (B, N, 2), generator=gen, device='cuda', dtype=torch.int8)
+    r = torch.view_as_complex(((bits.to(torch.float64) * 2 - 1) * np.sqrt(0.5)).contiguous())
+    h_true = torch.view_as_complex(torch.randn((B, N, 2), generator=gen, device='cuda', dtype=torch.float64))
+    os.environ['QCE_TC_BUCKET'] = '0'
+    try:
+        e0, a0 = model.estimate(r, 1, 'tc', h_true=h_true)
+    finally:
+        del os.environ['QCE_TC_BUCKET']
+    e1, a1 = model.estimate(r, 1, 'tc', h_true=h_true)
+    assert torch.equal(e0, e1)
+    os.environ['QCE_TC_MODE_CHUNK'] = '150000'
+    try:
+        e2, a2 = model.estimate(r, 1, 'tc', h_true=h_true)
+    finally:
+        del os.environ['QCE_TC_MODE_CHUNK']
+    assert torch.equal(e0, e2) and not bool(torch.isnan(e2.real).any())
+    for a in (a1, a2):
+        np.testing.assert_allclose(a.cpu().numpy(), a0.cpu().numpy(), rtol=1e-9)
+        assert a.cpu().numpy()[2] == B
