@@ -226,16 +226,18 @@ __device__ __forceinline__ void fmt_items(const TcArgs& a, int64_t first_tile, i
     }
 }
 
-// EPI selects the epilogue: 0 = fused 'all' estimate (online softmax), 1 = export the weighted log-probabilities l_k only,
-// 2 = combine with given per-pilot weights (the top-1 / top-n / cumulative-probability modes run 1 -> select -> 2)
-// KDC = n_obs / 16 (reduction length 32 KDC); NCHZ = 0 (no whitening columns: an H-part launch) or KDC; NCHH = H columns / 32
-// PRO = true: fused prologue -- no formatter launch, the kernel builds its own pilot tiles from (h, noise): the epilogue warps format
-// the first work unit of the CTA, warp 2 every further one while the tensor pipe works on the previous.
 // hi_a + lo_a > hi_b + lo_b, exactly (the FP64 sums of FP32 pairs are exact)
 __device__ __noinline__ bool pair_greater_f64(float hi_a, float lo_a, float hi_b, float lo_b) {
     return ((double)hi_a + (double)lo_a) > ((double)hi_b + (double)lo_b);
 }
 
+// EPI selects the epilogue: 0 = fused 'all' estimate (online softmax), 1 = export the weighted log-probabilities l_k only (or, with
+// TcArgs::top_out, keep only their running argmax: the top-1 label), 2 = combine with given per-pilot weights (the top-n /
+// cumulative-probability modes run 1 -> select -> 2) or, with TcArgs::unit_comp, the single component of each work unit of pilots
+// regrouped by label (top-1 on large batches: 1 -> bucket -> 2)
+// KDC = n_obs / 16 (reduction length 32 KDC); NCHZ = 0 (no whitening columns: an H-part launch) or KDC; NCHH = H columns / 32
+// PRO = true: fused prologue -- no formatter launch, the kernel builds its own pilot tiles from (h, noise): the epilogue warps format
+// the first work unit of the CTA, warp 2 every further one while the tensor pipe works on the previous.
 template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC, bool PRO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
