@@ -71,6 +71,10 @@ const char* qce_last_error_string(void);
 int64_t qce_launch_count(void);
 /* 1 if a CUDA device of compute capability 10.x is visible */
 int qce_device_ok(void);
+/* Rows of the most recent QCE_PREC_TC estimate enqueued on `stream` (current device) that the tensor-core path handed to the
+ * complex128 kernel: pilots off the quantiser grid and hard selections (top-1 / top-n / cumulative) whose deciding log-likelihood
+ * gap is below what FP32 accumulation resolves.  Synchronises the stream.  -1 if no such call has been made on the stream. */
+int64_t qce_last_fix_count(void* stream);
 
 /* ---- quantiser (modules/utils.py:189-203; tables from utils.py:531-590) ----------------------- */
 

@@ -18,6 +18,7 @@ _SIGS = {
     'qce_last_error_string': (C.c_char_p, []),
     'qce_launch_count': (C.c_int64, []),
     'qce_device_ok': (C.c_int, []),
+    'qce_last_fix_count': (C.c_int64, [C.c_void_p]),
     'qce_quantizer_create': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     'qce_quantizer_destroy': (None, [C.c_void_p]),
     'qce_quantize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -11,6 +12,19 @@
 namespace qce {
 static thread_local char g_err[512] = "";
 int64_t g_launch_count = 0;
+
+// fix list (count first) of the most recent tensor-core estimate per (device, stream): qce_last_fix_count
+static std::mutex g_fix_mu;
+static std::map<std::pair<int, cudaStream_t>, const int*> g_fix_last;
+void note_fix_list(cudaStream_t s, const int* fix_buf) {
+    std::lock_guard<std::mutex> lock(g_fix_mu);
+    g_fix_last[std::make_pair(current_device(), s)] = fix_buf;
+}
+const int* last_fix_list(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_fix_mu);
+    auto it = g_fix_last.find(std::make_pair(current_device(), s));
+    return it == g_fix_last.end() ? nullptr : it->second;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -60,6 +74,15 @@ std::mutex g_staging_mu;          // one host-path call at a time (the slots are
 extern "C" {
 
 int qce_abi_version(void) { return QCE_ABI_VERSION; }
+
+int64_t qce_last_fix_count(void* stream) {
+    const int* p = last_fix_list((cudaStream_t)stream);
+    if (!p) return -1;
+    int n = 0;
+    if (cudaMemcpyAsync(&n, p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
 const char* qce_last_error_string(void) { return g_err; }
 int64_t qce_launch_count(void) { return g_launch_count; }
 

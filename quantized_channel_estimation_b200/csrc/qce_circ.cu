@@ -27,6 +27,8 @@ struct CircArgs {
     double* acc;
     int mode, n_top, flags;
     double rho;
+    const int* rows;              // re-evaluation of listed pilots (null: pilots 0 .. B-1 in order): tile entry i is pilot rows[i],
+    const int* n_rows_dev;        // i < *n_rows_dev
 };
 
 __device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
@@ -70,17 +72,20 @@ __global__ void __launch_bounds__(256) circ_kernel(CircArgs a) {
     double2* tw1 = reinterpret_cast<double2*>(part + (size_t)256 * TS);   // [n1] e^{-2 pi i j / n1}
     double2* tw2 = tw1 + n1;                                          // [n2]
     __shared__ double red[3];
+    __shared__ int64_t s_row[TS];
     const int t = threadIdx.x;
-    const int64_t base = (int64_t)blockIdx.x * TS;
-    const int nvalid = (int)((a.B - base) < TS ? (a.B - base) : TS);
-
     for (int j = t; j < n1; j += 256) { double sn, cs; sincospi(-2.0 * j / n1, &sn, &cs); tw1[j] = make_double2(cs, sn); }
     for (int j = t; j < n2; j += 256) { double sn, cs; sincospi(-2.0 * j / n2, &sn, &cs); tw2[j] = make_double2(cs, sn); }
+    const int64_t n_rows = a.n_rows_dev ? (int64_t)__ldg(a.n_rows_dev) : a.B;
+    for (int64_t base = (int64_t)blockIdx.x * TS; base < n_rows; base += (int64_t)gridDim.x * TS) {
+    const int nvalid = (int)((n_rows - base) < TS ? (n_rows - base) : TS);
+    if (t < TS) s_row[t] = (t < nvalid) ? (a.rows ? (int64_t)a.rows[base + t] : base + t) : 0;
+    if (t < 3) red[t] = 0.0;
+    __syncthreads();
     for (int o = t; o < TS * N; o += 256) {
         const int s = o / N;
-        X[o] = (s < nvalid) ? a.r[base * N + o] : make_double2(0.0, 0.0);
+        X[o] = (s < nvalid) ? a.r[s_row[s] * N + (o % N)] : make_double2(0.0, 0.0);
     }
-    if (t < 3) red[t] = 0.0;
     __syncthreads();
 
     // ---- rt = F r  (n2 axis, then n1 axis)
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(256) circ_kernel(CircArgs a) {
         }
     }
     if (a.logp_out) {
-        for (int o = t; o < nvalid * K; o += 256) a.logp_out[base * K + o] = lp[o];
+        for (int o = t; o < nvalid * K; o += 256) a.logp_out[s_row[o / K] * K + (o % K)] = lp[o];
         __syncthreads();
     }
     if (t < TS) weights_from_logp(lp + (size_t)t * K, K, a.mode, a.n_top, a.rho, a.flags);
@@ -170,9 +175,10 @@ __global__ void __launch_bounds__(256) circ_kernel(CircArgs a) {
         double err = 0.0, pw = 0.0;
         for (int o = t; o < nvalid * N; o += 256) {
             const double2 v = X[o];
-            if (a.h_est) a.h_est[base * N + o] = v;
+            const int64_t go = s_row[o / N] * N + (o % N);
+            if (a.h_est) a.h_est[go] = v;
             if (a.acc && a.h_true) {
-                const double2 h = a.h_true[base * N + o];
+                const double2 h = a.h_true[go];
                 const double dx = v.x - h.x, dy = v.y - h.y;
                 err += dx * dx + dy * dy;
                 pw += h.x * h.x + h.y * h.y;
@@ -189,16 +195,17 @@ __global__ void __launch_bounds__(256) circ_kernel(CircArgs a) {
             if (t == 0) { atomicAdd(a.acc + 0, red[0]); atomicAdd(a.acc + 1, red[1]); atomicAdd(a.acc + 2, (double)nvalid); }
         }
     }
+    __syncthreads();      // the tile buffers are rewritten by the next tile of this CTA
+    }
 }
 
 template <int TS>
-static qce_status launch_ts(const CircArgs& a, cudaStream_t s, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        QCE_CUDA_TRY(cudaFuncSetAttribute(circ_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
-    circ_kernel<TS><<<(unsigned)((a.B + TS - 1) / TS), 256, smem, s>>>(a);
+static qce_status launch_ts(const CircArgs& a, cudaStream_t s, size_t smem, int64_t grid_cap = 0) {
+    static PerDeviceOnce once;
+    if (once.first(current_device())) QCE_CUDA_TRY(cudaFuncSetAttribute(circ_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int64_t grid = (a.B + TS - 1) / TS;
+    if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+    circ_kernel<TS><<<(unsigned)grid, 256, smem, s>>>(a);
     QCE_CHECK_LAUNCH("circ_kernel");
     return QCE_OK;
 }
@@ -211,6 +218,7 @@ qce_status launch_circ(const qce_circ_model* m, cudaStream_t s, const double* r,
     a.inv_lambda_t = m->inv_lambda_t; a.gain = m->gain; a.logc = m->logc;
     a.r = (const double2*)r; a.h_est = (double2*)h_est; a.logp_out = logp_out; a.h_true = (const double2*)h_true; a.acc = acc;
     a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;
+    a.rows = nullptr; a.n_rows_dev = nullptr;
     auto need = [&](int ts) {
         return (size_t)2 * ts * a.N * sizeof(double2) + (size_t)ts * a.K * sizeof(double) + (size_t)256 * ts * sizeof(double) +
                (size_t)(a.n1 + a.n2) * sizeof(double2);
@@ -221,6 +229,25 @@ qce_status launch_circ(const qce_circ_model* m, cudaStream_t s, const double* r,
     if (need(4) <= cap) return launch_ts<4>(a, s, need(4));
     set_error("circulant kernel: N=%d, K=%d do not fit shared memory", a.N, a.K);
     return QCE_ERR_UNSUPPORTED;
+}
+
+// complex128 re-evaluation of a device-side list of pilots (rows[0 .. *n_rows_dev)): small tiles, a grid that does not depend on
+// the length of the list (CTAs without a tile exit at once; long lists are walked grid-stride)
+qce_status launch_circ_rows(const qce_circ_model* m, cudaStream_t s, const double* r, const int* rows, const int* n_rows_dev, int64_t max_rows,
+                            int mode, int n_top, double rho, double* h_est, const double* h_true, double* acc) {
+    if (max_rows == 0) return QCE_OK;
+    CircArgs a;
+    a.n1 = m->n1; a.n2 = m->n2; a.N = m->n_ant; a.K = m->n_comp; a.B = max_rows;
+    a.inv_lambda_t = m->inv_lambda_t; a.gain = m->gain; a.logc = m->logc;
+    a.r = (const double2*)r; a.h_est = (double2*)h_est; a.logp_out = nullptr; a.h_true = (const double2*)h_true; a.acc = acc;
+    a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;
+    a.rows = rows; a.n_rows_dev = n_rows_dev;
+    const size_t need = (size_t)2 * 4 * a.N * sizeof(double2) + (size_t)4 * a.K * sizeof(double) + (size_t)256 * 4 * sizeof(double) +
+                        (size_t)(a.n1 + a.n2) * sizeof(double2);
+    if (need > (size_t)220 * 1024) { set_error("circulant kernel: N=%d, K=%d do not fit shared memory", a.N, a.K); return QCE_ERR_UNSUPPORTED; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+    return launch_ts<4>(a, s, need, 2 * (int64_t)sms);
 }
 
 }  // namespace qce

@@ -16,6 +16,9 @@
 // Any real-valued pilots are accepted (no grid assumption: Lloyd-Max labels, infinite resolution).
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+
 #include "qce_common.cuh"
 
 namespace qce {
@@ -55,6 +58,8 @@ struct CircTcArgs {
     int mode, n_top, flags;
     double rho;
     int prefetch_dist;               // tiles ahead to prefetch into L2 (= resident CTAs), 0 = off
+    int* fix_buf;                    // [1 + B] hard selections too close to call in FP32: count, then the pilots -- not answered
+    double tie_eps;                  // here but re-evaluated by the complex128 kernel (launch_circ_rows)
 };
 
 __device__ __forceinline__ float2 operator+(const float2 a, const float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
     float* invsc = reinterpret_cast<float*>(R + CT_R_BYTES);                       // [32] 1 / per-pilot scale of |rt|^2
     float* qref = invsc + CT_P;                                                    // [32] sum_i |rt_i|^2 mean_k(1 / lambda_k,i)
     double* red = reinterpret_cast<double*>(R + CT_R_BYTES + 256);                 // [2]
+    int* tief = reinterpret_cast<int*>(R + CT_R_BYTES + 288);                      // [32] pilot handed to the complex128 kernel
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t base = (int64_t)blockIdx.x * CT_P;
@@ -336,7 +342,13 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
             }
         }
     } else {
-        if (tid < CT_P) weights_from_logp(lbuf + tid * LP, K, a.mode, a.n_top, a.rho, a.flags);
+        if (tid < CT_P) {
+            bool tie = false;
+            weights_from_logp(lbuf + tid * LP, K, a.mode, a.n_top, a.rho, a.flags, &tie, a.tie_eps);
+            tie = tie && tid < nvalid;
+            tief[tid] = tie;
+            if (tie) a.fix_buf[1 + atomicAdd(a.fix_buf, 1)] = (int)(base + tid);
+        }
         __syncthreads();
         for (int o = tid; o < CT_P * K; o += NT) {
             const int p = o / K, k = o % K;
@@ -434,7 +446,7 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
                 }
             }
             fft16<true>(v);
-            if (p < nvalid) {
+            if (p < nvalid && !(a.mode != QCE_MODE_ALL && tief[p])) {
                 const size_t o = (size_t)(base + p) * CT_N + b;
                 if (a.h_est) {
                     #pragma unroll
@@ -460,7 +472,11 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
             }
             if (lane == 0) { atomicAdd(&red[0], err); atomicAdd(&red[1], pw); }
             __syncthreads();
-            if (tid == 0) { atomicAdd(a.acc + 0, red[0]); atomicAdd(a.acc + 1, red[1]); atomicAdd(a.acc + 2, (double)nvalid); }
+            if (tid == 0) {
+                int cnt = nvalid;
+                if (a.mode != QCE_MODE_ALL) for (int p = 0; p < nvalid; ++p) cnt -= tief[p];
+                atomicAdd(a.acc + 0, red[0]); atomicAdd(a.acc + 1, red[1]); atomicAdd(a.acc + 2, (double)cnt);
+            }
         }
     }
 }
@@ -595,14 +611,30 @@ qce_status circ_tc_pack(qce_circ_model* m, cudaStream_t s) {
     return QCE_OK;
 }
 
+// fix list of a launch: one buffer per (device, stream), grown on demand; the count is reset in stream order
+static qce_status circ_fix_list(cudaStream_t s, int64_t rows, int** out) {
+    struct Buf { int* p = nullptr; size_t n = 0; };
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+    std::lock_guard<std::mutex> lock(mu);
+    Buf& b = bufs[std::make_pair(current_device(), s)];
+    if ((size_t)rows + 1 > b.n) {
+        if (b.p) QCE_CUDA_TRY(cudaFree(b.p));
+        b.p = nullptr; b.n = 0;
+        QCE_CUDA_TRY(cudaMalloc(&b.p, ((size_t)rows + 1) * sizeof(int)));
+        b.n = (size_t)rows + 1;
+    }
+    QCE_CUDA_TRY(cudaMemsetAsync(b.p, 0, sizeof(int), s));
+    note_fix_list(s, b.p);
+    *out = b.p;
+    return QCE_OK;
+}
+
 template <int KC, int NW>
 static qce_status launch_circ_tc_k(const CircTcArgs& a, cudaStream_t s) {
     constexpr size_t SMEM = CT_P * CT_XP * sizeof(float2) + CT_R_BYTES + 512;
-    static bool attr_set = false;
-    if (!attr_set) {
-        QCE_CUDA_TRY(cudaFuncSetAttribute(circ_tc_kernel<KC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_set = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first(current_device())) QCE_CUDA_TRY(cudaFuncSetAttribute(circ_tc_kernel<KC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     circ_tc_kernel<KC, NW><<<(unsigned)((a.B + CT_P - 1) / CT_P), 32 * NW, SMEM, s>>>(a);
     QCE_CHECK_LAUNCH("circ_tc_kernel");
     return QCE_OK;
@@ -627,9 +659,20 @@ qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double*
         const int pf_env = getenv("QCE_CIRC_PREFETCH") ? atoi(getenv("QCE_CIRC_PREFETCH")) : -1;
         a.prefetch_dist = pf_env >= 0 ? pf_env : sms;     // measured: 0 -> 396, sms/2 .. sms -> 412, 2 sms -> 354 M est/s at config 3
     }
+    // hard selections: pilots whose selection the FP32 log-likelihoods (~1.4e-5 nats rms, profiles/r02_flip_rate.json) cannot
+    // decide go on a fix list and are answered by the complex128 kernel.  QCE_TC_TIE_EPS overrides the gap (0: no re-evaluation).
+    a.fix_buf = nullptr;
+    a.tie_eps = getenv("QCE_TC_TIE_EPS") ? atof(getenv("QCE_TC_TIE_EPS")) : 5e-4;
+    if (mode != QCE_MODE_ALL) {
+        qce_status st = circ_fix_list(s, B, &a.fix_buf);
+        if (st) return st;
+    }
     const int nw = (getenv("QCE_CIRC_NW") && atoi(getenv("QCE_CIRC_NW")) == 16) ? 16 : 8;      // 16 warps x 64 registers measured 7 % slower
-    if (nw == 8) return m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 8>(a, s);
-    return m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 16>(a, s);
+    qce_status st;
+    if (nw == 8) st = m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 8>(a, s);
+    else st = m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 16>(a, s);
+    if (st || mode == QCE_MODE_ALL || !(h_est || acc)) return st;
+    return launch_circ_rows(m, s, r, a.fix_buf + 1, a.fix_buf, B, mode, n_top, rho, h_est, h_true, acc);
 }
 
 }  // namespace qce

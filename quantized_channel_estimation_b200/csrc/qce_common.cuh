@@ -11,6 +11,8 @@
 namespace qce {
 
 void set_error(const char* fmt, ...);
+void note_fix_list(cudaStream_t s, const int* fix_buf);      // qce_last_fix_count bookkeeping (qce_api.cu)
+const int* last_fix_list(cudaStream_t s);
 extern int64_t g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
@@ -33,6 +35,13 @@ inline void count_launch(int n = 1) { g_launch_count += n; }
         }                                                                                       \
         qce::count_launch();                                                                    \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: one flag per (kernel instantiation, device)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first(int dev) { if (dev < 0 || dev >= 64) return true; if (done[dev]) return false; done[dev] = true; return true; }
+};
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 
 struct QuantTables {            // device-resident quantiser tables
     int n_bits;
@@ -123,15 +132,67 @@ struct qce_model {
 
 #ifdef __CUDACC__
 namespace qce {
+// ---- the quantiser's scalar arithmetic (modules/utils.py:189-203), shared by quantize_kernel and the complex128 re-evaluation path
+// 1/np.sqrt(2) = 0x3FE6A09E667F3BCC (NOT sqrt(0.5) = ...BCD), SURVEY.md section 7 "bit-exact quantiser"
+__device__ __forceinline__ double inv_sqrt2() { return __longlong_as_double(0x3FE6A09E667F3BCCLL); }
+
+__device__ __forceinline__ double sign_np(double x) {   // np.sign: -1, 0, +1, NaN
+    return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : ((x == 0.0) ? 0.0 : x));
+}
+
+__device__ __forceinline__ int digitize(double x, const double* __restrict__ thr, int n_thr) {
+    // np.digitize(x, thr) with right=False on ascending thr: #{thr <= x}; NaN sorts last.
+    if (x != x) return n_thr;
+    int lo = 0, hi = n_thr;                // first index with thr[idx] > x
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (thr[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// r = Q(y) for one complex sample (tables anywhere the pointer reaches: shared or global memory)
+__device__ __forceinline__ double2 quantize_value(int n_bits, int n_thr, const double* __restrict__ thr, const double* __restrict__ lab,
+                                                  const double2 y, uchar2* code_out) {
+    double2 r;
+    uchar2 code;
+    if (n_bits == 1) {
+        const double sr = sign_np(y.x), si = sign_np(y.y);
+        code.x = (sr != sr) ? 3 : (unsigned char)((int)sr + 1);
+        code.y = (si != si) ? 3 : (unsigned char)((int)si + 1);
+        if (sr != sr || si != si) {        // numpy's complex product spreads a NaN to both parts
+            r.x = r.y = __longlong_as_double(0x7FF8000000000000LL);
+        } else {
+            r.x = __dmul_rn(inv_sqrt2(), sr) + 0.0;  // + 0.0: -0 -> +0 like numpy's (c*a - 0*b)
+            r.y = __dmul_rn(inv_sqrt2(), si) + 0.0;
+        }
+    } else {
+        const int ir = digitize(y.x, thr, n_thr), ii = digitize(y.y, thr, n_thr);
+        code.x = (unsigned char)ir;
+        code.y = (unsigned char)ii;
+        r.x = lab[ir];
+        r.y = lab[ii];
+    }
+    if (code_out) *code_out = code;
+    return r;
+}
+
 // Per-sample weights from weighted log-probabilities, in place (lp[k] -> w[k]); T = double, or float for the FP32 kernels.
+// tie != null (FP32 kernels): *tie is set when the hard selection is too close to call with log-likelihoods that carry an error of
+// up to ~tie_eps nats -- the deciding gap (maximum vs runner-up, last selected vs first left out) or a prefix sum vs rho -- so that
+// the caller can hand the pilot to the complex128 kernel.
 template <typename T>
-__device__ inline void weights_from_logp(T* lp, int K, int mode, int n_top, double rho, int flags) {
-    double mx = lp[0];
+__device__ inline void weights_from_logp(T* lp, int K, int mode, int n_top, double rho, int flags, bool* tie = nullptr, double tie_eps = 0.0) {
+    double mx = lp[0], mx2 = -INFINITY;
     int amax = 0;
-    for (int k = 1; k < K; ++k)
-        if (lp[k] > mx) { mx = lp[k]; amax = k; }
+    bool close = false;
+    for (int k = 1; k < K; ++k) {
+        if (lp[k] > mx) { mx2 = mx; mx = lp[k]; amax = k; }
+        else if ((double)lp[k] > mx2) mx2 = lp[k];
+    }
     if (mode == QCE_MODE_TOP1) {
         // gmm:349 argmax of the weighted log-prob; mofa:359-366 argmax of exp(.) -> 0 when all underflow
+        if (tie) *tie = !(mx - mx2 > tie_eps) || ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabs(mx + 745.1332) < 0.01);
         if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
         for (int k = 0; k < K; ++k) lp[k] = (k == amax) ? (T)1.0 : (T)0.0;
         return;
@@ -140,21 +201,33 @@ __device__ inline void weights_from_logp(T* lp, int K, int mode, int n_top, doub
     for (int k = 0; k < K; ++k) sum += exp((double)lp[k] - mx);
     const double lse = mx + log(sum);               // scipy.special.logsumexp (gmm:652) / _log_sum (mofa:394-400)
     for (int k = 0; k < K; ++k) lp[k] = (T)exp((double)lp[k] - lse);
+    if (tie) *tie = !(mx == mx);
     if (mode == QCE_MODE_ALL) return;
     // descending selection (np.argsort(p)[::-1], gmm:210 / :233); selected entries are marked by the sign bit
     const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
-    double cum = 0.0;
-    for (int it = 0; it < limit; ++it) {
+    double cum = 0.0, last = -1.0;
+    bool done = false;
+    for (int it = 0; it <= limit; ++it) {
         int best = -1;
         double bv = -1.0;
         for (int k = 0; k < K; ++k)
             if (!signbit(lp[k]) && (double)lp[k] > bv) { bv = (double)lp[k]; best = k; }
         if (best < 0) break;
+        if (done || it == limit) {                  // first candidate left out: a near-tie with the last selected one could swap them
+            if (bv > last * (1.0 - tie_eps)) close = true;
+            break;
+        }
         lp[best] = (T)(-bv);
         cum += bv;
+        last = bv;
         // searchsorted(cumsum, rho) + 1 (gmm:234): stop after the first prefix with cumsum >= rho
-        if (mode == QCE_MODE_CUMPROB && cum >= rho) break;
+        if (mode == QCE_MODE_CUMPROB) {
+            if (fabs(cum - rho) < tie_eps) close = true;
+            if (cum >= rho) { if (!tie) break; done = true; }
+        }
+        if (!tie && it + 1 == limit) break;
     }
+    if (tie && close) *tie = true;
     for (int k = 0; k < K; ++k) lp[k] = signbit(lp[k]) ? (T)((double)(-lp[k]) / cum) : (T)0.0;
 }
 
@@ -174,6 +247,20 @@ qce_status launch_dense_fp64(const qce_model* m, cudaStream_t s, const double* r
 qce_status launch_dense_fp64_raw(const qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top,
                                  double rho, double* h_est, double* logp_out, const void* h_true, int h_true_c64,
                                  double* acc);
+// complex128 re-evaluation of a device-side list of rows (rows[0 .. *n_rows_dev)) of a batch: the pilots are read from r, or
+// (r == null) observed + quantised on the fly from (obs_h, obs_noise) exactly like quantize_kernel; results are written to the
+// listed rows of h_est / logp_out and added to acc
+struct RowSource {
+    const double* r = nullptr;          // c128 [B][n_obs] quantised pilots, or null
+    const void* obs_h = nullptr;        // c64 / c128 [B][n_obs] channels (A = I)
+    const double* obs_noise = nullptr;  // c128 [B][n_obs]
+    double obs_noise_scale = 0.0;
+    int obs_h_c64 = 0;
+    QuantTables qt{};
+};
+qce_status launch_dense_fp64_rows(const qce_model* m, cudaStream_t s, const RowSource& src, const int* rows, const int* n_rows_dev,
+                                  int64_t max_rows, int mode, int n_top, double rho, double* h_est, double* logp_out,
+                                  const void* h_true, int h_true_c64, double* acc);
 // qce_dense_tc.cu
 qce_status tc_pack_params(qce_model* m, cudaStream_t s);
 void tc_free(qce_model* m);
@@ -199,4 +286,6 @@ qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double*
 // qce_circ.cu
 qce_status launch_circ(const qce_circ_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
                        double* h_est, double* logp_out, const double* h_true, double* acc);
+qce_status launch_circ_rows(const qce_circ_model* m, cudaStream_t s, const double* r, const int* rows, const int* n_rows_dev, int64_t max_rows,
+                            int mode, int n_top, double rho, double* h_est, const double* h_true, double* acc);
 }  // namespace qce

@@ -29,6 +29,15 @@ struct Fp64Args {
     double* acc;
     int mode, n_top, flags;
     double rho;
+    // re-evaluation of listed rows (null: the rows are 0 .. B-1 in order): tile entry i is row rows[i], i < *n_rows_dev
+    const int* rows;
+    const int* n_rows_dev;
+    // r == null: the pilots are observed + quantised on the fly (A = I), bit-exact to quantize_kernel
+    const void* obs_h;
+    const double2* obs_noise;
+    double obs_noise_scale;
+    int obs_h_c64;
+    QuantTables qt;
 };
 
 __device__ __forceinline__ void cfma(double2& acc, const double2 a, const double2 b) {
@@ -48,22 +57,38 @@ __global__ void __launch_bounds__(256) dense_fp64_kernel(Fp64Args a) {
     double* lp = reinterpret_cast<double*>(rT + (size_t)a.No * TS);           // [TS][K]
     double* part = lp + (size_t)TS * a.K;                                      // [8][TS]
     __shared__ double red[3];
+    __shared__ int64_t s_row[TS];       // batch row of every tile entry
 
     const int t = threadIdx.x;
     const int sp = t % SP, rg = t / SP;
     const int warp = t >> 5;
     const int No = a.No, N = a.N, K = a.K;
-    const int64_t base = (int64_t)blockIdx.x * TS;
-    const int nvalid = (int)((a.B - base) < TS ? (a.B - base) : TS);
+    const int64_t n_rows = a.n_rows_dev ? (int64_t)__ldg(a.n_rows_dev) : a.B;
+    for (int64_t base = (int64_t)blockIdx.x * TS; base < n_rows; base += (int64_t)gridDim.x * TS) {
+    const int nvalid = (int)((n_rows - base) < TS ? (n_rows - base) : TS);
+    if (t < TS) s_row[t] = (t < nvalid) ? (a.rows ? (int64_t)a.rows[base + t] : base + t) : 0;
+    if (t < 3) red[t] = 0.0;
+    __syncthreads();
 
     // stage the tile transposed: rT[j][s]
     for (int idx = t; idx < TS * No; idx += 256) {
         int s = idx / No, j = idx % No;
         double2 v = make_double2(0.0, 0.0);
-        if (s < nvalid) v = a.r[(base + s) * No + j];
+        if (s < nvalid) {
+            const int64_t e = s_row[s] * No + j;
+            if (a.r) {
+                v = a.r[e];
+            } else {      // get_observation_nbit with A = I (utils.py:241-251): two roundings, then the quantiser
+                double2 h;
+                if (a.obs_h_c64) { const float2 hf = reinterpret_cast<const float2*>(a.obs_h)[e]; h = make_double2((double)hf.x, (double)hf.y); }
+                else h = reinterpret_cast<const double2*>(a.obs_h)[e];
+                const double2 w = a.obs_noise[e];
+                const double2 y = make_double2(__dadd_rn(h.x, __dmul_rn(a.obs_noise_scale, w.x)), __dadd_rn(h.y, __dmul_rn(a.obs_noise_scale, w.y)));
+                v = quantize_value(a.qt.n_bits, a.qt.n_thr, a.qt.thr, a.qt.labels, y, nullptr);
+            }
+        }
         rT[(size_t)j * TS + s] = v;
     }
-    if (t < 3) red[t] = 0.0;
     __syncthreads();
 
     // ---- phase 1: weighted log-probabilities
@@ -106,7 +131,7 @@ __global__ void __launch_bounds__(256) dense_fp64_kernel(Fp64Args a) {
 
     // ---- phase 1.5: per-sample weights
     if (a.logp_out) {
-        for (int idx = t; idx < nvalid * K; idx += 256) a.logp_out[base * K + idx] = lp[idx];
+        for (int idx = t; idx < nvalid * K; idx += 256) a.logp_out[s_row[idx / K] * K + (idx % K)] = lp[idx];
         __syncthreads();
     }
     if (t < TS) weights_from_logp(lp + (size_t)t * K, K, a.mode, a.n_top, a.rho, a.flags);
@@ -149,7 +174,7 @@ __global__ void __launch_bounds__(256) dense_fp64_kernel(Fp64Args a) {
                     const int s = 2 * sp + u;
                     if (s >= nvalid) continue;
                     const double2 v = u ? acc1[m] : acc0[m];
-                    const int64_t o = (base + s) * N + i;
+                    const int64_t o = s_row[s] * N + i;
                     if (a.h_est) a.h_est[o] = v;
                     if (a.acc && a.h_true) {
                         double2 h;
@@ -181,16 +206,17 @@ __global__ void __launch_bounds__(256) dense_fp64_kernel(Fp64Args a) {
             atomicAdd(a.acc + 2, (double)nvalid);
         }
     }
+    __syncthreads();      // red[], s_row[], the tile and lp are rewritten by the next tile of this CTA
+    }
 }
 
 template <int TS>
-static qce_status launch_ts(const Fp64Args& a, cudaStream_t s, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
+static qce_status launch_ts(const Fp64Args& a, cudaStream_t s, size_t smem, int64_t grid_cap = 0) {
+    static PerDeviceOnce once;
+    if (once.first(current_device()))
         QCE_CUDA_TRY(cudaFuncSetAttribute(dense_fp64_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
     int64_t grid = (a.B + TS - 1) / TS;
+    if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
     dense_fp64_kernel<TS><<<(unsigned)grid, 256, smem, s>>>(a);
     QCE_CHECK_LAUNCH("dense_fp64_kernel");
     return QCE_OK;
@@ -207,6 +233,7 @@ qce_status launch_dense_fp64_raw(const qce_model* m, cudaStream_t s, const doubl
     a.r = (const double2*)r; a.h_est = (double2*)h_est; a.logp_out = logp_out;
     a.h_true = h_true; a.h_true_c64 = h_true_c64; a.acc = acc;
     a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;
+    a.rows = nullptr; a.n_rows_dev = nullptr; a.obs_h = nullptr; a.obs_noise = nullptr; a.obs_noise_scale = 0.0; a.obs_h_c64 = 0; a.qt = QuantTables{};
     auto need = [&](int ts) {
         return (size_t)a.No * ts * sizeof(double2) + (size_t)ts * a.K * sizeof(double) + (size_t)8 * ts * sizeof(double);
     };
@@ -217,6 +244,29 @@ qce_status launch_dense_fp64_raw(const qce_model* m, cudaStream_t s, const doubl
     if (need(8) <= cap) return launch_ts<8>(a, s, need(8));
     set_error("fp64 kernel: n_obs=%d, K=%d do not fit shared memory", a.No, a.K);
     return QCE_ERR_UNSUPPORTED;
+}
+
+// The listed rows are few (near-ties of a hard selection, pilots off the tensor-core grid): small tiles for parallelism, and a grid
+// that does not depend on the (device-side) length of the list -- CTAs without a tile exit at once, long lists are walked grid-stride.
+qce_status launch_dense_fp64_rows(const qce_model* m, cudaStream_t s, const RowSource& src, const int* rows, const int* n_rows_dev,
+                                  int64_t max_rows, int mode, int n_top, double rho, double* h_est, double* logp_out,
+                                  const void* h_true, int h_true_c64, double* acc) {
+    if (max_rows == 0) return QCE_OK;
+    Fp64Args a;
+    a.No = m->n_obs; a.N = m->n_ant; a.K = m->n_comp; a.B = max_rows;
+    a.Linv = (const double2*)m->Linv; a.W = (const double2*)m->W;
+    a.zoff = (const double2*)m->zoff; a.hoff = (const double2*)m->hoff; a.logc = m->logc;
+    a.r = (const double2*)src.r; a.h_est = (double2*)h_est; a.logp_out = logp_out;
+    a.h_true = h_true; a.h_true_c64 = h_true_c64; a.acc = acc;
+    a.mode = mode; a.n_top = n_top; a.flags = m->flags; a.rho = rho;
+    a.rows = rows; a.n_rows_dev = n_rows_dev;
+    a.obs_h = src.obs_h; a.obs_noise = (const double2*)src.obs_noise; a.obs_noise_scale = src.obs_noise_scale; a.obs_h_c64 = src.obs_h_c64; a.qt = src.qt;
+    if (!a.r && !(a.obs_h && a.obs_noise)) { set_error("re-evaluation of flagged rows: the source pilots are not available"); return QCE_ERR_INVALID; }
+    const size_t need = (size_t)a.No * 8 * sizeof(double2) + (size_t)8 * a.K * sizeof(double) + (size_t)8 * 8 * sizeof(double);
+    if (need > (size_t)220 * 1024) { set_error("fp64 kernel: n_obs=%d, K=%d do not fit shared memory", a.No, a.K); return QCE_ERR_UNSUPPORTED; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+    return launch_ts<8>(a, s, need, 2 * (int64_t)sms);
 }
 
 qce_status launch_dense_fp64(const qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top,

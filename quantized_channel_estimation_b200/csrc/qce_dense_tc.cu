@@ -195,7 +195,8 @@ __device__ __forceinline__ void fmt_store(const TcArgs& a, int64_t first_tile, i
     }
     if (!(qr == qr && qi == qi)) {     // NaN data: flag the row (its estimate becomes NaN)
         const int64_t fr = tile * TILE_M + mb * 8 + (lane & 7);      // (the flag buffer is padded to whole units)
-        atomicOr(reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(a.bad)) + (fr >> 2), 1u << (8 * (int)(fr & 3)));
+        const unsigned old = atomicOr(reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(a.bad)) + (fr >> 2), 1u << (8 * (int)(fr & 3)));
+        if (((old >> (8 * (int)(fr & 3))) & 0xffu) == 0u && fr < a.B) a.fix_idx[atomicAdd(a.fix_cnt, 1)] = (int)fr;      // first flag of this row
         qr = qi = 0.f;
     }
     unsigned char* tile_img = reinterpret_cast<unsigned char*>(const_cast<__half*>(a.a_img)) + (size_t)tile * TILE_M * KD * 2;
@@ -466,7 +467,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             float mref_hi = 0.f, mref_lo = 0.f;
             float ssum = 0.f;
             float best_hi = -INFINITY, best_lo = 0.f;  // EPI=1 label mode: running maximum of l_k as an FP32 pair
-            int best_k = 0;
+            float second = -INFINITY;                  // ... and the runner-up (rounded): the selection is re-evaluated in complex128
+            int best_k = 0;                            // when the two are closer than the FP32 log-likelihoods can tell apart
 
             // the pilot this thread handles, and the components of this unit
             int64_t src = tile_base + row;
@@ -564,7 +566,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         // ties, NaN, infinities, the first component: rare, and behind a warp-uniform branch and a call so that the
                         // compiler cannot turn the FP64 comparison into unconditional arithmetic + select
                         if (__any_sync(0xffffffffu, !safe)) { if (!safe) better = pair_greater_f64(l_hi, l_lo, best_hi, best_lo); }
-                        if (better) { best_hi = l_hi; best_lo = l_lo; best_k = k; }
+                        if (better) { second = best_hi + best_lo; best_hi = l_hi; best_lo = l_lo; best_k = k; }
+                        else second = fmaxf(second, l_hi + l_lo);
                     } else if (tile_base + row < a.B) a.lp_out[(tile_base + row) * a.K + k] = make_float2(l_hi, l_lo);
                     p = 0.f;
                 } else {
@@ -634,11 +637,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             if (EPI == 1 && a.top_out && valid) {
                 if ((a.top_flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp((double)best_hi + (double)best_lo) == 0.0) best_k = 0;
                 a.top_out[g] = best_k;
+                // too close to call (or NaN), or on the edge of the exp() underflow the MFA argmax quirk tests: complex128 decides
+                const float gap = (best_hi - second) + best_lo;
+                bool tie = !(gap > a.tie_eps);
+                if ((a.top_flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabsf(best_hi + 745.1332f) < 0.01f) tie = true;
+                if (tie) fix_append(const_cast<unsigned char*>(a.bad), a.fix_cnt, a.fix_idx, g, a.row0 + g, 2);
             }
-            if (EPI != 1 && valid) {
-                // (read here, after the last component: with the fused prologue the flags are written by other warps of this kernel)
-                const bool row_bad = (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) != 0;
-                const float invs = row_bad ? __int_as_float(0x7fc00000) : (EPI == 2 ? 1.f : 1.f / ssum);
+            // (flags read here, after the last component: with the fused prologue they are written by other warps of this kernel)
+            if (EPI != 1 && valid && (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) == 0) {
+                const float invs = EPI == 2 ? 1.f : 1.f / ssum;
                 if (a.h_est) {
                     double2* out = a.h_est + g * N + (a.h_col0 >> 1);
                     #pragma unroll
@@ -803,7 +810,7 @@ __global__ void tc_pack_small_kernel(const double2* __restrict__ zoff, const dou
 template <bool OBSERVE, bool H_C64, bool SPLIT>
 __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__ src, const double2* __restrict__ noise, double noise_scale,
                                                         QuantTables qt, int64_t B, int No, double inv_data_scale,
-                                                        __half* __restrict__ img, unsigned char* __restrict__ bad) {
+                                                        __half* __restrict__ img, unsigned char* __restrict__ bad, int* __restrict__ fix_buf) {
     extern __shared__ __align__(16) unsigned char s_dyn[];   // [copies][kbs][8 rows][16 B] core matrices of this block, then thr / labels (f64)
     __shared__ int s_bad[8];
     const int KD = 2 * No, kbs = KD / 8;
@@ -871,7 +878,7 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
             } else {
                 const float mr = (float)v[u].x, mi = (float)v[u].y;
                 const float qr = rintf(mr), qi = rintf(mi);
-                // off-grid / out-of-range / NaN data cannot be represented exactly: flag the row (its estimate becomes NaN)
+                // off-grid / out-of-range / NaN data cannot be represented exactly: flag the row (re-evaluated by the complex128 kernel)
                 if (!(fabsf(mr - qr) <= 1e-4f * fmaxf(1.f, fabsf(qr)) && fabsf(mi - qi) <= 1e-4f * fmaxf(1.f, fabsf(qi)) &&
                       fabsf(qr) <= 2048.f && fabsf(qi) <= 2048.f))
                     my_bad = 1;
@@ -888,7 +895,11 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
         *reinterpret_cast<uint32_t*>(tile_img + (size_t)copy * TILE_M * KD * 2 + (size_t)(kb * (TILE_M / 8) + mb) * 128 + lane * 4) =
             *reinterpret_cast<const uint32_t*>(s_img + c * 128 + lane * 4);
     }
-    if (threadIdx.x < 8) bad[tile * TILE_M + mb * 8 + threadIdx.x] = (unsigned char)s_bad[threadIdx.x];
+    if (threadIdx.x < 8) {      // rows that cannot be represented go on the fix list (complex128 re-evaluation after the tensor-core launches)
+        const int64_t row = tile * TILE_M + mb * 8 + threadIdx.x;
+        bad[row] = (unsigned char)s_bad[threadIdx.x];
+        if (s_bad[threadIdx.x] && row < B) fix_buf[1 + atomicAdd(fix_buf, 1)] = (int)row;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ mode selection
@@ -899,14 +910,16 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
 template <int PER>      // entries per lane: K <= 32 PER
 __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho,
                                                         int flags, float* __restrict__ w_out, double* __restrict__ logp_out,
-                                                        int* __restrict__ top_out) {
+                                                        int* __restrict__ top_out, unsigned char* __restrict__ bad, int* __restrict__ fix_buf,
+                                                        int64_t row0, double tie_eps) {
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
     double l[PER];
     const int per = (K + 31) / 32;
-    double mx = -INFINITY;
+    double mx = -INFINITY, mx2 = -INFINITY;      // maximum and runner-up (a second entry equal to the maximum counts as runner-up)
     int amax = 0;
+    bool tie = false;                            // selection too close to call in these FP32-derived log-likelihoods -> complex128 decides
     #pragma unroll
     for (int i = 0; i < PER; ++i) {
         l[i] = -INFINITY;
@@ -916,19 +929,26 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
                 const float2 v = lp2[b * K + k];
                 l[i] = (double)v.x + (double)v.y;
                 if (logp_out) logp_out[b * K + k] = l[i];
-                if (l[i] > mx) { mx = l[i]; amax = k; }
+                if (l[i] != l[i]) tie = true;                     // NaN: let the complex128 kernel reproduce numpy's answer
+                if (l[i] > mx) { mx2 = mx; mx = l[i]; amax = k; } else if (l[i] > mx2) mx2 = l[i];
             }
         }
     }
     // warp argmax (first index among equal maxima, like np.argmax)
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        const double om = __shfl_xor_sync(0xffffffffu, mx, off);
+        const double om = __shfl_xor_sync(0xffffffffu, mx, off), om2 = __shfl_xor_sync(0xffffffffu, mx2, off);
         const int oa = __shfl_xor_sync(0xffffffffu, amax, off);
+        mx2 = fmax(fmax(mx2, om2), fmin(mx, om));
         if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
     }
+    tie = __any_sync(0xffffffffu, tie);
     if (!w_out && !top_out) return;
+    // `bad` / the fix list: a row that is already flagged (pilots off the grid) stays as it is
+    auto flag_row = [&]() { if (lane == 0) fix_append(bad, fix_buf, fix_buf + 1, b, row0 + b, 2); };
     if (mode == QCE_MODE_TOP1) {
+        if (!(mx - mx2 > tie_eps) || ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabs(mx + 745.1332) < 0.01)) tie = true;
+        if (tie) flag_row();
         if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
         if (top_out) {      // bucketed combination: the label instead of a one-hot weight row
             if (lane == 0) top_out[b] = amax;
@@ -955,6 +975,7 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
     #pragma unroll
     for (int i = 0; i < PER; ++i) if (l[i] >= 0.0) l[i] *= inv_sum;
     if (mode == QCE_MODE_ALL) {
+        if (tie) flag_row();
         #pragma unroll
         for (int i = 0; i < PER; ++i)
             if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = (float)l[i]; }
@@ -963,8 +984,9 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
     // descending selection; selected entries are flagged by a set bit in `sel`
     const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
     unsigned sel = 0;
-    double cum = 0.0;
-    for (int it = 0; it < limit; ++it) {
+    double cum = 0.0, last = -1.0;
+    bool done = false;                 // selection complete: one more pass looks at the best candidate left out
+    for (int it = 0; it <= limit; ++it) {
         double bv = -1.0;
         int bk = 0x7fffffff;
         #pragma unroll
@@ -976,11 +998,20 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
             const int ok = __shfl_xor_sync(0xffffffffu, bk, off);
             if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
         }
-        if (bv < 0.0) break;
+        if (bv < 0.0) break;           // no candidates left
+        if (done || it == limit) {     // a near-tie between the last selected and the first left out could swap them
+            if (bv > last * (1.0 - tie_eps)) tie = true;
+            break;
+        }
         if ((bk & 31) == lane) sel |= 1u << (bk >> 5);
         cum += bv;
-        if (mode == QCE_MODE_CUMPROB && cum >= rho) break;      // searchsorted(cumsum, rho) + 1 entries (gmm:234)
+        last = bv;
+        if (mode == QCE_MODE_CUMPROB) {
+            if (fabs(cum - rho) < tie_eps) tie = true;      // a prefix sum this close to rho: which side it falls on is not decidable here
+            if (cum >= rho) done = true;                    // searchsorted(cumsum, rho) + 1 entries (gmm:234)
+        }
     }
+    if (tie) flag_row();
     #pragma unroll
     for (int i = 0; i < PER; ++i)
         if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = ((sel >> i) & 1u) ? (float)(l[i] / cum) : 0.f; }
@@ -1053,12 +1084,13 @@ __global__ void __launch_bounds__(256) tc_bucket_gather_kernel(const unsigned ch
     }
 }
 
+// keyed by (device, stream): stream handles are only unique per device (the default stream is 0 everywhere)
 static std::mutex g_scratch_mu;
-static std::map<cudaStream_t, TileScratch> g_scratch;
+static std::map<std::pair<int, cudaStream_t>, TileScratch> g_scratch;
 
 static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, TileScratch** out) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
-    TileScratch& t = g_scratch[s];
+    TileScratch& t = g_scratch[std::make_pair(current_device(), s)];
     const size_t tiles = (size_t)((rows + TILE_M - 1) / TILE_M + 4);   // the last work unit (up to 4 tiles) may reach past the end
     const size_t need_img = tiles * TILE_M * 2 * (size_t)m->n_obs * sizeof(__half) * (m->tc.split_a ? 2 : 1), need_bad = tiles * TILE_M;
     if (need_img > t.img_bytes) {
@@ -1075,8 +1107,26 @@ static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, T
         QCE_CUDA_TRY(cudaMemset(t.bad, 0, need_bad));
         t.bad_bytes = need_bad;
     }
+    const size_t need_fix = (need_bad + 1) * sizeof(int);
+    if (need_fix > t.fix_bytes) {
+        if (t.fix_buf) QCE_CUDA_TRY(cudaFree(t.fix_buf));
+        t.fix_buf = nullptr; t.fix_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t.fix_buf, need_fix));
+        t.fix_bytes = need_fix;
+    }
+    QCE_CUDA_TRY(cudaMemsetAsync(t.fix_buf, 0, sizeof(int), s));      // a new batch is about to be formatted: empty fix list
+    note_fix_list(s, t.fix_buf);
     *out = &t;
     return QCE_OK;
+}
+
+// complex128 re-evaluation of the rows on the fix list (pilots off the tensor-core grid, hard selections too close to call): they
+// were neither written nor accumulated by the tensor-core launches.  The list is short (typically 1e-4 of the batch), its length
+// lives on the device: the launch is sized independently of it.
+static qce_status tc_fix_rows(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int mode, int n_top, double rho,
+                              double* h_est, double* logp_out, const void* h_true, int h_true_c64, double* acc) {
+    if (!h_est && !logp_out && !acc) return QCE_OK;
+    return launch_dense_fp64_rows(m, s, ts->src, ts->fix_buf + 1, ts->fix_buf, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
 }
 
 static qce_status tc_scratch_aux(TileScratch* t, size_t rows, size_t K) {
@@ -1220,14 +1270,11 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
 template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC = 1, bool PRO = false>
 static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
     using Cfg = TcCfg<32 * KDC, 32 * NCHZ, 32 * NCHH, CG, ORDER, AC>;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     auto kern = dense_tc_kernel<KDC, NCHZ, NCHH, OFFS, CG, EPI, ORDER, AC, PRO>;
-    if (!attr_set) {
-        QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
+    const int dev = current_device();
+    if (once.first(dev)) QCE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_units = (a.B + CG * Cfg::NTILES * TILE_M - 1) / (CG * Cfg::NTILES * TILE_M);
     const int64_t max_clusters = sms / CG;
@@ -1276,6 +1323,15 @@ static qce_status launch_split(const TcArgs& a, bool offs, int epi, bool split_a
     }
 }
 
+// Log-likelihood gap (nats) below which a hard selection is handed to the complex128 kernel.  The FP16-split / FP32-accumulate
+// log-likelihoods are within ~1e-5 nats of the complex128 ones at n_obs = 64 (profiles/r02_flip_rate.json: the error grows with
+// the number of accumulated squares); the margin is >= 10x.  QCE_TC_TIE_EPS overrides (0 disables the re-evaluation: A/B runs).
+static double tc_tie_eps(const qce_model* m) {
+    if (const char* e = getenv("QCE_TC_TIE_EPS")) return atof(e);
+    const double scale = m->n_obs > 64 ? (double)m->n_obs / 64.0 : 1.0;
+    return 2e-4 * scale * (m->tc.split_a ? 2.0 : 1.0);
+}
+
 static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc,
                          TcArgs* out) {
     const TcParams& p = m->tc;
@@ -1292,14 +1348,17 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     a.skip_thresh = th ? (float)atof(th) : 1e-30f;
     a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr;
     a.top_out = nullptr; a.top_flags = m->flags;
+    a.fix_cnt = ts->fix_buf; a.fix_idx = ts->fix_buf + 1; a.row0 = 0;
+    a.tie_eps = (float)tc_tie_eps(m);
 }
 
 static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,
                                const void* h_true, int h_true_c64, double* acc, const int* unit_comp = nullptr, const int* perm = nullptr,
-                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr) {
+                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr, int64_t row0 = 0) {
     const TcParams& p = m->tc;
     TcArgs a;
     tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
+    a.row0 = row0;
     if (unit_comp) { a.unit_comp = unit_comp; a.perm = perm; a.n_units_dev = n_units_dev; a.a_img = (const __half*)bucket_img; }
     a.top_out = top_out;
     a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
@@ -1354,12 +1413,14 @@ static qce_status tc_format_into(qce_model* m, cudaStream_t s, const double* r, 
     QuantTables none{};
     if (m->tc.split_a)
         tc_format_kernel<false, false, true><<<(unsigned)(tiles * (TILE_M / 8)), 256, 2 * (size_t)(2 * m->n_obs / 8) * 128, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
-                                                                                            (__half*)ts->img, (unsigned char*)ts->bad);
+                                                                                            (__half*)ts->img, (unsigned char*)ts->bad, ts->fix_buf);
     else
         tc_format_kernel<false, false, false><<<(unsigned)(tiles * (TILE_M / 8)), 256, (size_t)(2 * m->n_obs / 8) * 128, s>>>(r, nullptr, 0.0, none, B, m->n_obs, 1.0 / m->tc.eff_scale,
-                                                                                             (__half*)ts->img, (unsigned char*)ts->bad);
+                                                                                             (__half*)ts->img, (unsigned char*)ts->bad, ts->fix_buf);
     QCE_CHECK_LAUNCH("tc_format_kernel");
     ts->owner = m; ts->rows = B;
+    ts->src = RowSource();
+    ts->src.r = r;
     *out = ts;
     return QCE_OK;
 }
@@ -1409,7 +1470,7 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         const void* ht = h_true ? (const void*)((const char*)h_true + (size_t)b0 * true_row) : nullptr;
         // top-1 without log-probability export: the whitening launch keeps the running argmax itself (no [rows][K] export, no selection launch)
         const bool label_in_kernel = bucketed && !logp_out;
-        st = tc_run_split(m, &v, s, nb, 1, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, label_in_kernel ? b_top : nullptr);
+        st = tc_run_split(m, &v, s, nb, 1, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, label_in_kernel ? b_top : nullptr, b0);
         if (st) return st;
         if (bucketed) {
             QCE_CUDA_TRY(cudaMemsetAsync(b_cnt, 0, m->n_comp * sizeof(int), s));
@@ -1418,9 +1479,11 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         if (!label_in_kernel) {
             const unsigned grid = (unsigned)((nb + 7) / 8);
             float* wts = (want_est && !bucketed) ? (float*)v.wts : nullptr;
-            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
-            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
-            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top);
+            unsigned char* vb = (unsigned char*)v.bad;
+            const double eps = tc_tie_eps(m);
+            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->fix_buf, b0, eps);
+            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->fix_buf, b0, eps);
+            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->fix_buf, b0, eps);
         }
         QCE_CHECK_LAUNCH("tc_select_kernel");
         if (!want_est) continue;
@@ -1449,7 +1512,7 @@ qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double
     TileScratch* ts = nullptr;
     {
         std::lock_guard<std::mutex> lock(g_scratch_mu);
-        auto it = g_scratch.find(s);
+        auto it = g_scratch.find(std::make_pair(current_device(), s));
         if (it != g_scratch.end()) ts = &it->second;
     }
     if (!ts || ts->owner != m || B > ts->rows) {
@@ -1457,8 +1520,10 @@ qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double
         return QCE_ERR_INVALID;
     }
     if (B == 0) return QCE_OK;
-    if (m->tc.split) return tc_run_modes(m, ts, s, B, QCE_MODE_ALL, 0, 0.0, h_est, nullptr, h_true, h_true_c64, acc);
-    return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
+    qce_status st = m->tc.split ? tc_run_modes(m, ts, s, B, QCE_MODE_ALL, 0, 0.0, h_est, nullptr, h_true, h_true_c64, acc)
+                                : tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
+    if (st) return st;
+    return tc_fix_rows(m, ts, s, B, QCE_MODE_ALL, 0, 0.0, h_est, nullptr, h_true, h_true_c64, acc);
 }
 
 // pilots given as complex128 values (estimate_from_y): format, then estimate
@@ -1468,8 +1533,10 @@ qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_
     TileScratch* ts = nullptr;
     qce_status st = tc_format_into(m, s, r, B, &ts);
     if (st) return st;
-    if (mode == QCE_MODE_ALL && !logp_out && !m->tc.split) return tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
-    return tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
+    if (mode == QCE_MODE_ALL && !logp_out && !m->tc.split) st = tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
+    else st = tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
+    if (st) return st;
+    return tc_fix_rows(m, ts, s, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
 }
 
 // fused Monte-Carlo step: observe (A = I) -> quantise -> estimate -> NMSE accumulators; the quantised pilots never exist in HBM
@@ -1481,6 +1548,8 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
     TileScratch* ts = nullptr;
     qce_status st = tc_scratch(m, s, B, &ts);
     if (st) return st;
+    RowSource obs_src;          // where the complex128 re-evaluation of flagged rows finds the pilots: it observes + quantises them again
+    obs_src.obs_h = h; obs_src.obs_noise = noise; obs_src.obs_noise_scale = noise_scale; obs_src.obs_h_c64 = h_is_c64; obs_src.qt = *qt;
     // Fused prologue (QCE_TC_FUSE=1): ONE launch observes, quantises, formats and estimates (mode 'all', fused shapes, 1-bit pilots,
     // SM-pair variant, K a multiple of the items per warp): the epilogue warps build the NEXT work unit's tiles one core matrix per
     // component.  Bit-identical results, but no faster than the formatter launch + estimate launch pair (4.78 vs 4.79 ms per 2^20
@@ -1498,9 +1567,12 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
             a.obs_h = h; a.obs_noise = (const double2*)noise; a.obs_noise_scale = noise_scale; a.obs_noise_scale_f = (float)noise_scale; a.obs_inv_scale = 1.0 / m->tc.eff_scale;
             a.obs_h_c64 = h_is_c64; a.obs_bits = qt->n_bits; a.obs_n_thr = qt->n_thr; a.obs_thr = qt->thr; a.obs_labels = qt->labels;
             ts->owner = m; ts->rows = B;
+            ts->src = obs_src;
             const bool offs = m->tc.has_offsets;
-            if (cz == 4) return offs ? launch_cfg<4, 4, 4, true, 2, 0, 0, 1, true>(a, s) : launch_cfg<4, 4, 4, false, 2, 0, 0, 1, true>(a, s);
-            return offs ? launch_cfg<2, 2, 2, true, 2, 0, 0, 1, true>(a, s) : launch_cfg<2, 2, 2, false, 2, 0, 0, 1, true>(a, s);
+            if (cz == 4) st = offs ? launch_cfg<4, 4, 4, true, 2, 0, 0, 1, true>(a, s) : launch_cfg<4, 4, 4, false, 2, 0, 0, 1, true>(a, s);
+            else st = offs ? launch_cfg<2, 2, 2, true, 2, 0, 0, 1, true>(a, s) : launch_cfg<2, 2, 2, false, 2, 0, 0, 1, true>(a, s);
+            if (st) return st;
+            return tc_fix_rows(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);
         }
     }
     const int64_t tiles = (B + TILE_M - 1) / TILE_M;
@@ -1508,14 +1580,17 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
     const unsigned grid = (unsigned)(tiles * (TILE_M / 8));
     const double inv_scale = 1.0 / m->tc.eff_scale;
 #define QCE_FMT(C64, SPL) tc_format_kernel<true, C64, SPL><<<grid, 256, smem, s>>>(h, (const double2*)noise, noise_scale, *qt, B, m->n_obs, inv_scale, \
-                                                                                 (__half*)ts->img, (unsigned char*)ts->bad)
+                                                                                 (__half*)ts->img, (unsigned char*)ts->bad, ts->fix_buf)
     if (h_is_c64) { if (m->tc.split_a) QCE_FMT(true, true); else QCE_FMT(true, false); }
     else { if (m->tc.split_a) QCE_FMT(false, true); else QCE_FMT(false, false); }
 #undef QCE_FMT
     QCE_CHECK_LAUNCH("tc_format_kernel(observe)");
     ts->owner = m; ts->rows = B;
-    if (mode == QCE_MODE_ALL && !m->tc.split) return tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
-    return tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);
+    ts->src = obs_src;
+    if (mode == QCE_MODE_ALL && !m->tc.split) st = tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
+    else st = tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);
+    if (st) return st;
+    return tc_fix_rows(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);
 }
 
 }  // namespace qce

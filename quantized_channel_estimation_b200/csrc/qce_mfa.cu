@@ -177,11 +177,8 @@ __global__ void __launch_bounds__(256) mfa_kernel(MfaArgs a) {
 
 template <int TS>
 static qce_status launch_ts(const MfaArgs& a, cudaStream_t s, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        QCE_CUDA_TRY(cudaFuncSetAttribute(mfa_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first(current_device())) QCE_CUDA_TRY(cudaFuncSetAttribute(mfa_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     mfa_kernel<TS><<<(unsigned)((a.B + TS - 1) / TS), 256, smem, s>>>(a);
     QCE_CHECK_LAUNCH("mfa_kernel");
     return QCE_OK;

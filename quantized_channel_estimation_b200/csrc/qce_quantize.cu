@@ -7,24 +7,6 @@
 
 namespace qce {
 
-// 1/np.sqrt(2) = 0x3FE6A09E667F3BCC (NOT sqrt(0.5) = ...BCD), SURVEY.md section 7 "bit-exact quantiser"
-__device__ __forceinline__ double inv_sqrt2() { return __longlong_as_double(0x3FE6A09E667F3BCCLL); }
-
-__device__ __forceinline__ double sign_np(double x) {   // np.sign: -1, 0, +1, NaN
-    return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : ((x == 0.0) ? 0.0 : x));
-}
-
-__device__ __forceinline__ int digitize(double x, const double* __restrict__ thr, int n_thr) {
-    // np.digitize(x, thr) with right=False on ascending thr: #{thr <= x}; NaN sorts last.
-    if (x != x) return n_thr;
-    int lo = 0, hi = n_thr;                // first index with thr[idx] > x
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (thr[mid] <= x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
 template <bool OBSERVE, bool H_C64>
 __global__ void __launch_bounds__(256) quantize_kernel(QuantTables t, bool have_q, const void* __restrict__ src,
                                                        const double2* __restrict__ noise, double noise_scale,
@@ -39,7 +21,6 @@ __global__ void __launch_bounds__(256) quantize_kernel(QuantTables t, bool have_
     }
     const double* s_thr = s_tab;
     const double* s_lab = s_tab + n_thr;
-    const double c = inv_sqrt2();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double2 y;
         if (OBSERVE) {
@@ -59,25 +40,8 @@ __global__ void __launch_bounds__(256) quantize_kernel(QuantTables t, bool have_
             y = reinterpret_cast<const double2*>(src)[i];
         }
         if (!have_q) continue;
-        double2 r;
         uchar2 code;
-        if (t.n_bits == 1) {
-            double sr = sign_np(y.x), si = sign_np(y.y);
-            code.x = (sr != sr) ? 3 : (unsigned char)((int)sr + 1);
-            code.y = (si != si) ? 3 : (unsigned char)((int)si + 1);
-            if (sr != sr || si != si) {        // numpy's complex product spreads a NaN to both parts
-                r.x = r.y = __longlong_as_double(0x7FF8000000000000LL);
-            } else {
-                r.x = __dmul_rn(c, sr) + 0.0;  // + 0.0: -0 -> +0 like numpy's (c*a - 0*b)
-                r.y = __dmul_rn(c, si) + 0.0;
-            }
-        } else {
-            int ir = digitize(y.x, s_thr, n_thr), ii = digitize(y.y, s_thr, n_thr);
-            code.x = (unsigned char)ir;
-            code.y = (unsigned char)ii;
-            r.x = s_lab[ir];
-            r.y = s_lab[ii];
-        }
+        const double2 r = quantize_value(t.n_bits, n_thr, s_thr, s_lab, y, &code);
         if (r_out) r_out[i] = r;
         if (codes_out) codes_out[i] = code;
     }

@@ -11,9 +11,19 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-from . import engine, precompute
+from . import _lib, engine, precompute
 
 _SUPPORTED_TYPES = ('full', 'circulant', 'block-circulant', 'toeplitz', 'block-toeplitz')
+
+
+def _fingerprint(a):
+    """Cheap content key of a parameter array (identity alone would serve stale GPU handles after an in-place edit of
+    ``means_cplx`` / ``covs_cplx`` / ``gm.weights_``): shape, XOR of the 64-bit words, sum."""
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a)
+    words = a.view(np.uint64).ravel() if a.dtype.itemsize % 8 == 0 else np.frombuffer(a.tobytes(), dtype=np.uint8)
+    return (a.shape, a.dtype.str, int(np.bitwise_xor.reduce(words)) if words.size else 0, complex(a.sum()))
 
 
 def _table_key(quantizer):
@@ -92,7 +102,7 @@ class Gmm_nbit:
 
     def fit(self, h, blocks=None, zero_mean=False):
         """Fit the complex GMM with EM (reference :96-163); see ``em.py``.  'full', 'circulant', 'block-circulant'
-        (``blocks=(n1, n2)``); the Toeplitz types raise ``NotImplementedError``."""
+        (``blocks=(n1, n2)``) and 'toeplitz' / 'block-toeplitz' (inverse EM on the oversampled DFT grid, reference :792-826)."""
         if self.gm.covariance_type not in _SUPPORTED_TYPES:
             raise NotImplementedError(f'Fitting for covariance_type = {self.gm.covariance_type} is not implemented.')
         from . import em
@@ -126,7 +136,9 @@ class Gmm_nbit:
         if not (self.use_structure and self.blocks is not None and self.fft_covs is not None):
             return False
         A = np.asarray(A)
-        N = self.fft_covs.shape[1]
+        K, N = self.fft_covs.shape
+        if max(self.blocks) > 256 or K > 4096:       # limits of qce_circ_model_create; larger models take the dense path
+            return False
         return A.shape == (N, N) and np.array_equal(A, np.eye(N)) and not np.any(self.means_cplx)
 
     def _prepared(self, A, snr_dB, n_bits, quantizer_type, quantizer):
@@ -134,13 +146,17 @@ class Gmm_nbit:
             nb = 'inf' if (n_bits == 'inf' or n_bits == np.inf) else int(n_bits)
             tables = _table_key(quantizer) if (nb != 1 and nb != 'inf' and quantizer_type == 'lloyd') else None
             key = ('circ', float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, self.blocks,
-                   id(self.fft_covs), id(self.gm.weights_))
+                   _fingerprint(self.fft_covs), _fingerprint(self.gm.weights_))
 
             def make_circ():
                 prep = precompute.prepare_circulant(self.fft_covs, self.gm.weights_, self.blocks, snr_dB,
                                                     np.inf if nb == 'inf' else nb, quantizer_type, quantizer)
                 return engine.CircModel(prep, flags=0)
-            return self._cache.get(key, make_circ)
+            try:
+                return self._cache.get(key, make_circ)
+            except _lib.QceError as e:      # a shape the structured kernels refuse: the dense path handles it (reference behaviour)
+                if e.status not in (_lib.ERR_INVALID, _lib.ERR_UNSUPPORTED) or self.covs_cplx is None:
+                    raise
         if self.means_cplx is None or self.covs_cplx is None or self.gm.weights_ is None:
             raise RuntimeError('Gmm_nbit: model is not fitted (means_cplx / covs_cplx / gm.weights_ missing)')
         if self.gm.covariance_type != 'full':
@@ -149,7 +165,7 @@ class Gmm_nbit:
         nb = 'inf' if (n_bits == 'inf' or n_bits == np.inf) else int(n_bits)
         tables = _table_key(quantizer) if (nb != 1 and nb != 'inf' and quantizer_type == 'lloyd') else None
         key = (float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, A.shape, A.tobytes(),
-               id(self.means_cplx), id(self.covs_cplx), id(self.gm.weights_))
+               _fingerprint(self.means_cplx), _fingerprint(self.covs_cplx), _fingerprint(self.gm.weights_))
 
         def make():
             prep = precompute.prepare(self.means_cplx, self.covs_cplx, self.gm.weights_, A, snr_dB,

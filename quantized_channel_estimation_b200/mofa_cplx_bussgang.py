@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from . import _lib, engine, precompute
-from .gmm_cplx_bussgang import _PreparedCache, _table_key
+from .gmm_cplx_bussgang import _PreparedCache, _fingerprint, _table_key
 
 
 class Mofa:
@@ -80,8 +80,8 @@ class Mofa:
         if woodbury and self.precision != 'fp64' and engine.tc_shape_ok(A.shape[0], self.D):
             woodbury = False
         if woodbury:
-            key = ('woodbury', float(snr_dB), nb, quantizer_type if nb != 'inf' else None, tables, id(self.means), id(self.lambdas),
-                   id(self.psis), id(self.amps))
+            key = ('woodbury', float(snr_dB), nb, quantizer_type if nb != 'inf' else None, tables, _fingerprint(self.means),
+                   _fingerprint(self.lambdas), _fingerprint(self.psis), _fingerprint(self.amps))
 
             def make_w():
                 prep = precompute.prepare_mfa_woodbury(self.means, self.lambdas, self.psis, self.amps, snr_dB,
@@ -90,7 +90,7 @@ class Mofa:
             self._last = self._cache.get(key, make_w)
             return self._last
         key = (float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, A.shape, A.tobytes(),
-               id(self.means), id(self.covs), id(self.amps))
+               _fingerprint(self.means), _fingerprint(self.covs), _fingerprint(self.amps))
 
         def make():
             prep = precompute.prepare(self.means, self.covs, self.amps, A, snr_dB, np.inf if nb == 'inf' else nb,

@@ -34,6 +34,11 @@ def golden_gmm():
 
 
 @pytest.fixture(scope='session')
+def golden_gmm_tc():
+    return load_golden('gmm_tc')
+
+
+@pytest.fixture(scope='session')
 def golden_mfa():
     return load_golden('mfa')
 
@@ -59,6 +64,8 @@ def baseline_case(g, tag):
 
 GMM_TAGS = ['b1_zm', 'b1_mean', 'b2u_mean', 'b3l_zm', 'binf_mean', 'b1_pilots2', 'b2u_pilots2', 'b1_k1']
 GMM_MODES = {'all': 'all', 'top1': 1, 'top3': 3, 'cum90': 0.9}
+# tests/golden/make_golden_tc.py: reference outputs at shapes the tensor-core kernels are instantiated for
+GMM_TC_TAGS = ['n32_b1_zm', 'n16_b2u_mean', 'n16_b3l_zm', 'n16_b1_pilots2', 'n16_binf_mean']
 MFA_TAGS = ['b1_zm', 'b2u_mean', 'b3l_mean']
 MFA_MODES = {'all': 'all', 'top1': 1, 'top2': 2, 'cum90': 0.9}
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import BASELINE_TAGS, GMM_MODES, GMM_TAGS, MFA_MODES, MFA_TAGS, baseline_case, golden_quantizer_tuple, relerr
+from conftest import BASELINE_TAGS, GMM_MODES, GMM_TAGS, GMM_TC_TAGS, MFA_MODES, MFA_TAGS, baseline_case, golden_quantizer_tuple, relerr
 from oracle import qce_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -208,17 +208,55 @@ def test_gmm_vs_oracle(qce, K, N, B, snr, nb, qt, ms, precision):
             raise
         assert est.is_cuda and est.dtype == torch.complex128
         est = est.cpu().numpy()
-        if mode == 'all' or precision == 'fp64':
-            assert relerr(est, ref) < tol, (mode, relerr(est, ref))
-        else:
-            # hard selections can flip for near-ties under FP32 log-likelihoods: compare per sample, allow a few flips
-            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
-            assert np.mean(per > 1e-4) < 0.02, (mode, np.sort(per)[-5:])
+        assert relerr(est, ref) < tol, (mode, relerr(est, ref))
+        # north_star: every estimate within 1e-4 -- no exemption for the hard selections (near-ties are re-evaluated in complex128)
+        per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert per.max() < 1e-4, (mode, np.sort(per)[-5:])
     # NMSE within 0.01 dB of the oracle's (north_star)
     ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
     est = m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
     d_db = 10 * np.log10(orc.mse(est, h) / orc.mse(ref, h))
     assert abs(d_db) < 0.01
+
+
+@pytest.mark.parametrize('tag', GMM_TC_TAGS)
+def test_tc_golden_reference(qce, golden_gmm_tc, tag):
+    """The tensor-core path directly against outputs of the UNMODIFIED reference at shapes it is instantiated for
+    (tests/golden/make_golden_tc.py): every estimate within 1e-4 (north_star), all four combination modes, log-probabilities."""
+    g = golden_gmm_tc
+    qz = golden_quantizer_tuple(g, tag)
+    m = _gmm(qce, g, tag, 'tc')
+    N = g[f'{tag}_means'].shape[1]
+    for mtag, mode in GMM_MODES.items():
+        est = m.estimate_from_y(torch.from_numpy(g[f'{tag}_r']).cuda(), float(g[f'{tag}_snr']), N, A=g[f'{tag}_A'], n_summands_or_proba=mode,
+                                n_bits=_nb(g, tag), quantizer_type=str(g[f'{tag}_qtype']), quantizer=qz).cpu().numpy()
+        ref = g[f'{tag}_est_{mtag}']
+        per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert relerr(est, ref) < TOL_TC and per.max() < 1e-4, (tag, mtag, relerr(est, ref), per.max())
+    model = m._prepared(g[f'{tag}_A'], float(g[f'{tag}_snr']), _nb(g, tag), str(g[f'{tag}_qtype']), qz)
+    _, lp = model.estimate(torch.from_numpy(g[f'{tag}_r']).cuda(), 'all', 'tc', want_logp=True)
+    assert np.abs(lp.cpu().numpy() - g[f'{tag}_wlp']).max() < 2e-4
+
+
+def test_tc_statistical_size_zero_flips_and_nmse(qce):
+    """10 000 pilots per SNR over the -10 .. 30 dB sweep at the config-2 shape (N = 64, K = 64, 1 bit).  Every
+    estimate of the tensor-core path within 1e-4 of the oracle's in all four combination modes -- zero flipped selections -- and the
+    NMSE (Bussgang_GMM.py:289) within 0.01 dB."""
+    K, N, B = 64, 64, 10000
+    means, covs, w = orc.random_psd_gmm(K, N, seed=0)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    for i, snr in enumerate(range(-10, 31, 5)):
+        h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=100 + i)
+        r = orc.get_observation_nbit(h, snr, noise, None, 1)
+        rt = torch.from_numpy(r).cuda()
+        for mode in ('all', 1, 4, 0.9):
+            ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=1)
+            est = m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode).cpu().numpy()
+            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+            assert per.max() < 1e-4, (snr, mode, int((per > 1e-4).sum()), np.sort(per)[-3:])
+            d_db = 10 * np.log10(orc.mse(est, h) / orc.mse(ref, h))
+            assert abs(d_db) < 0.01, (snr, mode, d_db)
 
 
 def test_pipeline_matches_stepwise(qce):
@@ -377,11 +415,9 @@ def test_circulant_kernel_vs_dense_oracle(qce, n1, n2, K, nb, qt, tol):
         ref = orc.gmm_estimate_from_y(np.zeros((K, N)), covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt,
                                       quantizer=qz)
         est = m.estimate_from_y(r, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz)
-        if mode == 'all' or tol < 1e-8:
-            assert relerr(est, ref) < tol, (mode, relerr(est, ref))
-        else:   # 1-bit: near-ties of the hard selections may flip under the 1e-8 arcsine-diagonal difference
-            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
-            assert np.mean(per > 1e-6) < 0.02
+        assert relerr(est, ref) < tol, (mode, relerr(est, ref))
+        per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert per.max() < 100 * tol, (mode, np.sort(per)[-5:])      # no flipped selection
     # and the structured path agrees with our own dense kernels
     m.use_structure = False
     m._cache.clear()
@@ -416,11 +452,9 @@ def test_circulant_tc_kernel_vs_dense_oracle(qce, K, nb, qt, B, n1, n2):
                                       quantizer=qz)
         est = model.estimate(rt, mode, 'tc').cpu().numpy()
         assert est.shape == (B, N) and np.isfinite(est.view(np.float64)).all()
-        if mode == 'all':
-            assert relerr(est, ref) < TOL_TC, relerr(est, ref)
-        else:
-            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
-            assert np.mean(per > 1e-4) <= 0.02 + 1.0 / B, (mode, np.sort(per)[-5:])
+        assert relerr(est, ref) < TOL_TC, (mode, relerr(est, ref))
+        per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert per.max() < 1e-4, (mode, np.sort(per)[-5:])
     # log-probabilities, NMSE accumulators, agreement with the complex128 kernel; 'auto' picks the fast kernel
     est64, lp64 = model.estimate(rt, 'all', 'fp64', want_logp=True)
     est_tc, lp_tc, acc = model.estimate(rt, 'all', 'auto', want_logp=True, h_true=torch.from_numpy(h).cuda())
@@ -527,22 +561,18 @@ def test_tc_ragged_batches(qce, B):
         ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=1)
         est = m.estimate_from_y(torch.from_numpy(r).cuda(), snr, N, n_summands_or_proba=mode).cpu().numpy()
         assert est.shape == (B, N) and np.isfinite(est.view(np.float64)).all()
-        if mode == 'all':
-            assert relerr(est, ref) < TOL_TC
-        else:
-            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
-            assert np.mean(per > 1e-4) <= 0.02 + 1.0 / B
+        assert relerr(est, ref) < TOL_TC
+        per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert per.max() < 1e-4, (mode, np.sort(per)[-5:])
 
 
 def _check_modes(est_fn, ref_fn, B):
     for mode in ('all', 1, 3, 0.95):
         est, ref = est_fn(mode), ref_fn(mode)
         assert np.isfinite(est.view(np.float64)).all()
-        if mode == 'all':
-            assert relerr(est, ref) < TOL_TC, (mode, relerr(est, ref))
-        else:
-            per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
-            assert np.mean(per > 1e-4) <= 0.02 + 1.0 / B, (mode, np.sort(per)[-5:])
+        assert relerr(est, ref) < TOL_TC, (mode, relerr(est, ref))
+        per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert per.max() < 1e-4, (mode, np.sort(per)[-5:])
 
 
 @pytest.mark.parametrize('K,N,B,snr,nb,ms', [
@@ -720,21 +750,46 @@ def test_tc_single_component_and_many_components(qce):
                      lambda mode: orc.gmm_estimate_from_y(means, covs, w, r, 10, n_summands_or_proba=mode, n_bits=1), B)
 
 
-def test_tc_off_grid_pilots_come_back_nan(qce):
-    """Data that is not on the declared quantiser grid cannot be represented exactly: those rows fail loudly (NaN)."""
-    K, N, B, snr = 4, 32, 200, 10
+@pytest.mark.parametrize('mode', ['all', 1, 3, 0.9])
+def test_tc_off_grid_pilots_are_reevaluated_in_complex128(qce, mode):
+    """Data that is not on the declared quantiser grid cannot be represented exactly in the FP16 pilot tiles: those rows are answered
+    by the complex128 kernel (the reference gives a finite estimate for ANY y), NaN data gives NaN like numpy, and the NMSE
+    accumulators count every row once."""
+    K, N, B, snr = 4, 32, 700, 10
     means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.0, seed=2)
     m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
     m.precision = 'tc'
     bad = r.copy()
     bad[7, 3] = 0.3 + 0.1j
+    bad[600, :] = 0.25 * r[600]
     bad[150, 0] = complex(np.nan, 0.0)
-    est = m.estimate_from_y(torch.from_numpy(bad).cuda(), snr, N, n_summands_or_proba='all').cpu().numpy()
-    ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=1)
-    rows = np.zeros(B, bool)
-    rows[[7, 150]] = True
-    assert np.isnan(est[rows].view(np.float64)).all()
-    assert relerr(est[~rows], ref[~rows]) < TOL_TC
+    est = m.estimate_from_y(torch.from_numpy(bad).cuda(), snr, N, n_summands_or_proba=mode).cpu().numpy()
+    finite = np.ones(B, bool)
+    finite[150] = False
+    ref = orc.gmm_estimate_from_y(means, covs, w, bad[finite], snr, n_summands_or_proba=mode, n_bits=1)
+    assert np.isnan(est[150].view(np.float64)).all()
+    per = np.linalg.norm(est[finite] - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert per.max() < 1e-4 and relerr(est[finite], ref) < TOL_TC
+    assert relerr(est[[7, 600]], ref[[7, 599]]) < TOL_FP64          # the two off-grid rows: complex128 arithmetic
+    # accumulators: every (finite) row exactly once
+    model = m._prepared(np.eye(N), snr, 1, 'uniform', None)
+    _, acc = model.estimate(torch.from_numpy(bad[finite]).cuda(), mode, 'tc', h_true=torch.from_numpy(h[finite]).cuda())
+    acc = acc.cpu().numpy()
+    assert acc[2] == B - 1
+    np.testing.assert_allclose(acc[0], np.sum(np.abs(ref - h[finite]) ** 2), rtol=1e-5)
+
+
+def test_tc_whole_batch_off_grid_falls_to_complex128(qce):
+    """Uniform 2-bit pilots quantised with the step of ANOTHER SNR than the one passed to estimate_from_y: no row is on the
+    expected grid; the answer is still the reference's."""
+    K, N, B = 5, 32, 300
+    means, covs, w, h, noise, qz, r = _case(K, N, B, 0, 2, 'uniform', 0.1, seed=4)      # quantised for 0 dB
+    qz10 = orc.get_quantizer([10], 2, 'uniform')[10]
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    for mode in ('all', 1):
+        ref = orc.gmm_estimate_from_y(means, covs, w, r, 10, n_summands_or_proba=mode, n_bits=2, quantizer_type='uniform', quantizer=qz10)
+        est = m.estimate_from_y(torch.from_numpy(r).cuda(), 10, N, n_summands_or_proba=mode, n_bits=2, quantizer_type='uniform', quantizer=qz10)
+        assert relerr(est.cpu().numpy(), ref) < TOL_FP64
 
 
 def test_tc_non_triangular_whitening_uses_single_cta_variant(qce):
@@ -937,3 +992,48 @@ def test_tc_top1_bucketed_full_size_chunks(qce):
     for a in (a1, a2):
         np.testing.assert_allclose(a.cpu().numpy(), a0.cpu().numpy(), rtol=1e-9)
         assert a.cpu().numpy()[2] == B
+
+
+@pytest.mark.gpu
+def test_circulant_model_beyond_structured_limits_takes_the_dense_path(qce):
+    """a zero-mean plain-circulant model with 256 < N <= 1024 is detected as structured, but the DFT-domain kernels stop at
+    256 bins per axis -- estimate_from_y must fall back to the dense path (what the reference computes), not raise."""
+    K, N, B, snr = 3, 512, 40, 5
+    c, covs, w, F = orc.circulant_gmm(K, 1, N, seed=9)
+    h, noise, _ = orc.sample_gmm_channels(np.zeros((K, N), complex), covs, w, B, seed=5)
+    r = orc.get_observation_nbit(h, snr, noise, None, 1)
+    m = qce.Gmm_nbit(n_components=K, covariance_type='circulant').set_parameters(np.zeros((K, N)), covs, w, zero_mean=True)
+    assert m.blocks == (1, N)
+    from quantized_channel_estimation_b200.engine import DenseModel
+    assert isinstance(m._prepared(np.eye(N), snr, 1, 'uniform', None), DenseModel)
+    est = m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=1)
+    ref = orc.gmm_estimate_from_y(np.zeros((K, N)), covs, w, r, snr, n_summands_or_proba='all', n_bits=1)
+    assert relerr(est, ref) < 1e-8
+
+
+@pytest.mark.gpu
+def test_prepared_cache_follows_in_place_parameter_edits(qce):
+    """The prepared-model cache is keyed by the CONTENT of the parameter arrays: an in-place edit must not serve a stale GPU handle."""
+    K, N, B, snr = 4, 16, 64, 5
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.2, seed=11)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'fp64'
+    e0 = m.estimate_from_y(r, snr, N, n_summands_or_proba='all')
+    m.means_cplx *= 0.5                       # in place: same object identity
+    e1 = m.estimate_from_y(r, snr, N, n_summands_or_proba='all')
+    ref = orc.gmm_estimate_from_y(0.5 * means, covs, w, r, snr, n_summands_or_proba='all', n_bits=1)
+    assert relerr(e1, ref) < TOL_FP64 and relerr(e0, ref) > 1e-3
+
+
+@pytest.mark.gpu
+def test_last_fix_count_reports_reevaluated_rows(qce):
+    import ctypes as C
+    from quantized_channel_estimation_b200 import _lib
+    K, N, B, snr = 4, 32, 300, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.0, seed=2)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    bad = r.copy()
+    bad[[3, 77, 200], 0] = 0.123
+    m.estimate_from_y(torch.from_numpy(bad).cuda(), snr, N, n_summands_or_proba='all')
+    assert _lib.load().qce_last_fix_count(C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 3

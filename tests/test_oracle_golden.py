@@ -5,7 +5,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import BASELINE_TAGS, GMM_MODES, GMM_TAGS, MFA_MODES, MFA_TAGS, baseline_case, golden_quantizer_tuple, relerr
+from conftest import BASELINE_TAGS, GMM_MODES, GMM_TAGS, GMM_TC_TAGS, MFA_MODES, MFA_TAGS, baseline_case, golden_quantizer_tuple, relerr
 from oracle import qce_oracle as orc
 
 
@@ -112,6 +112,22 @@ def test_gmm_estimate(golden_gmm, tag):
             np.testing.assert_allclose(aux['wlp'], g[f'{tag}_wlp'], rtol=1e-12)
             np.testing.assert_allclose(aux['prep']['m_r'], g[f'{tag}_mr'], rtol=1e-14, atol=1e-16)
             np.testing.assert_allclose(aux['prep']['C_r'], g[f'{tag}_Cr'], rtol=1e-14, atol=1e-16)
+
+
+@pytest.mark.parametrize('tag', GMM_TC_TAGS)
+def test_gmm_estimate_tc_shapes(golden_gmm_tc, tag):
+    """The oracle against the reference outputs at the tensor-core shapes (N = 16 / 32)."""
+    g = golden_gmm_tc
+    nb = float(g[f'{tag}_nbits'])
+    nb = int(nb) if np.isfinite(nb) else np.inf
+    qz = golden_quantizer_tuple(g, tag)
+    for mtag, mode in GMM_MODES.items():
+        est, aux = orc.gmm_estimate_from_y(g[f'{tag}_means'], g[f'{tag}_covs'], g[f'{tag}_w'], g[f'{tag}_r'], float(g[f'{tag}_snr']),
+                                           A=g[f'{tag}_A'], n_summands_or_proba=mode, n_bits=nb,
+                                           quantizer_type=str(g[f'{tag}_qtype']), quantizer=qz, return_aux=True)
+        assert relerr(est, g[f'{tag}_est_{mtag}']) < 1e-11, (tag, mtag)
+        if mtag == 'all':
+            np.testing.assert_allclose(aux['wlp'], g[f'{tag}_wlp'], rtol=1e-11)
 
 
 @pytest.mark.parametrize('tag', MFA_TAGS)
