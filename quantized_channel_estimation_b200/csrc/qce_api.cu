@@ -78,10 +78,10 @@ int qce_abi_version(void) { return QCE_ABI_VERSION; }
 int64_t qce_last_fix_count(void* stream) {
     const int* p = last_fix_list((cudaStream_t)stream);
     if (!p) return -1;
-    int n = 0;
-    if (cudaMemcpyAsync(&n, p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+    int n[2] = {0, 0};      // rows answered completely in complex128, near-ties re-selected in complex128
+    if (cudaMemcpyAsync(n, p, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
         cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) { cudaGetLastError(); return -1; }
-    return n;
+    return (int64_t)n[0] + n[1];
 }
 const char* qce_last_error_string(void) { return g_err; }
 int64_t qce_launch_count(void) { return g_launch_count; }

@@ -58,7 +58,7 @@ struct CircTcArgs {
     int mode, n_top, flags;
     double rho;
     int prefetch_dist;               // tiles ahead to prefetch into L2 (= resident CTAs), 0 = off
-    int* fix_buf;                    // [1 + B] hard selections too close to call in FP32: count, then the pilots -- not answered
+    int* fix_buf;                    // [2 + B] hard selections too close to call in FP32: count, then the pilots -- not answered
     double tie_eps;                  // here but re-evaluated by the complex128 kernel (launch_circ_rows)
 };
 
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(32 * NW, 2) circ_tc_kernel(const CircTcArgs a)
             weights_from_logp(lbuf + tid * LP, K, a.mode, a.n_top, a.rho, a.flags, &tie, a.tie_eps);
             tie = tie && tid < nvalid;
             tief[tid] = tie;
-            if (tie) a.fix_buf[1 + atomicAdd(a.fix_buf, 1)] = (int)(base + tid);
+            if (tie) a.fix_buf[2 + atomicAdd(a.fix_buf, 1)] = (int)(base + tid);
         }
         __syncthreads();
         for (int o = tid; o < CT_P * K; o += NT) {
@@ -618,13 +618,13 @@ static qce_status circ_fix_list(cudaStream_t s, int64_t rows, int** out) {
     static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
     std::lock_guard<std::mutex> lock(mu);
     Buf& b = bufs[std::make_pair(current_device(), s)];
-    if ((size_t)rows + 1 > b.n) {
+    if ((size_t)rows + 2 > b.n) {      // [0] count, [1] unused here (layout of qce_last_fix_count), then the list
         if (b.p) QCE_CUDA_TRY(cudaFree(b.p));
         b.p = nullptr; b.n = 0;
-        QCE_CUDA_TRY(cudaMalloc(&b.p, ((size_t)rows + 1) * sizeof(int)));
-        b.n = (size_t)rows + 1;
+        QCE_CUDA_TRY(cudaMalloc(&b.p, ((size_t)rows + 2) * sizeof(int)));
+        b.n = (size_t)rows + 2;
     }
-    QCE_CUDA_TRY(cudaMemsetAsync(b.p, 0, sizeof(int), s));
+    QCE_CUDA_TRY(cudaMemsetAsync(b.p, 0, 2 * sizeof(int), s));
     note_fix_list(s, b.p);
     *out = b.p;
     return QCE_OK;
@@ -672,7 +672,7 @@ qce_status launch_circ_tc(const qce_circ_model* m, cudaStream_t s, const double*
     if (nw == 8) st = m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 8>(a, s);
     else st = m->n_comp == 64 ? launch_circ_tc_k<1, 8>(a, s) : launch_circ_tc_k<2, 16>(a, s);
     if (st || mode == QCE_MODE_ALL || !(h_est || acc)) return st;
-    return launch_circ_rows(m, s, r, a.fix_buf + 1, a.fix_buf, B, mode, n_top, rho, h_est, h_true, acc);
+    return launch_circ_rows(m, s, r, a.fix_buf + 2, a.fix_buf, B, mode, n_top, rho, h_est, h_true, acc);
 }
 
 }  // namespace qce

@@ -227,6 +227,8 @@ __device__ __forceinline__ void fmt_items(const TcArgs& a, int64_t first_tile, i
     }
 }
 
+__device__ __forceinline__ void tie_append(const unsigned char* bad, int* tie_buf, int64_t chunk_row);
+
 // hi_a + lo_a > hi_b + lo_b, exactly (the FP64 sums of FP32 pairs are exact)
 __device__ __noinline__ bool pair_greater_f64(float hi_a, float lo_a, float hi_b, float lo_b) {
     return ((double)hi_a + (double)lo_a) > ((double)hi_b + (double)lo_b);
@@ -467,6 +469,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             float mref_hi = 0.f, mref_lo = 0.f;
             float ssum = 0.f;
             float best_hi = -INFINITY, best_lo = 0.f;  // EPI=1 label mode: running maximum of l_k as an FP32 pair
+            float best_q = 0.f;                        // quadratic form of the best component (the FP32 error of l grows with it)
             float second = -INFINITY;                  // ... and the runner-up (rounded): the selection is re-evaluated in complex128
             int best_k = 0;                            // when the two are closer than the FP32 log-likelihoods can tell apart
 
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         // ties, NaN, infinities, the first component: rare, and behind a warp-uniform branch and a call so that the
                         // compiler cannot turn the FP64 comparison into unconditional arithmetic + select
                         if (__any_sync(0xffffffffu, !safe)) { if (!safe) better = pair_greater_f64(l_hi, l_lo, best_hi, best_lo); }
-                        if (better) { second = best_hi + best_lo; best_hi = l_hi; best_lo = l_lo; best_k = k; }
+                        if (better) { second = best_hi + best_lo; best_hi = l_hi; best_lo = l_lo; best_k = k; best_q = q_hi; }
                         else second = fmaxf(second, l_hi + l_lo);
                     } else if (tile_base + row < a.B) a.lp_out[(tile_base + row) * a.K + k] = make_float2(l_hi, l_lo);
                     p = 0.f;
@@ -637,11 +640,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             if (EPI == 1 && a.top_out && valid) {
                 if ((a.top_flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp((double)best_hi + (double)best_lo) == 0.0) best_k = 0;
                 a.top_out[g] = best_k;
-                // too close to call (or NaN), or on the edge of the exp() underflow the MFA argmax quirk tests: complex128 decides
+                // too close to call (or NaN), or on the edge of the exp() underflow the MFA argmax quirk tests: the pilot goes on the
+                // tie list and tc_refine_kernel decides in complex128 before the labels are used
                 const float gap = (best_hi - second) + best_lo;
-                bool tie = !(gap > a.tie_eps);
+                bool tie = !(gap > a.tie_eps * fmaxf(1.f, best_q * a.inv_nobs));
                 if ((a.top_flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabsf(best_hi + 745.1332f) < 0.01f) tie = true;
-                if (tie) fix_append(const_cast<unsigned char*>(a.bad), a.fix_cnt, a.fix_idx, g, a.row0 + g, 2);
+                if (tie) tie_append(a.bad, a.tie_buf, g);
             }
             // (flags read here, after the last component: with the fused prologue they are written by other warps of this kernel)
             if (EPI != 1 && valid && (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) == 0) {
@@ -898,7 +902,7 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
     if (threadIdx.x < 8) {      // rows that cannot be represented go on the fix list (complex128 re-evaluation after the tensor-core launches)
         const int64_t row = tile * TILE_M + mb * 8 + threadIdx.x;
         bad[row] = (unsigned char)s_bad[threadIdx.x];
-        if (s_bad[threadIdx.x] && row < B) fix_buf[1 + atomicAdd(fix_buf, 1)] = (int)row;
+        if (s_bad[threadIdx.x] && row < B) fix_buf[2 + atomicAdd(fix_buf, 1)] = (int)row;
     }
 }
 
@@ -907,31 +911,26 @@ __global__ void __launch_bounds__(256) tc_format_kernel(const void* __restrict__
 // the reference's semantics (gmm:197-242 / mofa:125-158): softmax responsibilities; top-1 = argmax of l (MFA flag: argmax
 // of exp(l), i.e. label 0 when everything underflows); top-n / cumulative-rho = descending selection, renormalised.
 // K <= 1024 (32 values per lane).  Also exports l as float64 when asked.
-template <int PER>      // entries per lane: K <= 32 PER
-__global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho,
-                                                        int flags, float* __restrict__ w_out, double* __restrict__ logp_out,
-                                                        int* __restrict__ top_out, unsigned char* __restrict__ bad, int* __restrict__ fix_buf,
-                                                        int64_t row0, double tie_eps) {
-    const int lane = threadIdx.x & 31;
-    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (b >= B) return;
-    double l[PER];
+// select_row: one warp, the K weighted log-probabilities of a pilot spread over the lanes (entry i of lane l is component 32 i + l,
+// -inf where there is none).  Writes the weight row or the top-1 label; returns whether the selection is too close to call when the
+// log-likelihoods carry an error of up to ~tie_eps nats (the deciding gap -- maximum vs runner-up, last selected vs first left out
+// -- or a prefix sum vs rho): the caller then has the pilot re-evaluated in complex128 (tc_refine_kernel, which calls this again
+// with tie_eps = 0 on the exact values).
+// EXACT: the responsibilities are formed like the complex128 kernel forms them (FP64 exp, logsumexp: gmm:652) -- the re-selection of
+// the listed near-ties must not decide a prefix sum that is within 1e-7 of rho with FP32 exponentials.
+template <int PER, bool EXACT = false>      // entries per lane: K <= 32 PER
+__device__ __forceinline__ bool select_row(double (&l)[PER], const int lane, const int K, const int mode, const int n_top, const double rho,
+                                           const int flags, double tie_eps, float* __restrict__ w_row, int* __restrict__ top_slot,
+                                           const double* __restrict__ logc = nullptr, const double inv_nobs = 0.0) {
     const int per = (K + 31) / 32;
     double mx = -INFINITY, mx2 = -INFINITY;      // maximum and runner-up (a second entry equal to the maximum counts as runner-up)
     int amax = 0;
-    bool tie = false;                            // selection too close to call in these FP32-derived log-likelihoods -> complex128 decides
+    bool tie = false;
     #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        l[i] = -INFINITY;
-        if (i < per) {
-            const int k = i * 32 + lane;
-            if (k < K) {
-                const float2 v = lp2[b * K + k];
-                l[i] = (double)v.x + (double)v.y;
-                if (logp_out) logp_out[b * K + k] = l[i];
-                if (l[i] != l[i]) tie = true;                     // NaN: let the complex128 kernel reproduce numpy's answer
-                if (l[i] > mx) { mx2 = mx; mx = l[i]; amax = k; } else if (l[i] > mx2) mx2 = l[i];
-            }
+        if (i < per && i * 32 + lane < K) {
+            if (l[i] != l[i]) tie = true;                         // NaN: let the complex128 kernel reproduce numpy's answer
+            if (l[i] > mx) { mx2 = mx; mx = l[i]; amax = i * 32 + lane; } else if (l[i] > mx2) mx2 = l[i];
         }
     }
     // warp argmax (first index among equal maxima, like np.argmax)
@@ -943,43 +942,53 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
         if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
     }
     tie = __any_sync(0xffffffffu, tie);
-    if (!w_out && !top_out) return;
-    // `bad` / the fix list: a row that is already flagged (pilots off the grid) stays as it is
-    auto flag_row = [&]() { if (lane == 0) fix_append(bad, fix_buf, fix_buf + 1, b, row0 + b, 2); };
+    if (!w_row && !top_slot) return false;
+    // the error of an FP32-accumulated log-likelihood grows with its quadratic form q = logc - l (~n_obs for a pilot that fits the
+    // component, much more for outliers): the gap scales with q / n_obs of the best component
+    if (logc && amax >= 0 && amax < K) tie_eps *= fmax(1.0, (__ldg(logc + amax) - mx) * inv_nobs);
     if (mode == QCE_MODE_TOP1) {
         if (!(mx - mx2 > tie_eps) || ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabs(mx + 745.1332) < 0.01)) tie = true;
-        if (tie) flag_row();
         if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
-        if (top_out) {      // bucketed combination: the label instead of a one-hot weight row
-            if (lane == 0) top_out[b] = amax;
-            return;
+        if (top_slot) {      // bucketed combination: the label instead of a one-hot weight row
+            if (lane == 0) *top_slot = amax;
+            return tie;
         }
         #pragma unroll
         for (int i = 0; i < PER; ++i)
-            if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = (k == amax) ? 1.f : 0.f; }
-        return;
+            if (i < per) { const int k = i * 32 + lane; if (k < K) w_row[k] = (k == amax) ? 1.f : 0.f; }
+        return tie;
     }
     // responsibilities exp(l - logsumexp(l)): the difference to the maximum is formed in FP64 (the pair carries ~48 bits),
     // the exponential in FP32 (an FP64 exp per entry made this kernel 15 % of the top-n / split-path time)
-    float sumf = 0.f;
-    #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const bool on = i < per && i * 32 + lane < K;
-        const float e = on ? expf((float)(l[i] - mx)) : 0.f;
-        l[i] = on ? (double)e : -1.0;                                                                 // -1 = no entry
-        sumf += e;
+    if (EXACT) {
+        double sum = 0.0;
+        #pragma unroll
+        for (int i = 0; i < PER; ++i) if (i < per && i * 32 + lane < K) sum += exp(l[i] - mx);
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const double lse = mx + log(sum);
+        #pragma unroll
+        for (int i = 0; i < PER; ++i) l[i] = (i < per && i * 32 + lane < K) ? exp(l[i] - lse) : -1.0;      // -1 = no entry
+    } else {
+        float sumf = 0.f;
+        #pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const bool on = i < per && i * 32 + lane < K;
+            const float e = on ? expf((float)(l[i] - mx)) : 0.f;
+            l[i] = on ? (double)e : -1.0;                                                             // -1 = no entry
+            sumf += e;
+        }
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sumf += __shfl_xor_sync(0xffffffffu, sumf, off);
+        const double inv_sum = 1.0 / (double)sumf;
+        #pragma unroll
+        for (int i = 0; i < PER; ++i) if (l[i] >= 0.0) l[i] *= inv_sum;
     }
-    #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sumf += __shfl_xor_sync(0xffffffffu, sumf, off);
-    const double inv_sum = 1.0 / (double)sumf;
-    #pragma unroll
-    for (int i = 0; i < PER; ++i) if (l[i] >= 0.0) l[i] *= inv_sum;
     if (mode == QCE_MODE_ALL) {
-        if (tie) flag_row();
         #pragma unroll
         for (int i = 0; i < PER; ++i)
-            if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = (float)l[i]; }
-        return;
+            if (i < per) { const int k = i * 32 + lane; if (k < K) w_row[k] = (float)l[i]; }
+        return tie;
     }
     // descending selection; selected entries are flagged by a set bit in `sel`
     const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
@@ -1011,10 +1020,154 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
             if (cum >= rho) done = true;                    // searchsorted(cumsum, rho) + 1 entries (gmm:234)
         }
     }
-    if (tie) flag_row();
     #pragma unroll
     for (int i = 0; i < PER; ++i)
-        if (i < per) { const int k = i * 32 + lane; if (k < K) w_out[b * K + k] = ((sel >> i) & 1u) ? (float)(l[i] / cum) : 0.f; }
+        if (i < per) { const int k = i * 32 + lane; if (k < K) w_row[k] = ((sel >> i) & 1u) ? (float)(l[i] / cum) : 0.f; }
+    return tie;
+}
+
+// the tie list of a chunk: [0] = count, then chunk rows.  Rows that are off the quantiser grid (bad != 0) are not listed: the
+// complex128 kernel answers them completely after the tensor-core launches.
+__device__ __forceinline__ void tie_append(const unsigned char* bad, int* tie_buf, int64_t chunk_row) {
+    if (bad[chunk_row] == 0) tie_buf[1 + atomicAdd(tie_buf, 1)] = (int)chunk_row;
+}
+
+// One warp per pilot: weighted log-probabilities (FP32 pairs from the EPI=1 pass) -> combination weights per mode, with
+// the reference's semantics (gmm:197-242 / mofa:125-158): softmax responsibilities; top-1 = argmax of l (MFA flag: argmax
+// of exp(l), i.e. label 0 when everything underflows); top-n / cumulative-rho = descending selection, renormalised.
+// K <= 1024 (32 values per lane).  Also exports l as float64 when asked.
+template <int PER, bool EXACT = false>
+__global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho,
+                                                        int flags, float* __restrict__ w_out, double* __restrict__ logp_out,
+                                                        int* __restrict__ top_out, const unsigned char* __restrict__ bad, int* __restrict__ tie_buf,
+                                                        double tie_eps, const int* __restrict__ list, const double* __restrict__ logc, double inv_nobs) {
+    const int lane = threadIdx.x & 31;
+    // list != null: re-selection of the pilots on the tie list after tc_refine_kernel made their log-probabilities exact
+    const int64_t n = list ? (int64_t)__ldg(list) : B;
+    for (int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += (int64_t)gridDim.x * 8) {
+        const int64_t b = list ? (int64_t)__ldg(list + 1 + e) : e;
+        double l[PER];
+        #pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            l[i] = -INFINITY;
+            const int k = i * 32 + lane;
+            if (k < K) {
+                const float2 v = lp2[b * K + k];
+                l[i] = (double)v.x + (double)v.y;
+                if (logp_out) logp_out[b * K + k] = l[i];
+            }
+        }
+        const bool tie = select_row<PER, EXACT>(l, lane, K, mode, n_top, rho, flags, tie_eps, w_out ? w_out + b * K : nullptr, top_out ? top_out + b : nullptr,
+                                                logc, inv_nobs);
+        if (tie && lane == 0 && tie_buf) tie_append(bad, tie_buf, b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ exact re-selection of near-ties
+// The pilots on the tie list get their K weighted log-probabilities in complex128 (the arithmetic of dense_fp64_kernel's phase 1:
+// l_k = logc_k - |Linv_k r - zoff_k|^2, gmm:380-386, 413-417, 435), written over the FP32-derived pairs in lp2; tc_select_kernel
+// then runs again on the listed pilots (tie_eps = 0) and overwrites their weight rows / labels, and the combine launch answers
+// them like every other pilot.  Work item = (8 listed pilots) x (8 components, one per warp): the parameters of a component are
+// read once for 8 pilots (one pilot per CTA made this launch L2-bandwidth bound: K x 32 KB per pilot), and a short list still
+// spreads over many CTAs (the launch sits between the whitening and the combine launch: its latency counts).  Lane l takes the
+// rows l and 63 - l of every 64 rows of Linv_k (equal work under the triangular skip).
+// The length of the list lives on the device: the grid is fixed and walks the work items grid-stride.
+constexpr int REFINE_RT = 8;
+struct RefineArgs {
+    int No, K, tri;
+    const double2* Linv;
+    const double2* zoff;
+    const double* logc;
+    RowSource src;
+    int64_t row0;               // batch row of chunk row 0 (the source arrays are indexed by batch row)
+    const int* tie_buf;         // [0] count, then chunk rows
+    int* tie_total;             // running total over the chunks of a batch (qce_last_fix_count)
+    float2* lp2;                // [chunk rows][K]
+    double* logp_out;           // [chunk rows][K] or null: exact values for the listed pilots
+};
+
+__global__ void __launch_bounds__(256) tc_refine_kernel(const RefineArgs a) {
+    extern __shared__ __align__(16) unsigned char refine_smem[];
+    double2* r_s = reinterpret_cast<double2*>(refine_smem);                 // [RT][No]
+    __shared__ int s_crow[REFINE_RT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int No = a.No, K = a.K;
+    const int n_list = __ldg(a.tie_buf);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_list > 0) atomicAdd(a.tie_total, n_list);
+    const int kblocks = (K + 7) / 8;
+    const int n_items = ((n_list + REFINE_RT - 1) / REFINE_RT) * kblocks;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int tile = w / kblocks, kb = w - tile * kblocks;
+        const int e0 = tile * REFINE_RT, nv = (n_list - e0) < REFINE_RT ? (n_list - e0) : REFINE_RT;
+        if (threadIdx.x < REFINE_RT) s_crow[threadIdx.x] = threadIdx.x < nv ? __ldg(a.tie_buf + 1 + e0 + threadIdx.x) : -1;
+        __syncthreads();
+        for (int o = threadIdx.x; o < REFINE_RT * No; o += 256) {
+            const int t = o / No, j = o - t * No;
+            double2 v = make_double2(0.0, 0.0);
+            if (t < nv) {
+                const int64_t idx = (a.row0 + s_crow[t]) * No + j;
+                if (a.src.r) {
+                    v = reinterpret_cast<const double2*>(a.src.r)[idx];
+                } else {      // get_observation_nbit with A = I (utils.py:241-251): two roundings, then the quantiser
+                    double2 h;
+                    if (a.src.obs_h_c64) { const float2 hf = reinterpret_cast<const float2*>(a.src.obs_h)[idx]; h = make_double2((double)hf.x, (double)hf.y); }
+                    else h = reinterpret_cast<const double2*>(a.src.obs_h)[idx];
+                    const double2 wn = reinterpret_cast<const double2*>(a.src.obs_noise)[idx];
+                    const double2 y = make_double2(__dadd_rn(h.x, __dmul_rn(a.src.obs_noise_scale, wn.x)), __dadd_rn(h.y, __dmul_rn(a.src.obs_noise_scale, wn.y)));
+                    v = quantize_value(a.src.qt.n_bits, a.src.qt.n_thr, a.src.qt.thr, a.src.qt.labels, y, nullptr);
+                }
+            }
+            r_s[o] = v;
+        }
+        __syncthreads();
+        {
+            const int k = kb * 8 + warp;
+            if (k < K) {
+            const double2* __restrict__ Lk = a.Linv + (size_t)k * No * No;
+            double q[REFINE_RT];
+            #pragma unroll
+            for (int t = 0; t < REFINE_RT; ++t) q[t] = 0.0;
+            for (int i0 = 0; i0 < 2 * No; i0 += 64) {
+                const int i = (i0 >> 7) * 64 + ((i0 & 64) ? 63 - lane : lane);
+                if (i >= No) continue;
+                const double2 zo = __ldg(a.zoff + (size_t)k * No + i);
+                double2 z[REFINE_RT];
+                #pragma unroll
+                for (int t = 0; t < REFINE_RT; ++t) z[t] = make_double2(-zo.x, -zo.y);
+                const int jn = a.tri ? i + 1 : No;
+                const double2* __restrict__ Lrow = Lk + (size_t)i * No;
+                #pragma unroll 4
+                for (int j = 0; j < jn; ++j) {
+                    const double2 l = __ldg(Lrow + j);
+                    #pragma unroll
+                    for (int t = 0; t < REFINE_RT; ++t) {
+                        const double2 r = r_s[t * No + j];
+                        z[t].x = fma(l.x, r.x, z[t].x); z[t].x = fma(-l.y, r.y, z[t].x);
+                        z[t].y = fma(l.x, r.y, z[t].y); z[t].y = fma(l.y, r.x, z[t].y);
+                    }
+                }
+                #pragma unroll
+                for (int t = 0; t < REFINE_RT; ++t) q[t] += z[t].x * z[t].x + z[t].y * z[t].y;
+            }
+            #pragma unroll
+            for (int t = 0; t < REFINE_RT; ++t) {
+                #pragma unroll
+                for (int off = 16; off > 0; off >>= 1) q[t] += __shfl_xor_sync(0xffffffffu, q[t], off);
+            }
+            double mine = 0.0;
+            #pragma unroll
+            for (int t = 0; t < REFINE_RT; ++t) if (lane == t) mine = q[t];
+            if (lane < nv) {
+                const double lv = a.logc[k] - mine;
+                const float hi = (float)lv;
+                const size_t o = (size_t)s_crow[lane] * K + k;
+                a.lp2[o] = make_float2(hi, (float)(lv - (double)hi));      // 48 significant bits: ~1e-13 nats
+                if (a.logp_out) a.logp_out[o] = lv;
+            }
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ bucketed top-1 combination
@@ -1107,14 +1260,14 @@ static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, T
         QCE_CUDA_TRY(cudaMemset(t.bad, 0, need_bad));
         t.bad_bytes = need_bad;
     }
-    const size_t need_fix = (need_bad + 1) * sizeof(int);
+    const size_t need_fix = (need_bad + 2) * sizeof(int);       // [0] rows on the list, [1] near-ties re-selected so far, then the list
     if (need_fix > t.fix_bytes) {
         if (t.fix_buf) QCE_CUDA_TRY(cudaFree(t.fix_buf));
         t.fix_buf = nullptr; t.fix_bytes = 0;
         QCE_CUDA_TRY(cudaMalloc(&t.fix_buf, need_fix));
         t.fix_bytes = need_fix;
     }
-    QCE_CUDA_TRY(cudaMemsetAsync(t.fix_buf, 0, sizeof(int), s));      // a new batch is about to be formatted: empty fix list
+    QCE_CUDA_TRY(cudaMemsetAsync(t.fix_buf, 0, 2 * sizeof(int), s));      // a new batch is about to be formatted: empty fix list
     note_fix_list(s, t.fix_buf);
     *out = &t;
     return QCE_OK;
@@ -1126,11 +1279,17 @@ static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, T
 static qce_status tc_fix_rows(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int mode, int n_top, double rho,
                               double* h_est, double* logp_out, const void* h_true, int h_true_c64, double* acc) {
     if (!h_est && !logp_out && !acc) return QCE_OK;
-    return launch_dense_fp64_rows(m, s, ts->src, ts->fix_buf + 1, ts->fix_buf, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
+    return launch_dense_fp64_rows(m, s, ts->src, ts->fix_buf + 2, ts->fix_buf, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
 }
 
 static qce_status tc_scratch_aux(TileScratch* t, size_t rows, size_t K) {
     std::lock_guard<std::mutex> lock(g_scratch_mu);
+    if ((rows + 1) * sizeof(int) > t->tie_bytes) {
+        if (t->tie_buf) QCE_CUDA_TRY(cudaFree(t->tie_buf));
+        t->tie_buf = nullptr; t->tie_bytes = 0;
+        QCE_CUDA_TRY(cudaMalloc(&t->tie_buf, (rows + 1) * sizeof(int)));
+        t->tie_bytes = (rows + 1) * sizeof(int);
+    }
     const size_t need_lp = rows * K * sizeof(float2), need_w = rows * K * sizeof(float);
     if (need_lp > t->lp2_bytes) {
         if (t->lp2) QCE_CUDA_TRY(cudaFree(t->lp2));
@@ -1323,13 +1482,14 @@ static qce_status launch_split(const TcArgs& a, bool offs, int epi, bool split_a
     }
 }
 
-// Log-likelihood gap (nats) below which a hard selection is handed to the complex128 kernel.  The FP16-split / FP32-accumulate
-// log-likelihoods are within ~1e-5 nats of the complex128 ones at n_obs = 64 (profiles/r02_flip_rate.json: the error grows with
-// the number of accumulated squares); the margin is >= 10x.  QCE_TC_TIE_EPS overrides (0 disables the re-evaluation: A/B runs).
+// Log-likelihood gap (nats) below which a hard selection is re-made in complex128.  Measured error of the DIFFERENCE of two
+// FP16-split / FP32-accumulated log-likelihoods of a pilot (profiles/r02_flip_rate.json, max over 2^16..2^18 pilots): 2.2e-5 nats
+// at n_obs = 64, 3.5e-5 at n_obs = 128 and on the three-pass (off-grid) path: the gap keeps a margin of >= 4x, and grows per pilot
+// with the quadratic form of its best component.  QCE_TC_TIE_EPS overrides (0 disables the re-evaluation: A/B runs).
 static double tc_tie_eps(const qce_model* m) {
     if (const char* e = getenv("QCE_TC_TIE_EPS")) return atof(e);
     const double scale = m->n_obs > 64 ? (double)m->n_obs / 64.0 : 1.0;
-    return 2e-4 * scale * (m->tc.split_a ? 2.0 : 1.0);
+    return 1e-4 * scale * (m->tc.split_a ? 1.5 : 1.0);
 }
 
 static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc,
@@ -1348,17 +1508,16 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     a.skip_thresh = th ? (float)atof(th) : 1e-30f;
     a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr;
     a.top_out = nullptr; a.top_flags = m->flags;
-    a.fix_cnt = ts->fix_buf; a.fix_idx = ts->fix_buf + 1; a.row0 = 0;
-    a.tie_eps = (float)tc_tie_eps(m);
+    a.fix_cnt = ts->fix_buf; a.fix_idx = ts->fix_buf + 2; a.tie_buf = ts->tie_buf;
+    a.tie_eps = (float)tc_tie_eps(m); a.inv_nobs = 1.f / (float)m->n_obs;
 }
 
 static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,
                                const void* h_true, int h_true_c64, double* acc, const int* unit_comp = nullptr, const int* perm = nullptr,
-                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr, int64_t row0 = 0) {
+                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr) {
     const TcParams& p = m->tc;
     TcArgs a;
     tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
-    a.row0 = row0;
     if (unit_comp) { a.unit_comp = unit_comp; a.perm = perm; a.n_units_dev = n_units_dev; a.a_img = (const __half*)bucket_img; }
     a.top_out = top_out;
     a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
@@ -1470,7 +1629,11 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         const void* ht = h_true ? (const void*)((const char*)h_true + (size_t)b0 * true_row) : nullptr;
         // top-1 without log-probability export: the whitening launch keeps the running argmax itself (no [rows][K] export, no selection launch)
         const bool label_in_kernel = bucketed && !logp_out;
-        st = tc_run_split(m, &v, s, nb, 1, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, label_in_kernel ? b_top : nullptr, b0);
+        // hard selections: pilots whose selection is too close to call go on the chunk's tie list (QCE_TC_TIE_EPS=0: nobody does)
+        const double eps = tc_tie_eps(m);
+        const bool refine = want_est && mode != QCE_MODE_ALL && eps > 0.0 && (ts->src.r || ts->src.obs_h);
+        QCE_CUDA_TRY(cudaMemsetAsync(ts->tie_buf, 0, sizeof(int), s));
+        st = tc_run_split(m, &v, s, nb, 1, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, label_in_kernel ? b_top : nullptr);
         if (st) return st;
         if (bucketed) {
             QCE_CUDA_TRY(cudaMemsetAsync(b_cnt, 0, m->n_comp * sizeof(int), s));
@@ -1479,14 +1642,31 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         if (!label_in_kernel) {
             const unsigned grid = (unsigned)((nb + 7) / 8);
             float* wts = (want_est && !bucketed) ? (float*)v.wts : nullptr;
-            unsigned char* vb = (unsigned char*)v.bad;
-            const double eps = tc_tie_eps(m);
-            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->fix_buf, b0, eps);
-            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->fix_buf, b0, eps);
-            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->fix_buf, b0, eps);
+            const unsigned char* vb = (const unsigned char*)v.bad;
+            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
+            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
+            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
+            QCE_CHECK_LAUNCH("tc_select_kernel");
         }
-        QCE_CHECK_LAUNCH("tc_select_kernel");
         if (!want_est) continue;
+        if (refine) {      // exact log-probabilities for the pilots on the tie list, then their selection again (weight rows / labels overwritten)
+            RefineArgs ra;
+            ra.No = m->n_obs; ra.K = m->n_comp; ra.tri = m->tc.triangular ? 1 : 0;
+            ra.Linv = (const double2*)m->Linv; ra.zoff = (const double2*)m->zoff; ra.logc = m->logc;
+            ra.src = ts->src; ra.row0 = b0; ra.tie_buf = ts->tie_buf; ra.tie_total = ts->fix_buf + 1;
+            ra.lp2 = (float2*)v.lp2; ra.logp_out = lo;
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+            const size_t rsm = (size_t)REFINE_RT * m->n_obs * sizeof(double2);
+            tc_refine_kernel<<<(unsigned)(4 * sms), 256, rsm, s>>>(ra);
+            QCE_CHECK_LAUNCH("tc_refine_kernel");
+            float* wts = bucketed ? nullptr : (float*)v.wts;
+            const unsigned sgrid = (unsigned)sms;
+            if (m->n_comp <= 64) tc_select_kernel<2, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0);
+            else if (m->n_comp <= 256) tc_select_kernel<8, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0);
+            else tc_select_kernel<32, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0);
+            QCE_CHECK_LAUNCH("tc_select_kernel(list)");
+        }
         if (bucketed) {
             tc_bucket_count_kernel<<<(unsigned)((nb + 1023) / 1024), 1024, 0, s>>>(b_top, nb, m->n_comp, b_cnt);
             tc_bucket_scan_kernel<<<1, 1024, 0, s>>>(b_cnt, m->n_comp, bucket_rows, b_off, b_cur, b_ucomp, b_nu);

@@ -30,13 +30,14 @@ struct TcArgs {
     const float* hoff;         // [K][2N]
     const float2* logc2;       // [K] logc_k as an unevaluated FP32 pair (hi, lo)
     const __half* a_img;       // [n_tiles][128 x 2No] pilots as exact FP16 integers, canonical K-major core-matrix tiles
-    const unsigned char* bad;  // [n_tiles * 128] rows the tensor-core path must not answer: 1 = data not on the quantiser grid,
-                               // 2 = a hard selection (top-1 / top-n / cumulative) too close to call in FP32.  Their estimates are
-                               // neither written nor accumulated here; the rows are on the fix list and re-evaluated in complex128
-    int* fix_idx;              // [rows] the fix list (indices relative to the first row of the formatted batch)
+    const unsigned char* bad;  // [n_tiles * 128] rows the tensor-core path cannot answer (data not on the quantiser grid): their
+                               // estimates are neither written nor accumulated here; they are on the fix list and re-evaluated
+                               // completely by the complex128 kernel after the tensor-core launches
+    int* fix_idx;              // [rows] the fix list (rows of the formatted batch)
     int* fix_cnt;              // its length (device side)
-    int64_t row0;              // first row of this launch within the formatted batch (chunked mode path)
-    float tie_eps;             // a selection is "too close to call" when the deciding log-likelihood gap is below this (nats)
+    int* tie_buf;              // EPI=1 label mode: [0] count, then the rows of this launch whose top-1 selection is too close to
+    float tie_eps, inv_nobs;   // call (deciding log-likelihood gap below tie_eps nats, times q / n_obs of the best component when
+                               // that exceeds one): tc_refine_kernel + the exact selection re-select them
     double2* h_est;            // [B][N] or null
     float2* lp_out;            // EPI=1: [B][K] weighted log-probabilities as FP32 (hi, lo) pairs
     const float* w_in;         // EPI=2: [B][K] combination weights
@@ -203,19 +204,16 @@ struct TileScratch {
     const qce_model* owner = nullptr;      // model whose pilots are currently formatted here
     int64_t rows = 0;
     // fix list: rows of the formatted batch that are re-evaluated by the complex128 kernel after the tensor-core launches
-    // ([0] of fix_buf is the length, the indices follow), and where their pilots come from
+    // ([0] of fix_buf is the length, [1] counts the near-ties re-selected so far, the indices follow), and where their pilots come from
     int* fix_buf = nullptr;
     size_t fix_bytes = 0;
     RowSource src;
+    // tie list of the chunk in flight ([0] = count, then chunk rows): hard selections too close to call in FP32, re-selected in
+    // complex128 (tc_refine_kernel) before the combine launch
+    int* tie_buf = nullptr;
+    size_t tie_bytes = 0;
 };
 
-// append a row to the fix list unless it is on it already (bad[row] != 0).  Flagged rows are rare: one global atomic each.
-// (`bad` is the flag array of the launch's chunk, indexed by the row within the chunk; the list holds rows of the whole batch)
-__device__ __forceinline__ void fix_append(unsigned char* bad, int* fix_cnt, int* fix_idx, int64_t chunk_row, int64_t batch_row, unsigned char why) {
-    if (bad[chunk_row] == 0) {
-        bad[chunk_row] = why;
-        fix_idx[atomicAdd(fix_cnt, 1)] = (int)batch_row;
-    }
-}
+
 
 }  // namespace qce

@@ -723,7 +723,7 @@ def test_tc_fused_prologue_variant(qce, K, N, c64):
     try:
         l0 = _launches()
         est1, acc1 = model.pipeline(quant, h, noise, 10 ** (-snr / 20), 'all', 'tc', want_est=True)
-        assert _launches() - l0 == 1                # one kernel launch
+        assert _launches() - l0 == 2                # one estimate launch + the complex128 launch that answers off-grid / NaN rows
     finally:
         del os.environ['QCE_TC_FUSE']
     ok = ~torch.isnan(est0.real).any(dim=1)

@@ -55,7 +55,7 @@ def run_case(tag, model, r, chunk64=1 << 16):
     # error of the DIFFERENCE to the best component: what a selection actually depends on
     dd = d - d.gather(1, lp_64.argmax(1)[:, None])
     out['logp_gap_err_max'] = float(dd[top].abs().max())
-    del lp_tc, lp_64, d, dd, top
+    del d, dd, top
     for mtag, mode in MODES.items():
         ref = torch.cat([model.estimate(r[i:i + chunk64], mode, 'fp64') for i in range(0, B, chunk64)])
         rn = ref.norm(dim=1).clamp(min=1e-300)
@@ -69,7 +69,20 @@ def run_case(tag, model, r, chunk64=1 << 16):
         out[mtag] = dict(flips_no_fix=int((p0 > 1e-4).sum()), flip_rate_no_fix=float((p0 > 1e-4).float().mean()),
                          flips=int((p1 > 1e-4).sum()), worst=float(p1.max()), fixed=nfix, fixed_share=nfix / B,
                          ms=ms1, ms_no_fix=ms0)
+        if int((p1 > 1e-4).sum()) and os.environ.get('FLIP_DEBUG'):
+            for row in torch.nonzero(p1 > 1e-4)[:3, 0].tolist():
+                l64, ltc = lp_64[row], lp_tc[row]
+                order = torch.argsort(l64, descending=True)[:40]
+                p64 = torch.softmax(l64, 0)[order]
+                ptc = torch.softmax(ltc, 0)[order]
+                print('DEBUG', tag, mtag, 'row', row, 'err', float(p1[row]), file=sys.stderr)
+                print('  order', order.tolist(), file=sys.stderr)
+                print('  p64  ', ['%.6e' % v for v in p64.tolist()], file=sys.stderr)
+                print('  cum64', ['%.9f' % v for v in torch.cumsum(p64, 0).tolist()], file=sys.stderr)
+                print('  cumtc', ['%.9f' % v for v in torch.cumsum(torch.sort(torch.softmax(ltc, 0), descending=True).values, 0)[:40].tolist()], file=sys.stderr)
+                print('  dl   ', ['%.2e' % v for v in (ltc - l64)[order].tolist()], file=sys.stderr)
         del ref, e0, e1
+    del lp_tc, lp_64
     print(json.dumps(out), flush=True)
 
 
