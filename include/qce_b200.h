@@ -181,9 +181,13 @@ qce_status qce_mfa_model_set_params(qce_mfa_model* m, void* stream, const double
 qce_status qce_mfa_estimate(qce_mfa_model* m, void* stream, const void* r_dev, int64_t B, int mode, int n_top, double rho,
                             void* h_est_dev, double* logp_out_dev, const void* h_true_dev, double* acc_dev);
 
-/* Host-buffer form of qce_estimate: r_host c128 [B][n_obs] -> h_est_host c128 [B][n_ant].  Copies are
- * chunked through pinned staging buffers owned by the model and overlapped with the kernels on the
- * model's own streams; returns after the last chunk has landed in h_est_host (synchronous). */
+/* Host-buffer form of qce_estimate: r_host c128 [B][n_obs] -> h_est_host c128 [B][n_ant].  Copies are chunked (32 MiB, four chunks
+ * in flight) and overlapped with the kernels on private streams; the streams and the pinned + device staging slots belong to the model
+ * handle (created on the first host-buffer call, freed with the model).  Calls on the same model take turns, calls on different
+ * models run concurrently; the private streams wait on an event recorded after the model's last parameter upload -- no device-wide
+ * synchronisation.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly, pageable
+ * ones through the pinned slots.  Returns after the last chunk has landed in h_est_host (synchronous).  The calling thread's current
+ * device must be the one the model was created on (QCE_ERR_INVALID otherwise). */
 qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho,
                              int precision, void* h_est_host);
 /* The same for the circulant / block-circulant and the Woodbury-MFA models (r_host and h_est_host c128 [B][n_ant]). */

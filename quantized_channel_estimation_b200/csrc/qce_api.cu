@@ -36,9 +36,10 @@ void set_error(const char* fmt, ...) {
 
 using namespace qce;
 
-namespace {
-struct HostStaging {            // qce_estimate_host: double-buffered pinned + device staging, shared by all models
+struct HostCtx {                // staging of ONE model's host-buffer calls: double-buffered pinned + device slots on private streams
     static constexpr int NSLOT = 4;  // chunks in flight: keeps the H2D and the D2H copy engines busy back to back
+    std::mutex mu;              // calls on the same model take turns; different models run concurrently
+    int device = -1;
     cudaStream_t streams[NSLOT] = {};
     cudaEvent_t done[NSLOT] = {};
     void* pin_in[NSLOT] = {};
@@ -47,7 +48,27 @@ struct HostStaging {            // qce_estimate_host: double-buffered pinned + d
     void* dev_out[NSLOT] = {};
     size_t in_bytes = 0, out_bytes = 0;
 };
-HostStaging g_staging;
+
+void host_ctx_free(HostCtx* c) {
+    if (!c) return;
+    for (int i = 0; i < HostCtx::NSLOT; ++i) {
+        if (c->streams[i]) { cudaStreamSynchronize(c->streams[i]); tc_scratch_release(c->streams[i]); cudaStreamDestroy(c->streams[i]); }
+        if (c->done[i]) cudaEventDestroy(c->done[i]);
+        if (c->pin_in[i]) cudaFreeHost(c->pin_in[i]);
+        if (c->pin_out[i]) cudaFreeHost(c->pin_out[i]);
+        if (c->dev_in[i]) cudaFree(c->dev_in[i]);
+        if (c->dev_out[i]) cudaFree(c->dev_out[i]);
+    }
+    delete c;
+}
+
+namespace {
+std::mutex g_host_create_mu;
+HostCtx* host_ctx_get(HostCtx** slot) {
+    std::lock_guard<std::mutex> lock(g_host_create_mu);
+    if (!*slot) *slot = new HostCtx();
+    return *slot;
+}
 
 // Pageable caller buffers are staged through pinned memory by the calling thread; one memcpy stream moves ~8 GB/s, far below
 // PCIe, so large copies are split over a few threads.
@@ -68,7 +89,6 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     memcpy(dst, src, piece < bytes ? piece : bytes);
     for (auto& t : th) t.join();
 }
-std::mutex g_staging_mu;          // one host-path call at a time (the slots are shared by all models)
 }  // namespace
 
 extern "C" {
@@ -162,6 +182,8 @@ qce_status qce_model_create(int n_obs, int n_ant, int n_comp, int flags, qce_mod
     if (st) return st;
     qce_model* m = new qce_model();
     m->n_obs = n_obs; m->n_ant = n_ant; m->n_comp = n_comp; m->flags = flags;
+    m->device = current_device();
+    cudaEventCreateWithFlags(&m->params_ready, cudaEventDisableTiming);
     const size_t K = n_comp, No = n_obs, N = n_ant;
     cudaError_t e = cudaMalloc(&m->Linv, K * No * No * 16);
     if (e == cudaSuccess) e = cudaMalloc(&m->W, K * N * No * 16);
@@ -179,6 +201,8 @@ qce_status qce_model_create(int n_obs, int n_ant, int n_comp, int flags, qce_mod
 
 void qce_model_destroy(qce_model* m) {
     if (!m) return;
+    host_ctx_free(m->host);
+    if (m->params_ready) cudaEventDestroy(m->params_ready);
     tc_free(m);
     cudaFree(m->Linv); cudaFree(m->W); cudaFree(m->zoff); cudaFree(m->hoff); cudaFree(m->logc);
     if (m->pipe_r) cudaFree(m->pipe_r);
@@ -202,6 +226,7 @@ qce_status qce_model_set_params(qce_model* m, void* stream, const double* Linv, 
         qce_status st = tc_pack_params(m, s);
         if (st) return st;
     }
+    QCE_CUDA_TRY(cudaEventRecord(m->params_ready, s));
     return QCE_OK;
 }
 
@@ -305,6 +330,8 @@ qce_status qce_circ_model_create(int n1, int n2, int n_comp, int flags, qce_circ
     if (st) return st;
     qce_circ_model* m = new qce_circ_model();
     m->n1 = n1; m->n2 = n2; m->n_ant = n1 * n2; m->n_comp = n_comp; m->flags = flags;
+    m->device = current_device();
+    cudaEventCreateWithFlags(&m->params_ready, cudaEventDisableTiming);
     const size_t N = m->n_ant, K = n_comp;
     cudaError_t e = cudaMalloc(&m->inv_lambda_t, N * K * 8);
     if (e == cudaSuccess) e = cudaMalloc(&m->gain, N * K * 8);
@@ -316,6 +343,8 @@ qce_status qce_circ_model_create(int n1, int n2, int n_comp, int flags, qce_circ
 
 void qce_circ_model_destroy(qce_circ_model* m) {
     if (!m) return;
+    host_ctx_free(m->host);
+    if (m->params_ready) cudaEventDestroy(m->params_ready);
     circ_tc_free(m);
     cudaFree(m->inv_lambda_t); cudaFree(m->gain); cudaFree(m->logc);
     delete m;
@@ -329,7 +358,10 @@ qce_status qce_circ_model_set_params(qce_circ_model* m, void* stream, const doub
     QCE_CUDA_TRY(cudaMemcpyAsync(m->gain, gain, N * K * 8, cudaMemcpyDeviceToDevice, s));
     QCE_CUDA_TRY(cudaMemcpyAsync(m->logc, logc, K * 8, cudaMemcpyDeviceToDevice, s));
     m->params_set = true;
-    return circ_tc_pack(m, s);
+    qce_status st = circ_tc_pack(m, s);
+    if (st) return st;
+    QCE_CUDA_TRY(cudaEventRecord(m->params_ready, s));
+    return QCE_OK;
 }
 
 qce_status qce_circ_estimate_prec(qce_circ_model* m, void* stream, const void* r, int64_t B, int mode, int n_top, double rho, int precision,
@@ -354,6 +386,8 @@ qce_status qce_mfa_model_create(int n_ant, int latent, int n_comp, int flags, qc
     if (st) return st;
     qce_mfa_model* m = new qce_mfa_model();
     m->n_ant = n_ant; m->latent = latent; m->n_comp = n_comp; m->flags = flags;
+    m->device = current_device();
+    cudaEventCreateWithFlags(&m->params_ready, cudaEventDisableTiming);
     const size_t N = n_ant, M2 = 2 * (size_t)latent, K = n_comp;
     cudaError_t e = cudaMalloc(&m->inv_delta, K * N * 8);
     if (e == cudaSuccess) e = cudaMalloc(&m->evec, K * N * 8);
@@ -369,6 +403,8 @@ qce_status qce_mfa_model_create(int n_ant, int latent, int n_comp, int flags, qc
 
 void qce_mfa_model_destroy(qce_mfa_model* m) {
     if (!m) return;
+    host_ctx_free(m->host);
+    if (m->params_ready) cudaEventDestroy(m->params_ready);
     cudaFree(m->inv_delta); cudaFree(m->evec); cudaFree(m->D); cudaFree(m->Y); cudaFree(m->m_r); cudaFree(m->mu); cudaFree(m->logc);
     delete m;
 }
@@ -386,6 +422,7 @@ qce_status qce_mfa_model_set_params(qce_mfa_model* m, void* stream, const double
     QCE_CUDA_TRY(cudaMemcpyAsync(m->mu, mu, K * N * 16, cudaMemcpyDeviceToDevice, s));
     QCE_CUDA_TRY(cudaMemcpyAsync(m->logc, logc, K * 8, cudaMemcpyDeviceToDevice, s));
     m->params_set = true;
+    QCE_CUDA_TRY(cudaEventRecord(m->params_ready, s));
     return QCE_OK;
 }
 
@@ -416,12 +453,18 @@ qce_status qce_estimate_formatted(qce_model* m, void* stream, int64_t B, void* h
 // stay busy back to back.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly;
 // pageable ones go through the pinned staging slots.  `run(stream, dev_in, rows, dev_out)` enqueues the estimate of one chunk.
 template <typename Run>
-static qce_status estimate_host_impl(size_t n_in, size_t n_out, const void* r_host, int64_t B, void* h_est_host, Run run) {
+static qce_status estimate_host_impl(HostCtx** ctx_slot, int model_device, cudaEvent_t params_ready, size_t n_in, size_t n_out,
+                                     const void* r_host, int64_t B, void* h_est_host, Run run) {
     const size_t in_row = n_in * 16, out_row = n_out * 16;
-    std::lock_guard<std::mutex> lock(g_staging_mu);
-    HostStaging* hs = &g_staging;
+    if (current_device() != model_device) {
+        set_error("host-buffer estimate: the model lives on device %d, the calling thread's current device is %d", model_device, current_device());
+        return QCE_ERR_INVALID;
+    }
+    HostCtx* hs = host_ctx_get(ctx_slot);
+    std::lock_guard<std::mutex> lock(hs->mu);
+    hs->device = model_device;
     const size_t slot_bytes = (size_t)32 << 20;
-    constexpr int NSLOT = HostStaging::NSLOT;
+    constexpr int NSLOT = HostCtx::NSLOT;
     int64_t chunk = (int64_t)(slot_bytes / (in_row > out_row ? in_row : out_row));
     if (chunk < 128) chunk = 128;
     {
@@ -445,8 +488,9 @@ static qce_status estimate_host_impl(size_t n_in, size_t n_out, const void* r_ho
         if (hs->in_bytes < need_in) hs->in_bytes = need_in;
         if (hs->out_bytes < need_out) hs->out_bytes = need_out;
     }
-    // parameters were packed on the caller's stream: make them visible to the private streams
-    QCE_CUDA_TRY(cudaDeviceSynchronize());
+    // parameters were uploaded / packed on the caller's stream: the private streams wait for that upload (an event, not a device-wide
+    // synchronisation: other streams of the process are left alone)
+    for (int i = 0; i < NSLOT; ++i) QCE_CUDA_TRY(cudaStreamWaitEvent(hs->streams[i], params_ready, 0));
     const int64_t nchunks = (B + chunk - 1) / chunk;
     auto is_pinned = [](const void* p) {
         cudaPointerAttributes at;
@@ -492,7 +536,7 @@ extern "C" {
 qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
                              void* h_est_host) {
     if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
-    return estimate_host_impl((size_t)m->n_obs, (size_t)m->n_ant, r_host, B, h_est_host,
+    return estimate_host_impl(&m->host, m->device, m->params_ready, (size_t)m->n_obs, (size_t)m->n_ant, r_host, B, h_est_host,
                               [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
                                   return estimate_impl(m, s, din, nb, mode, n_top, rho, precision, dout, nullptr, nullptr, 0, nullptr);
                               });
@@ -501,7 +545,7 @@ qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mo
 qce_status qce_circ_estimate_host(qce_circ_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
                                   void* h_est_host) {
     if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_circ_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
-    return estimate_host_impl((size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
+    return estimate_host_impl(&m->host, m->device, m->params_ready, (size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
                               [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
                                   return qce_circ_estimate_prec(m, (void*)s, din, nb, mode, n_top, rho, precision, dout, nullptr, nullptr, nullptr);
                               });
@@ -509,7 +553,7 @@ qce_status qce_circ_estimate_host(qce_circ_model* m, const void* r_host, int64_t
 
 qce_status qce_mfa_estimate_host(qce_mfa_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, void* h_est_host) {
     if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_mfa_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
-    return estimate_host_impl((size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
+    return estimate_host_impl(&m->host, m->device, m->params_ready, (size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
                               [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
                                   return qce_mfa_estimate(m, (void*)s, din, nb, mode, n_top, rho, dout, nullptr, nullptr, nullptr);
                               });

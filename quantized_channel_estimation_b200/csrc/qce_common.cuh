@@ -85,8 +85,16 @@ struct TcParams {
     int part_cols = 0;          // real columns (of the 2 n_ant) per row block
 };
 
+// host-buffer entry points: every model owns its staging (pinned + device slots, streams; created on first use, qce_api.cu) and an
+// event recorded after the last parameter upload, which the staging streams wait on
+struct HostCtx;
+void host_ctx_free(HostCtx* c);
+
 struct qce_circ_model {
     int n1, n2, n_ant, n_comp, flags;
+    int device = 0;
+    HostCtx* host = nullptr;
+    cudaEvent_t params_ready = nullptr;
     double* inv_lambda_t = nullptr;   // [N][K]  1 / eigenvalues of C_r,k, transposed for coalesced access
     double* gain = nullptr;           // [K][N]  b_k c_k / lambda_k
     double* logc = nullptr;           // [K]
@@ -104,6 +112,9 @@ struct qce_circ_model {
 
 struct qce_mfa_model {
     int n_ant, latent, n_comp, flags;
+    int device = 0;
+    HostCtx* host = nullptr;
+    cudaEvent_t params_ready = nullptr;
     double* inv_delta = nullptr;      // [K][N]
     double* evec = nullptr;           // [K][N]
     double* D = nullptr;              // c128 [K][2M][N]
@@ -116,6 +127,9 @@ struct qce_mfa_model {
 
 struct qce_model {
     int n_obs, n_ant, n_comp, flags;
+    int device = 0;
+    HostCtx* host = nullptr;
+    cudaEvent_t params_ready = nullptr;
     // fp64 parameter copies (device)
     double* Linv = nullptr;     // c128 [K][No][No]
     double* W = nullptr;        // c128 [K][N][No]
@@ -274,6 +288,7 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
                               const double* noise, double noise_scale, int64_t B, int mode, int n_top, double rho, double* h_est,
                               double* acc);
 bool tc_supported(const qce_model* m, int mode);
+void tc_scratch_release(cudaStream_t s);
 // qce_mfa.cu
 qce_status launch_mfa(const qce_mfa_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top, double rho,
                       double* h_est, double* logp_out, const double* h_true, double* acc);

@@ -1273,6 +1273,16 @@ static qce_status tc_scratch(const qce_model* m, cudaStream_t s, int64_t rows, T
     return QCE_OK;
 }
 
+// a stream is about to be destroyed (the private streams of a model's host-buffer path): free its scratch
+void tc_scratch_release(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    auto it = g_scratch.find(std::make_pair(current_device(), s));
+    if (it == g_scratch.end()) return;
+    TileScratch& t = it->second;
+    cudaFree(t.img); cudaFree(t.bad); cudaFree(t.lp2); cudaFree(t.wts); cudaFree(t.img2); cudaFree(t.bidx); cudaFree(t.fix_buf); cudaFree(t.tie_buf);
+    g_scratch.erase(it);
+}
+
 // complex128 re-evaluation of the rows on the fix list (pilots off the tensor-core grid, hard selections too close to call): they
 // were neither written nor accumulated by the tensor-core launches.  The list is short (typically 1e-4 of the batch), its length
 // lives on the device: the launch is sized independently of it.

@@ -158,3 +158,26 @@ def test_baselines(golden_baselines, tag):
     assert relerr(orc.blmmse_estimate_genie(r, g['t'], snr, A, nb, qt, qz), g[tag + '_blmmse_genie']) < 1e-11
     if tag + '_ls_genie' in g:
         assert relerr(orc.ls_estimate_genie(r, g['t'], snr, A, nb, qt, qz), g[tag + '_ls_genie']) < 1e-12
+
+
+def test_oracle_vs_vendored_reference():
+    """Second pin of the oracle: the UNMODIFIED reference modules vendored by oracle/build_ref.py (where they exist), run here on a
+    fresh seeded case that is in no fixture -- all four combination modes, 2-bit uniform pilots, non-zero means."""
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip('oracle/_ref not built (run python oracle/build_ref.py where /root/reference exists)')
+    Gmm_nbit, _, ut = build_ref.import_reference()
+    K, N, B, snr, nb = 5, 12, 40, 7, 2
+    means, covs, w = orc.random_psd_gmm(K, N, seed=31, mean_scale=0.2)
+    h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=32)
+    qz = ut.get_quantizer_gauss([snr], nb, 'uniform')[snr]
+    r = orc.get_observation_nbit(h, snr, noise, None, nb, qz[0], qz[1])
+    assert _bits_equal(r, ut.quant(h + 10 ** (-snr / 20) * noise, nb, qz[0], qz[1]))
+    for mode in ('all', 1, 2, 0.8):
+        g = Gmm_nbit(n_components=K, covariance_type='full')
+        g.params['zero_mean'] = False
+        g.means_cplx, g.covs_cplx = means.copy(), covs.copy()
+        g.gm.weights_ = w.copy()
+        ref = g.estimate_from_y(r, snr, N, None, mode, nb, 'uniform', qz)
+        est = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type='uniform', quantizer=qz)
+        assert relerr(est, ref) < 1e-12, mode
