@@ -1,12 +1,15 @@
 """Training (EM) for the complex GMM and the mixture of factor analysers -- SURVEY.md section 8f-1, the first row
-after the inference hot path.  Torch float64 / complex128 on the GPU when there is one (batched GEMMs, Cholesky: cuBLAS /
-cuSOLVER "plumbing"; training is not the path the hand-written kernels accelerate).
+after the inference hot path.  On a GPU the E-step of the 'full' / Toeplitz GMM is the whitening launch of the inference path
+(``engine.DenseModel.log_prob``: the same ``l_k = logc_k - |L_k^-1 x - L_k^-1 mu_k|^2`` on the tensor cores, three-pass split for
+unquantised data, shapes zero-padded to the next instantiated one; near-ties do not matter for soft responsibilities) and the
+M-step is one batched GEMM over all components; the per-iteration Cholesky factors are cuSOLVER "plumbing".  Everything else is
+torch float64 / complex128.
 
 GMM (reference modules/gmm_cplx_bussgang.py:96-163, 437-848): sklearn-style EM on complex data -- k-means initialisation
 on the (Re, Im) features, E-step with Cholesky-whitened complex Gaussian log-densities, M-step with weighted sample
 covariances + ``reg_covar``, stop when the mean log-likelihood changes by less than ``tol``; ``n_init`` restarts.
 'circulant' / 'block-circulant' run the diagonal EM in the (2-D) DFT domain and densify afterwards, as the reference does.
-The Toeplitz types (Barton-Fuhrmann inverse EM, gmm:787-816) are not implemented yet.
+The Toeplitz types run the Barton-Fuhrmann inverse EM on the twofold-oversampled DFT grid (gmm:787-826).
 
 MFA (reference modules/mofa_cplx_bussgang.py:94-113, 219-339, 403-421): k-means means, random small loadings, per-component
 EM with Woodbury inverses, optional PPCA / locked psis.
@@ -75,12 +78,27 @@ def _m_step(X, resp, reg_covar, diag, zero_mean):
         avg_xm = (means.conj() * ((resp.T.to(X.dtype) @ X) / nk[:, None])).real
         covs = avg_x2 - 2 * avg_xm + (means.real ** 2 + means.imag ** 2) + reg_covar
     else:                                                               # gmm:730-766
-        covs = torch.empty((K, N, N), dtype=X.dtype, device=X.device)
-        eye = torch.eye(N, dtype=X.dtype, device=X.device)
-        for k in range(K):
-            diff = X - means[k]
-            covs[k] = (diff.T * resp[:, k]) @ diff.conj() / nk[k] + reg_covar * eye
+        covs = _weighted_scatter(X, resp, nk, means) + reg_covar * torch.eye(N, dtype=X.dtype, device=X.device)
     return nk, means, covs
+
+
+def _weighted_scatter(X, resp, nk, means, chunk=4096):
+    """``S_k = sum_b r_bk (x_b - mu_k)(x_b - mu_k)^T*`` / n_k for all components at once: one GEMM ``resp^T [K, B] x (x x^H) [B, N^2]``
+    per chunk of samples instead of a Python loop of K weighted Gram products, then the rank-one mean terms (with ``mu_k`` the
+    resp-weighted mean -- or zero -- the centred form equals the raw second moment minus mean terms)."""
+    B, N = X.shape
+    K = resp.shape[1]
+    S = torch.zeros((K, N * N), dtype=X.dtype, device=X.device)
+    rT = resp.T.to(X.dtype)
+    for b0 in range(0, B, chunk):
+        xb = X[b0:b0 + chunk]
+        outer = (xb[:, :, None] * xb.conj()[:, None, :]).reshape(xb.shape[0], N * N)
+        S += rT[:, b0:b0 + chunk] @ outer
+    S = S.reshape(K, N, N) / nk[:, None, None]
+    xbar = (rT @ X) / nk[:, None]                                       # resp-weighted sample means
+    # sum r (x - m)(x - m)^H / n = S - xbar m^H - m xbar^H + m m^H
+    m = means
+    return S - xbar[:, :, None] * m.conj()[:, None, :] - m[:, :, None] * xbar.conj()[:, None, :] + m[:, :, None] * m.conj()[:, None, :]
 
 
 def _m_step_inv(X, resp, reg_covar, zero_mean, covs_prev, Sigma, F2):
@@ -95,13 +113,41 @@ def _m_step_inv(X, resp, reg_covar, zero_mean, covs_prev, Sigma, F2):
     covs = torch.empty((K, N, N), dtype=X.dtype, device=X.device)
     eye = torch.eye(N, dtype=X.dtype, device=X.device)
     Cinv = torch.linalg.pinv(covs_prev, hermitian=True)
+    S_all = _weighted_scatter(X, resp, nk, means)                       # one batched GEMM for all components
     for k in range(K):
-        diff = X - means[k]
-        S = (diff.T * resp[:, k]) @ diff.conj() / nk[k]
+        S = S_all[k]
         theta = ((F2 @ (Cinv[k] @ S @ Cinv[k] - Cinv[k])) * F2.conj()).sum(1).real
         Sigma[k] = (Sigma[k] + Sigma[k] ** 2 * theta).clamp(min=reg_covar)
         covs[k] = (F2.conj().T * Sigma[k]) @ F2 + reg_covar * eye
     return nk, means, covs
+
+
+class _KernelEStep:
+    """E-step of the full-covariance GMM on the inference path's whitening launch (GPU only): the mixture is loaded into a
+    ``qce_model`` with a zero LMMSE block and ``log_prob`` returns ``l [B, K]`` -- the quantity ``_log_prob`` computes with K
+    triangular solves in torch."""
+
+    def __init__(self, X):
+        from . import engine
+        self.engine, self.X, self.model = engine, X.contiguous(), None
+        self.ok = X.is_cuda and engine.tc_padded_shape(X.shape[1], X.shape[1]) is not None
+
+    def log_prob(self, weights, means, covs):
+        K, N = means.shape
+        L, info = torch.linalg.cholesky_ex(covs)
+        if int(info.max()) != 0:
+            raise ValueError(precompute.NOT_PD_MSG)
+        eye = torch.eye(N, dtype=covs.dtype, device=covs.device)
+        Linv = torch.linalg.solve_triangular(L, eye.expand(K, N, N), upper=False)
+        logdet = 2 * torch.log(torch.diagonal(L, dim1=1, dim2=2).real).sum(1)
+        prep = dict(Linv=Linv.contiguous(), W=torch.zeros_like(Linv), zoff=(Linv @ means[:, :, None])[:, :, 0].contiguous(),
+                    hoff=torch.zeros_like(means), logc=(torch.log(weights) - N * math.log(math.pi) - logdet).contiguous(),
+                    data_scale=0.0, n_obs=N, n_ant=N, n_comp=K)             # data_scale 0: unquantised data (three-pass split)
+        if self.model is None:
+            self.model = self.engine.DenseModel(prep, pad=True)
+        else:
+            self.model.update(prep)
+        return self.model.log_prob(self.X, 'auto')
 
 
 def _log_prob(X, weights, means, covs, diag):
@@ -130,6 +176,7 @@ def _em_gmm(X, K, diag, zero_mean, reg_covar, tol, max_iter, n_init, init_params
     B = X.shape[0]
     best = None
     converged_any = False
+    kernel_e = _KernelEStep(X) if not diag else None
     for init in range(n_init):
         if init_params == 'kmeans':                                     # gmm:560-567
             labels = kmeans_labels(torch.cat([X.real, X.imag], 1), K, gen)
@@ -147,7 +194,10 @@ def _em_gmm(X, K, diag, zero_mean, reg_covar, tol, max_iter, n_init, init_params
         lower, converged, n_iter = -np.inf, False, 0
         for n_iter in range(1, max_iter + 1):
             prev = lower
-            wlp = _log_prob(X, weights, means, covs, diag)              # E-step (gmm:612-650)
+            if kernel_e is not None and kernel_e.ok:                    # E-step (gmm:612-650) on the whitening launch
+                wlp = kernel_e.log_prob(weights, means, covs)
+            else:
+                wlp = _log_prob(X, weights, means, covs, diag)
             lpn = torch.logsumexp(wlp, 1)
             resp = torch.exp(wlp - lpn[:, None])
             if F2 is None:
@@ -164,7 +214,8 @@ def _em_gmm(X, K, diag, zero_mean, reg_covar, tol, max_iter, n_init, init_params
         converged_any |= converged
         if best is None or lower > best[0]:
             best = (lower, weights, means, covs, n_iter, converged)
-    if not best[5]:
+    best = best[:5] + (converged_any,)                                  # sklearn keeps converged_ sticky over the n_init restarts
+    if not converged_any:
         warnings.warn('EM did not converge. Try different init parameters, or increase max_iter, tol or check for degenerate data.')
     return best
 

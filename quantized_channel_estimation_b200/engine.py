@@ -36,6 +36,35 @@ def tc_shape_ok(n_obs, n_ant):
     return (n_obs, n_ant) in ((128, 64), (128, 128), (96, 48), (96, 96))
 
 
+def tc_padded_shape(n_obs, n_ant):
+    """Smallest tensor-core shape that holds an (n_obs, n_ant) model after zero padding (None: there is none).  Padded rows / columns
+    of the parameter blocks are zero, padded pilot entries are zero: they add exact zeros to the quadratic forms and produce estimate
+    entries that are cut off again."""
+    if tc_shape_ok(n_obs, n_ant):
+        return n_obs, n_ant
+    up = lambda x: -(-x // 16) * 16
+    cands = [(o, a) for o in (16, 32, 48, 64, 96, 128) for a in (16, 32, 48, 64, 96, 128)
+             if o >= n_obs and a >= n_ant and tc_shape_ok(o, a)]
+    return min(cands, key=lambda c: c[0] * (c[0] + c[1])) if cands else None
+
+
+def _pad_prep(prep, No_p, N_p):
+    """Zero-pad the parameter blocks of ``precompute.prepare`` to (No_p, N_p)."""
+    K, No, N = int(prep['n_comp']), int(prep['n_obs']), int(prep['n_ant'])
+    out = dict(prep)
+    dev = prep['Linv'].device
+
+    def z(*shape):
+        return torch.zeros(shape, dtype=torch.complex128, device=dev)
+    Linv, W, zoff, hoff = z(K, No_p, No_p), z(K, N_p, No_p), z(K, No_p), z(K, N_p)
+    Linv[:, :No, :No] = prep['Linv']
+    W[:, :N, :No] = prep['W']
+    zoff[:, :No] = prep['zoff']
+    hoff[:, :N] = prep['hoff']
+    out.update(Linv=Linv, W=W, zoff=zoff, hoff=hoff, n_obs=No_p, n_ant=N_p)
+    return out
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -124,18 +153,42 @@ def observe_quantize(h, noise, noise_scale, quantizer=None, want_y=False, want_c
 class DenseModel:
     """One (SNR, bit width, quantiser) parameter set resident on the GPU (qce_model)."""
 
-    def __init__(self, prep, flags=0):
+    def __init__(self, prep, flags=0, pad=False):
+        """``pad=True``: a shape the tensor-core kernels are not instantiated for (n_obs / n_ant not multiples of 16, or an unlisted
+        pair) is zero-padded to the next one that is, instead of running on the complex128 kernel (~100x slower)."""
         lib = _lib.require_device()
         self.n_obs, self.n_ant, self.n_comp = int(prep['n_obs']), int(prep['n_ant']), int(prep['n_comp'])
+        self.pad_obs, self.pad_ant = self.n_obs, self.n_ant          # shape of the library handle
+        if pad and not tc_shape_ok(self.n_obs, self.n_ant):
+            ps = tc_padded_shape(self.n_obs, self.n_ant)
+            if ps is not None:
+                self.pad_obs, self.pad_ant = ps
         self.handle = C.c_void_p()
-        _lib.check(lib.qce_model_create(self.n_obs, self.n_ant, self.n_comp, int(flags), C.byref(self.handle)))
-        dev = torch.device('cuda', torch.cuda.current_device())
-        t = {k: prep[k].to(dev).contiguous() for k in ('Linv', 'W', 'zoff', 'hoff', 'logc')}
+        _lib.check(lib.qce_model_create(self.pad_obs, self.pad_ant, self.n_comp, int(flags), C.byref(self.handle)))
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.update(prep)
+
+    @property
+    def padded(self):
+        return (self.pad_obs, self.pad_ant) != (self.n_obs, self.n_ant)
+
+    def update(self, prep):
+        """(Re)load the parameter blocks of ``precompute.prepare`` (same shape): ``fit()`` calls this once per EM iteration."""
+        if self.padded:
+            prep = _pad_prep(prep, self.pad_obs, self.pad_ant)
+        t = {k: prep[k].to(self.device).contiguous() for k in ('Linv', 'W', 'zoff', 'hoff', 'logc')}
         assert t['Linv'].dtype == torch.complex128 and t['logc'].dtype == torch.float64
-        _lib.check(lib.qce_model_set_params(self.handle, _stream(), _ptr(t['Linv']), _ptr(t['W']), _ptr(t['zoff']),
-                                            _ptr(t['hoff']), _ptr(t['logc']), float(prep['data_scale'])))
-        torch.cuda.current_stream().synchronize()      # the library copied the blocks; t may now be freed
-        self.device = dev
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().qce_model_set_params(self.handle, _stream(), _ptr(t['Linv']), _ptr(t['W']), _ptr(t['zoff']),
+                                                        _ptr(t['hoff']), _ptr(t['logc']), float(prep['data_scale'])))
+            torch.cuda.current_stream().synchronize()      # the library copied the blocks; t may now be freed
+
+    def _pad_in(self, r):
+        if self.pad_obs == self.n_obs:
+            return r
+        out = torch.zeros((r.shape[0], self.pad_obs), dtype=r.dtype, device=r.device)
+        out[:, :self.n_obs] = r
+        return out
 
     def __del__(self):
         try:
@@ -168,16 +221,23 @@ class DenseModel:
         if r.dim() != 2 or r.shape[1] != self.n_obs:
             raise ValueError(f'y must be [B, {self.n_obs}]')
         B = r.shape[0]
-        h_est = torch.empty((B, self.n_ant), dtype=torch.complex128, device=r.device)
+        r = self._pad_in(r)
+        h_est = torch.empty((B, self.pad_ant), dtype=torch.complex128, device=r.device)
         logp = torch.empty((B, self.n_comp), dtype=torch.float64, device=r.device) if want_logp else None
         acc = None
         if h_true is not None:
             h_true = _as_c128_cuda(h_true, 'h_true')
+            if self.pad_ant != self.n_ant:
+                ht = torch.zeros((B, self.pad_ant), dtype=h_true.dtype, device=h_true.device)
+                ht[:, :self.n_ant] = h_true
+                h_true = ht
             acc = torch.zeros(3, dtype=torch.float64, device=r.device)
         lib = _lib.load()
         with torch.cuda.device(r.device):
             self._call(precision, mode, lambda p: lib.qce_estimate(self.handle, _stream(), _ptr(r), B, mode, n_top, rho, p,
                                                                    _ptr(h_est), _ptr(logp), _ptr(h_true), _ptr(acc)))
+        if self.pad_ant != self.n_ant:
+            h_est = h_est[:, :self.n_ant].contiguous()
         out = (h_est,)
         if want_logp:
             out += (logp,)
@@ -185,12 +245,29 @@ class DenseModel:
             out += (acc,)
         return out if len(out) > 1 else h_est
 
+    def log_prob(self, r, precision='auto'):
+        """Weighted log-probabilities ``l [B, K]`` float64 only (no estimate: the library skips the combination launches)."""
+        r = _as_c128_cuda(r, 'y')
+        if r.dim() != 2 or r.shape[1] != self.n_obs:
+            raise ValueError(f'y must be [B, {self.n_obs}]')
+        B = r.shape[0]
+        r = self._pad_in(r)
+        logp = torch.empty((B, self.n_comp), dtype=torch.float64, device=r.device)
+        lib = _lib.load()
+        with torch.cuda.device(r.device):
+            self._call(precision, _lib.MODE_ALL, lambda p: lib.qce_estimate(self.handle, _stream(), _ptr(r), B, _lib.MODE_ALL, 0, 0.0, p,
+                                                                            None, _ptr(logp), None, None))
+        return logp
+
     def estimate_host(self, r, n_summands_or_proba='all', precision='auto'):
         """r: numpy c128 [B, n_obs] (host) -> numpy c128 [B, n_ant]; copies run inside the library."""
         mode, n_top, rho = parse_mode(n_summands_or_proba)
         r = np.ascontiguousarray(np.asarray(r, dtype=np.complex128))
         if r.ndim != 2 or r.shape[1] != self.n_obs:
             raise ValueError(f'y must be [B, {self.n_obs}]')
+        if self.padded:       # padded models: pad on the device (the host path of the library moves whole rows)
+            est = self.estimate(torch.from_numpy(r).to(self.device), n_summands_or_proba, precision)
+            return est.cpu().numpy()
         out = np.empty((r.shape[0], self.n_ant), dtype=np.complex128)
         lib = _lib.load()
         with torch.cuda.device(self.device):
@@ -202,6 +279,8 @@ class DenseModel:
                  acc=None):
         """observe -> quantise -> estimate -> NMSE accumulators for device-resident channels (A = I)."""
         mode, n_top, rho = parse_mode(n_summands_or_proba)
+        if self.padded:
+            raise ValueError('pipeline(): zero-padded models are not supported (create the DenseModel with pad=False)')
         h_c64 = h.dtype == torch.complex64
         if not h_c64:
             h = h.to(torch.complex128)
@@ -262,6 +341,9 @@ class CircModel:
         if h_true is not None:
             out += (acc,)
         return out if len(out) > 1 else h_est
+
+    def log_prob(self, r, precision='auto'):
+        return self.estimate(r, 'all', precision, want_logp=True)[1]
 
     def _run(self, precision, head, tail):
         """'fp64': complex128 kernel; 'tc': FP32-FFT / tensor-core kernel (16 x 16 blocks, K = 64 or 128); 'auto': the latter

@@ -164,13 +164,14 @@ class Gmm_nbit:
         A = np.asarray(A)
         nb = 'inf' if (n_bits == 'inf' or n_bits == np.inf) else int(n_bits)
         tables = _table_key(quantizer) if (nb != 1 and nb != 'inf' and quantizer_type == 'lloyd') else None
+        pad = self.precision != 'fp64'        # shapes the tensor-core kernels do not cover are zero-padded to one they do
         key = (float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, A.shape, A.tobytes(),
-               _fingerprint(self.means_cplx), _fingerprint(self.covs_cplx), _fingerprint(self.gm.weights_))
+               _fingerprint(self.means_cplx), _fingerprint(self.covs_cplx), _fingerprint(self.gm.weights_), pad)
 
         def make():
             prep = precompute.prepare(self.means_cplx, self.covs_cplx, self.gm.weights_, A, snr_dB,
                                       np.inf if nb == 'inf' else nb, quantizer_type, quantizer)
-            return engine.DenseModel(prep, flags=0)
+            return engine.DenseModel(prep, flags=0, pad=pad)
         return self._cache.get(key, make)
 
     def estimate_from_y(self, y, snr_dB, n_antennas, A=None, n_summands_or_proba=1, n_bits=1,
@@ -202,7 +203,8 @@ class Gmm_nbit:
                 A = np.eye(self.means_cplx.shape[1], dtype=complex)
             model = self._last = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
         yt = y if isinstance(y, torch.Tensor) and y.is_cuda else torch.as_tensor(np.asarray(y)).cuda()
-        _, lp = model.estimate(yt, 'all', 'fp64', want_logp=True)
+        # the whitening launch of the estimate path (self.precision: tensor cores when the shape is covered), log-probabilities only
+        lp = model.log_prob(yt, self.precision)
         return lp if isinstance(y, torch.Tensor) and y.is_cuda else lp.cpu().numpy()
 
     _estimate_weighted_log_prob = weighted_log_prob

@@ -77,7 +77,7 @@ class Mofa:
         # pilots on an integer grid and a tensor-core shape: the dense tcgen05 kernels beat the complex128 Woodbury kernel
         # (config 4: 55 M vs 0.9 M estimates/s) although they do 4x the flops
         # (off-grid pilots -- Lloyd-Max labels, unquantised data -- take three tensor passes)
-        if woodbury and self.precision != 'fp64' and engine.tc_shape_ok(A.shape[0], self.D):
+        if woodbury and self.precision != 'fp64' and engine.tc_padded_shape(A.shape[0], self.D) is not None:
             woodbury = False
         if woodbury:
             key = ('woodbury', float(snr_dB), nb, quantizer_type if nb != 'inf' else None, tables, _fingerprint(self.means),
@@ -89,13 +89,14 @@ class Mofa:
                 return engine.MfaModel(prep, flags=_lib.FLAG_TOP1_EXP_ARGMAX)
             self._last = self._cache.get(key, make_w)
             return self._last
+        pad = self.precision != 'fp64'
         key = (float(snr_dB), nb, quantizer_type if nb not in (1, 'inf') else None, tables, A.shape, A.tobytes(),
-               _fingerprint(self.means), _fingerprint(self.covs), _fingerprint(self.amps))
+               _fingerprint(self.means), _fingerprint(self.covs), _fingerprint(self.amps), pad)
 
         def make():
             prep = precompute.prepare(self.means, self.covs, self.amps, A, snr_dB, np.inf if nb == 'inf' else nb,
                                       quantizer_type, quantizer)
-            return engine.DenseModel(prep, flags=_lib.FLAG_TOP1_EXP_ARGMAX)
+            return engine.DenseModel(prep, flags=_lib.FLAG_TOP1_EXP_ARGMAX, pad=pad)
         self._last = self._cache.get(key, make)
         return self._last
 
@@ -117,8 +118,7 @@ class Mofa:
             raise RuntimeError('Mofa.predict_proba: call estimate_from_y (or _prepared) first, like the reference, '
                                'whose predict_proba uses the state left by _prepare_for_prediction')
         dt = data if isinstance(data, torch.Tensor) and data.is_cuda else torch.as_tensor(np.asarray(data)).cuda()
-        _, lp = self._last.estimate(dt, 'all', 'fp64', want_logp=True)
-        return lp
+        return self._last.log_prob(dt, self.precision)
 
     def predict_proba(self, data):
         """Responsibilities ``[B, K]`` for the most recently prepared setting (reference :342-356)."""

@@ -1037,3 +1037,95 @@ def test_last_fix_count_reports_reevaluated_rows(qce):
     bad[[3, 77, 200], 0] = 0.123
     m.estimate_from_y(torch.from_numpy(bad).cuda(), snr, N, n_summands_or_proba='all')
     assert _lib.load().qce_last_fix_count(C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag,ctype,blocks,zm', [('full_zm', 'full', None, True), ('full_mean', 'full', None, False),
+                                                 ('toep', 'toeplitz', None, True)])
+def test_fit_on_gpu_reaches_reference_likelihood(qce, tag, ctype, blocks, zm):
+    """fit() on the GPU -- E-step on the inference path's whitening launch (tensor cores, N = 4 / 8 zero-padded to 16), batched M-step
+    -- against the likelihood the UNMODIFIED reference EM reaches on the same seeded data (tests/golden/fit.npz)."""
+    import warnings
+    from conftest import load_golden
+    from fit_common import avg_loglik, make_data
+    from quantized_channel_estimation_b200 import _lib
+    gold = load_golden('fit')
+    h, true = make_data(tag)
+    g = qce.Gmm_nbit(n_components=3, covariance_type=ctype, random_state=0, max_iter=200, tol=1e-5, n_init=2 if ctype == 'full' else 1)
+    l0 = _lib.launch_count()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        g.fit(h, blocks=blocks, zero_mean=zm)
+    assert _lib.launch_count() - l0 > 10, 'the E-step did not run on the library kernels'
+    ll = avg_loglik(h, g.gm.weights_, g.means_cplx, g.covs_cplx)
+    if ctype == 'full':
+        assert ll > float(gold[f'{tag}_ref_ll']) - 0.02, (ll, float(gold[f'{tag}_ref_ll']))
+        assert ll > float(gold[f'{tag}_true_ll']) - 0.02
+    else:
+        assert abs(ll - float(gold[f'{tag}_ref_ll'])) < 0.02, (ll, float(gold[f'{tag}_ref_ll']))
+
+
+@pytest.mark.gpu
+def test_kernel_estep_matches_torch_log_prob(qce):
+    """The E-step's log-densities from the whitening launch (three-pass tensor-core path, padded shape) against the torch formula."""
+    from quantized_channel_estimation_b200 import em
+    from fit_common import make_data
+    h, (w, means, covs) = make_data('full_mean')
+    X = torch.as_tensor(h, dtype=torch.complex128, device='cuda')
+    wt, mt, ct = (torch.as_tensor(a, device='cuda') for a in (w, means, covs))
+    ks = em._KernelEStep(X)
+    assert ks.ok
+    lp_k = ks.log_prob(wt, mt.to(torch.complex128), ct.to(torch.complex128))
+    lp_t = em._log_prob(X, wt, mt.to(torch.complex128), ct.to(torch.complex128), False)
+    assert float((lp_k - lp_t).abs().max()) < 2e-4 * max(1.0, float(lp_t.abs().max()) / 50)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,K,nb,qt', [(20, 5, 1, 'uniform'), (8, 4, 2, 'uniform'), (40, 6, 3, 'lloyd')])
+def test_tc_zero_padded_shapes(qce, N, K, nb, qt):
+    """Antenna counts that are not multiples of 16 run on the tensor cores zero-padded to the next instantiated shape."""
+    from quantized_channel_estimation_b200.engine import DenseModel
+    B, snr = 300, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, qt, 0.2, seed=N)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    model = m._prepared(np.eye(N), snr, nb, qt, qz)
+    assert isinstance(model, DenseModel) and model.padded
+    for mode in ('all', 1, 2, 0.9):
+        ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz)
+        est = m.estimate_from_y(torch.from_numpy(r).cuda(), snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz).cpu().numpy()
+        assert est.shape == (B, N)
+        per = np.linalg.norm(est - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert relerr(est, ref) < TOL_TC and per.max() < 1e-4, (mode, relerr(est, ref), per.max())
+    # host arrays, responsibilities and the NMSE accumulators go through the padded handle too
+    est_h = m.estimate_from_y(r, snr, N, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+    ref = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
+    assert relerr(est_h, ref) < TOL_TC
+    _, aux = orc.gmm_estimate_from_y(means, covs, w, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz, return_aux=True)
+    np.testing.assert_allclose(m.predict_proba_cplx(r), aux['proba'], atol=2e-4)
+    _, acc = model.estimate(torch.from_numpy(r).cuda(), 'all', 'tc', h_true=torch.from_numpy(h).cuda())
+    np.testing.assert_allclose(acc.cpu().numpy()[0], np.sum(np.abs(ref - h) ** 2), rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_predict_proba_runs_on_the_whitening_launch(qce):
+    """predict_proba_cplx / _predict_cplx with the default precision use the tensor-core whitening launch (log-probabilities only, no
+    combination launches) and agree with the complex128 kernel."""
+    from quantized_channel_estimation_b200 import _lib
+    K, N, B, snr = 16, 64, 4000, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.0, seed=3)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    rt = torch.from_numpy(r).cuda()
+    m.estimate_from_y(rt[:8], snr, N, n_summands_or_proba='all')
+    l0 = _lib.launch_count()
+    p_tc = m.predict_proba_cplx(rt)
+    n_launch = _lib.launch_count() - l0
+    m.precision = 'fp64'
+    m.estimate_from_y(rt[:8], snr, N, n_summands_or_proba='all')
+    p_64 = m.predict_proba_cplx(rt)
+    assert n_launch <= 4                       # format, whitening, selection / export, (empty) complex128 fix-up
+    assert float((p_tc - p_64).abs().max()) < 1e-4
+    m.precision = 'auto'
+    m.estimate_from_y(rt[:8], snr, N, n_summands_or_proba='all')
+    lab = m._predict_cplx(rt)
+    assert float((lab != p_64.argmax(1)).float().mean()) < 1e-3
