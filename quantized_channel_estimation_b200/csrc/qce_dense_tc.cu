@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     unsigned char* sB = smem + NTILES * Cfg::A_TILE_BYTES;
     TcCtrl* ctrl = reinterpret_cast<TcCtrl*>(sB + S * Cfg::STAGE_BYTES);
 
+    if (a.run_flag != nullptr && __ldg(a.run_flag) != a.run_flag_want) return;      // (uniform over the whole grid)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work unit: CG * TILES tiles (256 pilots per CTA); the cluster (CG CTAs) walks the units round-robin
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             float zs_n = __ldg(a.zscale + kb), hs_n = __ldg(a.hscale + kb);
             float2 lc_n = __ldg(a.logc2 + kb);
             const int64_t grow = valid ? src : 0;     // rows past the end read row 0, never write
-            float w_n = (EPI == 2) ? (bucket ? (valid ? 1.f : 0.f) : __ldg(a.w_in + grow * a.K)) : 0.f;
+            float w_n = (EPI == 2) ? (bucket ? (valid ? (a.slot_w ? __ldg(a.slot_w + tile_base + row) : 1.f) : 0.f) : __ldg(a.w_in + grow * a.K)) : 0.f;
             const bool fmt_next = PRO && (unit + unit_step < n_units);
             const int64_t fmt_tile0 = ((unit + unit_step) * CG + rank) * NTILES;
             if (fmt_next && fmt_slot == 0 && lane == 0) fmt_prefetch_unit(a, fmt_tile0, NTILES, Cfg::KD);
@@ -650,6 +651,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             // (flags read here, after the last component: with the fused prologue they are written by other warps of this kernel)
             if (EPI != 1 && valid && (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) == 0) {
                 const float invs = EPI == 2 ? 1.f : 1.f / ssum;
+                if (EPI == 2 && a.slot_w) {      // pair mode: this slot's weighted row is one of several addends of the pilot's estimate:
+                    // vector reductions (4 floats each) into the FP32 row of the pilot; tc_pair_finish_kernel writes the estimate
+                    float4* out = reinterpret_cast<float4*>(a.pair_acc + (size_t)g * 2 * N + a.h_col0);
+                    #pragma unroll
+                    for (int j = 0; j < NH / 4; ++j) atomicAdd(out + j, make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y));
+                } else {
                 if (a.h_est) {
                     double2* out = a.h_est + g * N + (a.h_col0 >> 1);
                     #pragma unroll
@@ -674,6 +681,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     pw += (double)pwf;
                 }
                 cnt += 1.0;
+                }
             }
         }
         if (a.prof && blockIdx.x == 0 && lane == 0 && wq == 0) {
@@ -1040,7 +1048,8 @@ template <int PER, bool EXACT = false>
 __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho,
                                                         int flags, float* __restrict__ w_out, double* __restrict__ logp_out,
                                                         int* __restrict__ top_out, const unsigned char* __restrict__ bad, int* __restrict__ tie_buf,
-                                                        double tie_eps, const int* __restrict__ list, const double* __restrict__ logc, double inv_nobs) {
+                                                        double tie_eps, const int* __restrict__ list, const double* __restrict__ logc, double inv_nobs,
+                                                        int* __restrict__ pair_cnt = nullptr, float pair_thresh = 0.f) {
     const int lane = threadIdx.x & 31;
     // list != null: re-selection of the pilots on the tie list after tc_refine_kernel made their log-probabilities exact
     const int64_t n = list ? (int64_t)__ldg(list) : B;
@@ -1057,10 +1066,110 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
                 if (logp_out) logp_out[b * K + k] = l[i];
             }
         }
+        // (re-selection of a listed pilot: its pairs leave the histogram of the pair-bucketed combination and the new ones enter)
+        if (pair_cnt && w_out) for (int k = lane; k < K; k += 32) if (w_out[b * K + k] > pair_thresh) atomicSub(pair_cnt + k, 1);
         const bool tie = select_row<PER, EXACT>(l, lane, K, mode, n_top, rho, flags, tie_eps, w_out ? w_out + b * K : nullptr, top_out ? top_out + b : nullptr,
                                                 logc, inv_nobs);
+        if (pair_cnt && w_out) { __syncwarp(); for (int k = lane; k < K; k += 32) if (w_out[b * K + k] > pair_thresh) atomicAdd(pair_cnt + k, 1); }
         if (tie && lane == 0 && tie_buf) tie_append(bad, tie_buf, b);
     }
+}
+
+// The same selection with ONE THREAD PER PILOT (K <= 256): the warp-per-pilot form above spends its time in shuffles (~100 per pilot
+// at K = 64: 552 us per 2^19 pilots, the launch was half as long as the whitening launch it follows).  A block stages the FP32
+// (hi, lo) pairs of R pilots transposed in shared memory ([k][pilot]: conflict-free for thread = pilot), every thread then scans
+// its own K values: maximum / runner-up in exact FP64, responsibilities with FP32 exponentials, descending selection by repeated
+// scans (n + 1 of them for top-n), the same too-close-to-call rules.  The weight rows go back through shared memory so that the
+// global stores are coalesced.  pair_cnt != null: histogram of the selected (pilot, component) pairs with a weight above pair_thresh
+// (the count pass of the pair-bucketed combination, fused).
+template <int R>
+__global__ void __launch_bounds__(256) tc_select_rows_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho, int flags,
+                                                             float* __restrict__ w_out, double* __restrict__ logp_out, int* __restrict__ top_out,
+                                                             const unsigned char* __restrict__ bad, int* __restrict__ tie_buf, double tie_eps0,
+                                                             const double* __restrict__ logc, double inv_nobs, int* __restrict__ pair_cnt, float pair_thresh) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    constexpr int P = R + 1;                                   // pitch: thread = pilot reads column `pilot` of every row k
+    float* s_hi = reinterpret_cast<float*>(sel_smem);          // [K][P]  l_hi, later e_k = exp(l_k - max), later the weight
+    float* s_lo = s_hi + (size_t)K * P;                        // [K][P]  l_lo
+    int* s_cnt = reinterpret_cast<int*>(s_lo + (size_t)K * P); // [K] pair histogram of this block
+    const int64_t row0 = (int64_t)blockIdx.x * R;
+    const int nrow = (int)((B - row0) < R ? (B - row0) : R);
+    for (int i = threadIdx.x; i < nrow * K; i += 256) {
+        const int r = i / K, k = i - r * K;
+        const float2 v = lp2[(row0 + r) * K + k];
+        s_hi[k * P + r] = v.x;
+        s_lo[k * P + r] = v.y;
+        if (logp_out) logp_out[(row0 + r) * K + k] = (double)v.x + (double)v.y;
+    }
+    if (pair_cnt) for (int k = threadIdx.x; k < K; k += 256) s_cnt[k] = 0;
+    __syncthreads();
+    if (!w_out && !top_out) return;
+    const int r = threadIdx.x;
+    if (r < nrow) {
+        double mx = -INFINITY, mx2 = -INFINITY;
+        int amax = 0;
+        bool tie = false;
+        for (int k = 0; k < K; ++k) {
+            const double l = (double)s_hi[k * P + r] + (double)s_lo[k * P + r];
+            if (l != l) tie = true;
+            if (l > mx) { mx2 = mx; mx = l; amax = k; } else if (l > mx2) mx2 = l;
+        }
+        double tie_eps = tie_eps0;
+        if (logc) tie_eps *= fmax(1.0, (__ldg(logc + amax) - mx) * inv_nobs);
+        if (mode == QCE_MODE_TOP1) {
+            if (!(mx - mx2 > tie_eps) || ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabs(mx + 745.1332) < 0.01)) tie = true;
+            if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
+            if (top_out) top_out[row0 + r] = amax;
+            else for (int k = 0; k < K; ++k) s_hi[k * P + r] = (k == amax) ? 1.f : 0.f;
+        } else {
+            float sumf = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float e = expf((float)(((double)s_hi[k * P + r] + (double)s_lo[k * P + r]) - mx));
+                s_hi[k * P + r] = e;
+                sumf += e;
+            }
+            const double inv_sum = 1.0 / (double)sumf;
+            if (mode == QCE_MODE_ALL) {
+                for (int k = 0; k < K; ++k) {
+                    const float wk = (float)((double)s_hi[k * P + r] * inv_sum);
+                    s_hi[k * P + r] = wk;
+                    if (pair_cnt && wk > pair_thresh && bad[row0 + r] == 0) atomicAdd(&s_cnt[k], 1);
+                }
+            } else {
+                // descending selection: selected entries move to s_lo (as weights before normalisation), their s_hi slot becomes -1
+                for (int k = 0; k < K; ++k) s_lo[k * P + r] = 0.f;
+                const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
+                double cum = 0.0, last = -1.0;
+                bool done = false;
+                for (int it = 0; it <= limit; ++it) {
+                    float bvf = -1.f;
+                    int bk = -1;
+                    for (int k = 0; k < K; ++k) { const float e = s_hi[k * P + r]; if (e > bvf) { bvf = e; bk = k; } }
+                    if (bk < 0) break;                        // no candidates left
+                    const double bv = (double)bvf * inv_sum;
+                    if (done || it == limit) { if (bv > last * (1.0 - tie_eps)) tie = true; break; }
+                    s_hi[bk * P + r] = -1.f;
+                    s_lo[bk * P + r] = (float)bv > 0.f ? (float)bv : 1e-45f;      // (selected marker must survive a weight that underflowed)
+                    cum += bv;
+                    last = bv;
+                    if (mode == QCE_MODE_CUMPROB) {
+                        if (fabs(cum - rho) < tie_eps) tie = true;
+                        if (cum >= rho) done = true;
+                    }
+                }
+                for (int k = 0; k < K; ++k) {
+                    const float sel = s_lo[k * P + r];
+                    const float wk = sel > 0.f ? (float)((double)sel / cum) : 0.f;
+                    s_hi[k * P + r] = wk;
+                    if (pair_cnt && wk > pair_thresh && bad[row0 + r] == 0) atomicAdd(&s_cnt[k], 1);
+                }
+            }
+        }
+        if (tie && tie_buf) tie_append(bad, tie_buf, row0 + r);
+    }
+    __syncthreads();
+    if (w_out) for (int i = threadIdx.x; i < nrow * K; i += 256) { const int rr = i / K, k = i - rr * K; w_out[(row0 + rr) * K + k] = s_hi[k * P + rr]; }
+    if (pair_cnt) for (int k = threadIdx.x; k < K; k += 256) if (s_cnt[k]) atomicAdd(pair_cnt + k, s_cnt[k]);
 }
 
 // ------------------------------------------------------------------------------------------------ exact re-selection of near-ties
@@ -1237,6 +1346,109 @@ __global__ void __launch_bounds__(256) tc_bucket_gather_kernel(const unsigned ch
     }
 }
 
+// ---- pair mode: the (pilot, component) pairs with a non-negligible combination weight (top-n, cumulative rho, and 'all' when most of
+// the K weights of a pilot cannot change an FP32 accumulator) are regrouped by component exactly like the top-1 labels; a pilot
+// then owns several slots.  thresh: weights <= thresh are not pairs (0 for the hard selections, whose unselected weights are 0).
+__global__ void __launch_bounds__(1024) tc_pair_count_kernel(const float* __restrict__ w, const unsigned char* __restrict__ bad, int64_t B, int K,
+                                                             float thresh, int* __restrict__ cnt) {
+    __shared__ int s_cnt[1024];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b0 = (int64_t)blockIdx.x * 1024;
+    for (int64_t b = b0 + warp; b < b0 + 1024 && b < B; b += 32) {
+        if (bad[b]) continue;
+        for (int k = lane; k < K; k += 32) if (w[b * K + k] > thresh) atomicAdd(&s_cnt[k], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) if (s_cnt[k]) atomicAdd(cnt + k, s_cnt[k]);
+}
+
+// as tc_bucket_scan_kernel, plus the decision: more than max_units work units of pairs (a flat posterior: nearly every component
+// matters for nearly every pilot) -> the dense weighted launch is the cheaper one: flags[0] = 1 and no units
+__global__ void __launch_bounds__(1024) tc_pair_scan_kernel(const int* __restrict__ cnt, int K, int unit_rows, int max_units, int* __restrict__ off,
+                                                            int* __restrict__ cursor, int* __restrict__ unit_comp, int* __restrict__ n_units,
+                                                            int* __restrict__ dense_flag) {
+    __shared__ int s_first[1024];
+    __shared__ int s_dense;
+    if (threadIdx.x == 0) {
+        int u = 0;
+        for (int k = 0; k < K; ++k) { s_first[k] = u; u += (cnt[k] + unit_rows - 1) / unit_rows; }
+        s_dense = u > max_units;
+        *n_units = s_dense ? 0 : u;
+        *dense_flag = s_dense;
+    }
+    __syncthreads();
+    if (s_dense) return;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int u0 = s_first[k], nu = (cnt[k] + unit_rows - 1) / unit_rows;
+        off[k] = u0 * unit_rows;
+        cursor[k] = 0;
+        for (int u = 0; u < nu; ++u) unit_comp[u0 + u] = k;
+    }
+}
+
+__global__ void __launch_bounds__(1024) tc_pair_place_kernel(const float* __restrict__ w, const unsigned char* __restrict__ bad, int64_t B, int K,
+                                                             float thresh, const int* __restrict__ off, int* __restrict__ cursor,
+                                                             const int* __restrict__ dense_flag, int* __restrict__ perm, float* __restrict__ slot_w) {
+    // a block owns 1024 consecutive pilots; a warp walks pilots with its lanes over the components (coalesced weight rows).  Pass 1:
+    // block histogram; one global atomic per (block, component) reserves the block's slot range; pass 2: slots within the range.
+    if (__ldg(dense_flag)) return;
+    __shared__ int s_cnt[1024], s_base[1024];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b0 = (int64_t)blockIdx.x * 1024;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t b = b0 + warp; b < b0 + 1024 && b < B; b += 32) {
+            if (bad[b]) continue;
+            for (int k = lane; k < K; k += 32) {
+                const float wk = w[b * K + k];
+                if (wk > thresh) {
+                    const int local = atomicAdd(&s_cnt[k], 1);
+                    if (pass) { const int slot = s_base[k] + local; perm[slot] = (int)b; slot_w[slot] = wk; }
+                }
+            }
+        }
+        __syncthreads();
+        if (!pass) for (int k = threadIdx.x; k < K; k += blockDim.x) { const int c = s_cnt[k]; s_base[k] = c ? off[k] + atomicAdd(cursor + k, c) : 0; s_cnt[k] = 0; }
+        __syncthreads();
+    }
+}
+
+// pair mode, last step: the FP32 rows the pair launches added into -> complex128 estimates (and the NMSE accumulators)
+__global__ void __launch_bounds__(256) tc_pair_finish_kernel(const float2* __restrict__ rows, double2* __restrict__ h_est, const void* __restrict__ h_true,
+                                                             int h_true_c64, const unsigned char* __restrict__ bad, int64_t B, int N,
+                                                             const int* __restrict__ dense_flag, double* __restrict__ acc) {
+    if (__ldg(dense_flag)) return;                 // the dense weighted launch wrote the estimates and did the accumulation itself
+    double err = 0.0, pw = 0.0, cnt = 0.0;
+    const int lane = threadIdx.x & 31;
+    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += (int64_t)gridDim.x * 8) {
+        if (bad[b]) continue;
+        for (int j = lane; j < N; j += 32) {
+            const float2 e = rows[b * N + j];
+            if (h_est) h_est[b * N + j] = make_double2((double)e.x, (double)e.y);
+            if (acc && h_true) {
+                float2 h;
+                if (h_true_c64) h = reinterpret_cast<const float2*>(h_true)[b * N + j];
+                else { const double2 hd = reinterpret_cast<const double2*>(h_true)[b * N + j]; h = make_float2((float)hd.x, (float)hd.y); }
+                const float dx = e.x - h.x, dy = e.y - h.y;
+                err += (double)(dx * dx + dy * dy);
+                pw += (double)(h.x * h.x + h.y * h.y);
+            }
+        }
+        if (lane == 0) cnt += 1.0;
+    }
+    if (!acc) return;
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        err += __shfl_xor_sync(0xffffffffu, err, off);
+        pw += __shfl_xor_sync(0xffffffffu, pw, off);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    if (lane == 0 && cnt > 0.0) { atomicAdd(acc + 0, err); atomicAdd(acc + 1, pw); atomicAdd(acc + 2, cnt); }
+}
+
 // keyed by (device, stream): stream handles are only unique per device (the default stream is 0 everywhere)
 static std::mutex g_scratch_mu;
 static std::map<std::pair<int, cudaStream_t>, TileScratch> g_scratch;
@@ -1280,6 +1492,7 @@ void tc_scratch_release(cudaStream_t s) {
     if (it == g_scratch.end()) return;
     TileScratch& t = it->second;
     cudaFree(t.img); cudaFree(t.bad); cudaFree(t.lp2); cudaFree(t.wts); cudaFree(t.img2); cudaFree(t.bidx); cudaFree(t.fix_buf); cudaFree(t.tie_buf);
+    cudaFree(t.tmp_est);
     g_scratch.erase(it);
 }
 
@@ -1517,6 +1730,7 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     const char* th = getenv("QCE_TC_SKIP");                 // tuning knob (read per launch); measured: no effect up to 1e-9
     a.skip_thresh = th ? (float)atof(th) : 1e-30f;
     a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr;
+    a.slot_w = nullptr; a.run_flag = nullptr; a.run_flag_want = 0; a.pair_acc = nullptr;
     a.top_out = nullptr; a.top_flags = m->flags;
     a.fix_cnt = ts->fix_buf; a.fix_idx = ts->fix_buf + 2; a.tie_buf = ts->tie_buf;
     a.tie_eps = (float)tc_tie_eps(m); a.inv_nobs = 1.f / (float)m->n_obs;
@@ -1524,10 +1738,13 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
 
 static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,
                                const void* h_true, int h_true_c64, double* acc, const int* unit_comp = nullptr, const int* perm = nullptr,
-                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr) {
+                               const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr, const float* slot_w = nullptr, const int* run_flag = nullptr,
+                               int run_flag_want = 0) {
     const TcParams& p = m->tc;
     TcArgs a;
     tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
+    a.slot_w = slot_w; a.run_flag = run_flag; a.run_flag_want = run_flag_want;
+    a.pair_acc = (float*)ts->tmp_est;
     if (unit_comp) { a.unit_comp = unit_comp; a.perm = perm; a.n_units_dev = n_units_dev; a.a_img = (const __half*)bucket_img; }
     a.top_out = top_out;
     a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
@@ -1610,10 +1827,26 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
     int64_t chunk = (((int64_t)1 << 27) / m->n_comp) / unit_rows * unit_rows;
     if (const char* ce = getenv("QCE_TC_MODE_CHUNK")) chunk = atoll(ce) / unit_rows * unit_rows;      // test hook
     if (chunk < unit_rows) chunk = unit_rows;
+    const bool want_est = h_est || acc;
+    // Pair mode (top-n, cumulative rho, and 'all' on the large shapes): only the (pilot, component) pairs with a weight that matters
+    // are combined, regrouped by component like the top-1 labels.  'all': weights <= 1e-9 are below half an ulp of the FP32
+    // accumulators the weighted launch sums them in (64 of them together still are), so dropping them changes nothing that path
+    // could represent.  When a batch has more than QCE_TC_PAIR_CAP (4) pairs per pilot on average -- a flat posterior -- the dense
+    // weighted launch runs instead; the decision is made on the device (both are enqueued, one returns at once).
+    // Default: on for the large shapes (n_obs > 64: an LMMSE row block launch over all K components costs 2-4x the whitening launch),
+    // off for the fused shapes, where the weighted launch is as fast (measured at config 2, profiles/r02_modes.jsonl);
+    // QCE_TC_PAIRS=1 / 0 forces it on / off.
+    const int pair_env = getenv("QCE_TC_PAIRS") ? atoi(getenv("QCE_TC_PAIRS")) : -1;
+    const bool pair_on = pair_env < 0 ? m->tc.split : pair_env != 0;
+    const int pair_cap = getenv("QCE_TC_PAIR_CAP") ? atoi(getenv("QCE_TC_PAIR_CAP")) : 4;
+    const bool sparse_all = mode == QCE_MODE_ALL && m->tc.split && !(getenv("QCE_TC_SPARSE_ALL") && atoi(getenv("QCE_TC_SPARSE_ALL")) == 0);
+    const bool pair_mode_ok = (mode == QCE_MODE_TOPN && n_top <= pair_cap) || mode == QCE_MODE_CUMPROB || sparse_all;
+    const bool pairs = pair_on && pair_cap >= 1 && want_est && pair_mode_ok && m->n_comp >= 8 && B >= 16 * unit_rows;
+    const float pair_thresh = mode == QCE_MODE_ALL ? 1e-9f : 0.f;
+    if (pairs && chunk > ((int64_t)1 << 19)) chunk = (int64_t)1 << 19;      // (the regrouped pilot tiles take pair_cap x the chunk's tiles)
     if (chunk > B) chunk = B;
     qce_status st = tc_scratch_aux(ts, (size_t)chunk, (size_t)m->n_comp);
     if (st) return st;
-    const bool want_est = h_est || acc;
     const size_t tile_bytes = (size_t)TILE_M * 2 * m->n_obs * sizeof(__half) * (m->tc.split_a ? 2 : 1);
     const size_t true_row = (size_t)m->n_ant * (h_true_c64 ? 8 : 16);
     // top-1: regroup the pilots by selected component and run ONE component per work unit (QCE_TC_BUCKET=0: weighted launch instead)
@@ -1628,6 +1861,26 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         if (st) return st;
         b_top = (int*)ts->bidx; b_perm = b_top + chunk; b_ucomp = b_perm + cap_rows; b_cnt = b_ucomp + cap_units;
         b_off = b_cnt + m->n_comp; b_cur = b_off + m->n_comp; b_nu = b_cur + m->n_comp;
+    }
+    // pair mode: perm[slots] | slot_w[slots] | unit_comp[units] | cnt[K] off[K] cursor[K] | n_units | dense_flag
+    const int64_t p_units = (int64_t)pair_cap * (chunk / bucket_rows) + m->n_comp + 1, p_rows = p_units * bucket_rows;
+    int *p_perm = nullptr, *p_ucomp = nullptr, *p_cnt = nullptr, *p_off = nullptr, *p_cur = nullptr, *p_nu = nullptr, *p_dense = nullptr;
+    float* p_w = nullptr;
+    if (pairs && !bucketed) {
+        st = tc_scratch_bucket(ts, (size_t)(p_rows / TILE_M + 4) * tile_bytes, (size_t)(2 * p_rows + p_units + 3 * m->n_comp + 2));
+        if (st) return st;
+        p_perm = (int*)ts->bidx; p_w = (float*)(p_perm + p_rows); p_ucomp = p_perm + 2 * p_rows; p_cnt = p_ucomp + p_units;
+        p_off = p_cnt + m->n_comp; p_cur = p_off + m->n_comp; p_nu = p_cur + m->n_comp; p_dense = p_nu + 1;
+        {                  // FP32 rows the pair launches add into
+            std::lock_guard<std::mutex> lock(g_scratch_mu);
+            const size_t need = (size_t)chunk * m->n_ant * 8;
+            if (need > ts->tmp_est_bytes) {
+                if (ts->tmp_est) QCE_CUDA_TRY(cudaFree(ts->tmp_est));
+                ts->tmp_est = nullptr; ts->tmp_est_bytes = 0;
+                QCE_CUDA_TRY(cudaMalloc(&ts->tmp_est, need));
+                ts->tmp_est_bytes = need;
+            }
+        }
     }
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0) < chunk ? (B - b0) : chunk;
@@ -1649,14 +1902,29 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
             QCE_CUDA_TRY(cudaMemsetAsync(b_cnt, 0, m->n_comp * sizeof(int), s));
             QCE_CUDA_TRY(cudaMemsetAsync(b_perm, 0xFF, (size_t)cap_rows * sizeof(int), s));        // -1 = padding slot
         }
+        const bool pair_chunk = pairs && !bucketed;
+        const bool fused_count = pair_chunk && m->n_comp <= 256;      // the thread-per-pilot selection counts the pairs itself
+        if (pair_chunk) QCE_CUDA_TRY(cudaMemsetAsync(p_cnt, 0, m->n_comp * sizeof(int), s));
         if (!label_in_kernel) {
-            const unsigned grid = (unsigned)((nb + 7) / 8);
             float* wts = (want_est && !bucketed) ? (float*)v.wts : nullptr;
             const unsigned char* vb = (const unsigned char*)v.bad;
-            if (m->n_comp <= 64) tc_select_kernel<2><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
-            else if (m->n_comp <= 256) tc_select_kernel<8><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
-            else tc_select_kernel<32><<<grid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
-            QCE_CHECK_LAUNCH("tc_select_kernel");
+            const int K = m->n_comp;
+            if (K <= 256) {
+#define QCE_SEL_ROWS(R)                                                                                                                        \
+                {                                                                                                                              \
+                    const size_t sm = (size_t)2 * K * (R + 1) * sizeof(float) + (size_t)K * sizeof(int);                                      \
+                    static PerDeviceOnce once;                                                                                                 \
+                    if (once.first(current_device()))                                                                                          \
+                        QCE_CUDA_TRY(cudaFuncSetAttribute(tc_select_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+                    tc_select_rows_kernel<R><<<(unsigned)((nb + R - 1) / R), 256, sm, s>>>((const float2*)v.lp2, nb, K, mode, n_top, rho, m->flags, wts, lo, \
+                        b_top, vb, ts->tie_buf, eps, m->logc, 1.0 / m->n_obs, fused_count ? p_cnt : nullptr, pair_thresh);                    \
+                }
+                if (K <= 64) QCE_SEL_ROWS(256) else if (K <= 128) QCE_SEL_ROWS(128) else QCE_SEL_ROWS(64)
+#undef QCE_SEL_ROWS
+            } else {
+                tc_select_kernel<32><<<(unsigned)((nb + 7) / 8), 256, 0, s>>>((const float2*)v.lp2, nb, K, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
+            }
+            QCE_CHECK_LAUNCH("tc_select kernel");
         }
         if (!want_est) continue;
         if (refine) {      // exact log-probabilities for the pilots on the tie list, then their selection again (weight rows / labels overwritten)
@@ -1672,9 +1940,10 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
             QCE_CHECK_LAUNCH("tc_refine_kernel");
             float* wts = bucketed ? nullptr : (float*)v.wts;
             const unsigned sgrid = (unsigned)sms;
-            if (m->n_comp <= 64) tc_select_kernel<2, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0);
-            else if (m->n_comp <= 256) tc_select_kernel<8, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0);
-            else tc_select_kernel<32, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0);
+            int* pc = fused_count ? p_cnt : nullptr;
+            if (m->n_comp <= 64) tc_select_kernel<2, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0, pc, pair_thresh);
+            else if (m->n_comp <= 256) tc_select_kernel<8, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0, pc, pair_thresh);
+            else tc_select_kernel<32, true><<<sgrid, 256, 0, s>>>((const float2*)v.lp2, nb, m->n_comp, mode, n_top, rho, m->flags, wts, nullptr, b_top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0, pc, pair_thresh);
             QCE_CHECK_LAUNCH("tc_select_kernel(list)");
         }
         if (bucketed) {
@@ -1686,6 +1955,36 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
             QCE_CHECK_LAUNCH("tc_bucket kernels");
             for (int part = 0; part < m->tc.h_parts; ++part) {
                 st = tc_run_split(m, &v, s, cap_rows, 2, part, he, ht, h_true_c64, acc, b_ucomp, b_perm, b_nu, ts->img2);
+                if (st) return st;
+            }
+            continue;
+        }
+        if (pairs && !bucketed) {
+            const unsigned g1 = (unsigned)((nb + 1023) / 1024);
+            const unsigned char* vb = (const unsigned char*)v.bad;
+            QCE_CUDA_TRY(cudaMemsetAsync(p_perm, 0xFF, (size_t)p_rows * sizeof(int), s));          // -1 = padding slot
+            QCE_CUDA_TRY(cudaMemsetAsync(ts->tmp_est, 0, (size_t)nb * m->n_ant * 8, s));           // the pair rows are added into zeros
+            if (!fused_count) tc_pair_count_kernel<<<g1, 1024, 0, s>>>((const float*)v.wts, vb, nb, m->n_comp, pair_thresh, p_cnt);
+            tc_pair_scan_kernel<<<1, 1024, 0, s>>>(p_cnt, m->n_comp, bucket_rows, (int)(p_units - 1), p_off, p_cur, p_ucomp, p_nu, p_dense);
+            tc_pair_place_kernel<<<g1, 1024, 0, s>>>((const float*)v.wts, vb, nb, m->n_comp, pair_thresh, p_off, p_cur, p_dense, p_perm, p_w);
+            tc_bucket_gather_kernel<<<(unsigned)(p_rows / TILE_M), 256, 0, s>>>((const unsigned char*)v.img, p_perm, p_nu, tiles_per_unit,
+                                                                                2 * m->n_obs / 8, m->tc.split_a ? 2 : 1, (unsigned char*)ts->img2);
+            QCE_CHECK_LAUNCH("tc_pair kernels");
+            count_launch(fused_count ? 2 : 3);
+            for (int part = 0; part < m->tc.h_parts; ++part) {
+                st = tc_run_split(m, &v, s, p_rows, 2, part, nullptr, nullptr, 0, nullptr, p_ucomp, p_perm, p_nu, ts->img2, nullptr, p_w);
+                if (st) return st;
+            }
+            {
+                int sms = 148;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+                tc_pair_finish_kernel<<<(unsigned)(8 * sms), 256, 0, s>>>((const float2*)ts->tmp_est, (double2*)he, ht, h_true_c64, vb, nb, m->n_ant,
+                                                                          p_dense, acc);
+                QCE_CHECK_LAUNCH("tc_pair_finish_kernel");
+            }
+            // ... or, when the pairs were too many, the weighted launch over all K components (returns at once otherwise)
+            for (int part = 0; part < m->tc.h_parts; ++part) {
+                st = tc_run_split(m, &v, s, nb, 2, part, he, ht, h_true_c64, acc, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, p_dense, 1);
                 if (st) return st;
             }
             continue;

@@ -68,6 +68,15 @@ struct TcArgs {
     const int* unit_comp;      // [*n_units_dev]
     const int* perm;           // [B] (B = slot capacity of the launch)
     const int* n_units_dev;    // number of work units actually filled (device-side: the bucket sizes are data)
+    // pair mode of the bucketed combination (top-n / cumulative / sparse 'all'): a slot is one (pilot, component) pair with the
+    // combination weight slot_w[slot]; a pilot has several slots in different units, so the weighted LMMSE rows are ADDED to the
+    // pilot's (zero-initialised) FP32 row with vector reductions; tc_pair_finish_kernel turns the rows into estimates + NMSE sums
+    const float* slot_w;       // [slots] or null
+    float* pair_acc;           // [rows][2N] FP32 rows the pair launches add into (vector reductions)
+    // launches that are enqueued unconditionally but only one of which has work (bucketed pairs vs the dense weighted launch: the
+    // number of pairs is data): the kernel returns at once unless *run_flag == run_flag_want
+    const int* run_flag;
+    int run_flag_want;
     // EPI=1 with top_out != null: running argmax of l_k in the epilogue thread instead of the log-probability export (top-1 label
     // with tc_select_kernel's semantics: first index among equal maxima; QCE_FLAG_TOP1_EXP_ARGMAX in top_flags: label 0 on underflow)
     int* top_out;              // [B]
@@ -212,6 +221,8 @@ struct TileScratch {
     // complex128 (tc_refine_kernel) before the combine launch
     int* tie_buf = nullptr;
     size_t tie_bytes = 0;
+    void* tmp_est = nullptr;               // pair mode: [chunk rows][2N] FP32 rows the (pilot, component) launches add into
+    size_t tmp_est_bytes = 0;
 };
 
 

@@ -518,10 +518,11 @@ def test_mfa_woodbury_vs_dense_oracle(qce, K, N, M, nb, qt, ms):
     assert isinstance(m._prepared(np.eye(N), snr, 1, 'uniform', (None, None, None)), DenseModel)
     # 'auto': pilots on a uniform grid and a tensor-core shape go to the dense tcgen05 kernels, everything else stays Woodbury
     m.precision = 'auto'
-    from quantized_channel_estimation_b200.engine import tc_shape_ok
-    # every tensor-core shape (off-grid pilots -- Lloyd-Max labels, unquantised data -- as FP16 (hi, lo) tile pairs)
-    assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), DenseModel if tc_shape_ok(N, N) else MfaModel)
-    if tc_shape_ok(N, N):
+    from quantized_channel_estimation_b200.engine import tc_padded_shape
+    # every shape that fits a tensor-core shape after zero padding (off-grid pilots -- Lloyd-Max labels, unquantised data -- as FP16
+    # (hi, lo) tile pairs)
+    assert isinstance(m._prepared(np.eye(N), snr, nb, qt, qz), DenseModel if tc_padded_shape(N, N) is not None else MfaModel)
+    if tc_padded_shape(N, N) is not None:
         ref = orc.mofa_estimate_from_y(means, covs, amps, r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
         est = m.estimate_from_y(r, snr, n_summands_or_proba='all', n_bits=nb, quantizer_type=qt, quantizer=qz)
         assert relerr(est, ref) < TOL_TC
@@ -1129,3 +1130,47 @@ def test_predict_proba_runs_on_the_whitening_launch(qce):
     m.estimate_from_y(rt[:8], snr, N, n_summands_or_proba='all')
     lab = m._predict_cplx(rt)
     assert float((lab != p_64.argmax(1)).float().mean()) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('K,N,nb,qt,snr', [(64, 64, 1, 'uniform', 10), (16, 128, 2, 'uniform', 10), (64, 64, 1, 'uniform', -10)])
+def test_tc_pair_bucketed_combination(qce, K, N, nb, qt, snr):
+    """Top-n / cumulative-rho (and 'all' on the large shapes) through the pair-bucketed combination -- only the (pilot, component)
+    pairs with a weight that matters, regrouped by component -- against the dense weighted launch (QCE_TC_PAIRS=0) and the oracle.
+    -10 dB: the posterior is flat, the device-side decision falls back to the weighted launch; results must not change."""
+    import os
+    B = 20000
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, qt, 0.1, seed=K + N)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    rt, ht = torch.from_numpy(r).cuda(), torch.from_numpy(h).cuda()
+    model = m._prepared(np.eye(N), snr, nb, qt, qz)
+    for mode in ((2, 4, 0.9) if N <= 64 else ('all', 3, 0.95)):
+        try:
+            os.environ['QCE_TC_PAIRS'] = '1'       # (the default is on for n_obs > 64 only)
+            est, acc = model.estimate(rt, mode, 'tc', h_true=ht)
+            os.environ['QCE_TC_PAIRS'] = '0'
+            est0, acc0 = model.estimate(rt, mode, 'tc', h_true=ht)
+        finally:
+            del os.environ['QCE_TC_PAIRS']
+        per = ((est - est0).norm(dim=1) / est0.norm(dim=1)).max()
+        assert float(per) < 2e-6, (mode, float(per))
+        acc, acc0 = acc.cpu().numpy(), acc0.cpu().numpy()
+        assert acc[2] == acc0[2] == B
+        np.testing.assert_allclose(acc[:2], acc0[:2], rtol=1e-5)
+        nref = 3000
+        ref = orc.gmm_estimate_from_y(means, covs, w, r[:nref], snr, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz)
+        e = est[:nref].cpu().numpy()
+        pr = np.linalg.norm(e - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert pr.max() < 1e-4 and relerr(e, ref) < TOL_TC, (mode, pr.max())
+    # NMSE accumulators only (no estimate buffer from the caller): the fused pipeline entry point
+    from quantized_channel_estimation_b200 import engine
+    if nb == 1:
+        quant = engine.Quantizer.get(1)
+        os.environ['QCE_TC_PAIRS'] = '1'
+        try:
+            accp = model.pipeline(quant, ht, torch.from_numpy(noise).cuda(), 10 ** (-snr / 20), 4, 'tc')
+        finally:
+            del os.environ['QCE_TC_PAIRS']
+        est4 = model.estimate(rt, 4, 'tc')
+        np.testing.assert_allclose(accp.cpu().numpy()[0], float(((est4 - ht).abs() ** 2).sum()), rtol=1e-5)

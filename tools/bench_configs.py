@@ -32,6 +32,17 @@ def pilots(B, N, nb, qz, seed=0):
     return qce.quant(y, nb, qz[0], qz[1])
 
 
+def model_pilots(covs, w, B, snr, nb, qz, seed=0):
+    """Quantised observations of channels DRAWN FROM THE MIXTURE (h = C_k^{1/2} g, k ~ Cat(w)) at the given SNR: the posteriors --
+    and with them the work of the top-n / cumulative / sparse-'all' paths -- are those of the model's own data, not of white noise."""
+    import bench
+    dev = torch.device('cuda')
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    Lc = torch.linalg.cholesky(torch.as_tensor(covs, device=dev))
+    h, noise = bench.synth_channels(torch, Lc, torch.as_tensor(w, device=dev), B, gen, dev)
+    return qce.get_observation_nbit(h, snr, n_bits=nb, thresholds=qz[0], cluster=qz[1], noise=noise)
+
+
 def main():
     out = []
     snr = 10
@@ -51,10 +62,11 @@ def main():
     # C2 other modes on the tensor-core path
     means, covs, w = synthetic.random_psd_gmm(64, 64, seed=0)
     m = qce.Gmm_nbit(n_components=64).set_parameters(means, covs, w, detect_structure=False)
-    r = pilots(1 << 19, 64, 1, (None, None))
-    for mode in (1, 4, 0.9):
-        ms = timeit(lambda: m.estimate_from_y(r, snr, 64, n_summands_or_proba=mode))
-        out.append(dict(config=f'C2 GMM full 1-bit N=64 K=64 mode={mode}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='tc bucketed top-1' if mode == 1 else 'tc 3-launch'))
+    for tag, r in (('white-noise pilots', pilots(1 << 19, 64, 1, (None, None))), ('model-drawn pilots 10 dB', model_pilots(covs, w, 1 << 19, snr, 1, (None, None)))):
+        for mode in ('all', 1, 4, 0.9):
+            ms = timeit(lambda: m.estimate_from_y(r, snr, 64, n_summands_or_proba=mode))
+            out.append(dict(config=f'C2 GMM full 1-bit N=64 K=64 mode={mode}, {tag}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
+                            path='tc fused' if mode == 'all' else ('tc bucketed top-1' if mode == 1 else 'tc whitening -> selection -> pair-bucketed combine')))
     # C3: block-circulant 16x16, 3-bit Lloyd, N=256, K=128
     c, _, w, _ = synthetic.circulant_gmm(128, 16, 16, seed=0)
     qz = qce.get_quantizer([snr], 3, 'lloyd')[snr]
@@ -83,12 +95,15 @@ def main():
     # C4 through the dense tensor-core split path (whitening launch -> selection -> two row-block launches)
     mf.use_structure = False
     mf.precision = 'tc'
-    r = pilots(1 << 19, 128, 2, qz)
-    for mode in ('all', 1):
-        ms = timeit(lambda: mf.estimate_from_y(r, snr, n_summands_or_proba=mode, n_bits=2, quantizer_type='uniform', quantizer=qz))
-        out.append(dict(config=f'C4 MFA N=128 K=64 M=16 2-bit uniform mode={mode}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
-                        path='dense tc split', tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9,
-                        tflops_woodbury_equiv=(32 * 64 * 128 * 16 + 8 * 64 * 16 * 16) * r.shape[0] / ms / 1e9))
+    for tag, r in (('white-noise pilots', pilots(1 << 19, 128, 2, qz)), ('model-drawn pilots 10 dB', model_pilots(mf.covs, amps, 1 << 19, snr, 2, qz))):
+        for mode, env in (('all', {}), ('all', {'QCE_TC_SPARSE_ALL': '0'}), (1, {}), (4, {}), (0.9, {})):
+            os.environ.update(env)
+            ms = timeit(lambda: mf.estimate_from_y(r, snr, n_summands_or_proba=mode, n_bits=2, quantizer_type='uniform', quantizer=qz))
+            for k in env:
+                os.environ.pop(k)
+            out.append(dict(config=f'C4 MFA N=128 K=64 M=16 2-bit uniform mode={mode}, {tag}' + (' [dense weighted launch]' if env else ''), B=r.shape[0], ms=ms,
+                            est_per_s=r.shape[0] / ms * 1e3, path='dense tc split', tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9,
+                            tflops_woodbury_equiv=(32 * 64 * 128 * 16 + 8 * 64 * 16 * 16) * r.shape[0] / ms / 1e9))
     # C4 shape with a 3-bit Lloyd-Max quantiser: pilots off the integer grid -> (hi, lo) tile pairs, three passes, one tile per CTA
     qzl = qce.get_quantizer([snr], 3, 'lloyd')[snr]
     r = pilots(1 << 18, 128, 3, qzl)
