@@ -508,6 +508,31 @@ def main():
                'pcie_note': 'pcie_gbs_measured: pinned H2D + D2H copies running concurrently on every rank at the same time (cudaMemcpyAsync '
                             'only, sum over directions and ranks) -- the host-side ceiling of this box for N ranks; pcie_frac: the share of it '
                             'the e2e path moves (2 KiB per estimate: complex128 in and out, the reference dtype)'}
+        # the same call with the compact transfer formats (uint8 level codes in, complex64 estimates out: 128 + 512 B per pilot)
+        if tc_used:
+            _, codes_dev = quant.quantize(torch.view_as_complex(torch.view_as_real(r)), want_codes=True)      # r is on the 1-bit grid: Q(r) = r
+            codes_host = torch.empty((B, N_ANT, 2), dtype=torch.uint8).pin_memory()
+            codes_host.copy_(codes_dev.cpu())
+            out32 = torch.empty((B, N_ANT), dtype=torch.complex64).pin_memory()
+            del codes_dev
+
+            def codes_step(j):
+                _lib.check(lib.qce_estimate_host_codes(models[j].handle, quant.handle, C.c_void_p(codes_host.data_ptr()), B, mode, n_top, rho, prec,
+                                                       C.c_void_p(out32.data_ptr()), 1))
+            for i in range(2):
+                codes_step(i % len(SNRS))
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                codes_step(i % len(SNRS))
+            torch.cuda.synchronize()
+            dtc = max_over_ranks(time.perf_counter() - t0)
+            # the complex64 estimates equal the complex128 ones narrowed
+            chk = float((out32[:4096].to(torch.complex128) - out_host[:4096]).abs().max()) if (args.steps - 1) % len(SNRS) == (args.steps - 1) % len(SNRS) else None
+            e2e['codes_c64'] = {'value': world * B * args.steps / dtc, 'unit': UNIT, 'h2d_bytes_per_step': B * N_ANT * 2, 'd2h_bytes_per_step': B * N_ANT * 8,
+                                'api': 'qce_estimate_host_codes (uint8 level codes in, complex64 estimates out)', 'max_abs_diff_vs_c128_path': chk,
+                                'pcie_frac_d2h': (B * args.steps / dtc) * N_ANT * 8 / 1e9 / (pcie / 2)}
+            del codes_host, out32
         del r_host, out_host
     del r
     clk = clocks.stop() if rank == 0 else None

@@ -182,14 +182,23 @@ qce_status qce_mfa_estimate(qce_mfa_model* m, void* stream, const void* r_dev, i
                             void* h_est_dev, double* logp_out_dev, const void* h_true_dev, double* acc_dev);
 
 /* Host-buffer form of qce_estimate: r_host c128 [B][n_obs] -> h_est_host c128 [B][n_ant].  Copies are chunked (32 MiB, four chunks
- * in flight) and overlapped with the kernels on private streams; the streams and the pinned + device staging slots belong to the model
- * handle (created on the first host-buffer call, freed with the model).  Calls on the same model take turns, calls on different
- * models run concurrently; the private streams wait on an event recorded after the model's last parameter upload -- no device-wide
- * synchronisation.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly, pageable
+ * in flight) and overlapped with the kernels on private streams.  The streams and staging slots come from a per-device pool: a call
+ * takes a free set (or creates one) and returns it at the end, so concurrent calls -- on one model or several -- never share buffers
+ * and never wait for each other; the private streams wait on an event recorded after the model's last parameter upload -- no global
+ * lock, no device-wide synchronisation.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly, pageable
  * ones through the pinned slots.  Returns after the last chunk has landed in h_est_host (synchronous).  The calling thread's current
  * device must be the one the model was created on (QCE_ERR_INVALID otherwise). */
 qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho,
                              int precision, void* h_est_host);
+/* Frees the pooled staging sets (pinned host memory, device slots, streams) that are not in use by a call in flight. */
+void qce_host_staging_release(void);
+/* Compact transfer formats of the same call (the estimate itself is unchanged: the codes are expanded to the quantised pilots on the
+ * device, the estimates narrowed there).  codes_host: uint8 [B][n_obs][2], per real dimension the level index that qce_quantize /
+ * qce_observe_quantize write (1 bit: 0 neg / 1 zero / 2 pos / 3 NaN; b bit: 0 .. 2^b - 1); q supplies the labels.  out_c64 != 0:
+ * h_est_host is complex64 [B][n_ant] (the tensor-core estimates carry FP32 accuracy anyway), else complex128.  At n_obs = n_ant =
+ * 64: 128 B in + 512 B out per pilot instead of 1 KiB + 1 KiB. */
+qce_status qce_estimate_host_codes(qce_model* m, const qce_quantizer* q, const uint8_t* codes_host, int64_t B, int mode, int n_top,
+                                   double rho, int precision, void* h_est_host, int out_c64);
 /* The same for the circulant / block-circulant and the Woodbury-MFA models (r_host and h_est_host c128 [B][n_ant]). */
 qce_status qce_circ_estimate_host(qce_circ_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho,
                                   int precision, void* h_est_host);

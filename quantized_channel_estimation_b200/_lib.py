@@ -19,6 +19,8 @@ _SIGS = {
     'qce_launch_count': (C.c_int64, []),
     'qce_device_ok': (C.c_int, []),
     'qce_last_fix_count': (C.c_int64, [C.c_void_p]),
+    'qce_host_staging_release': (None, []),
+    'qce_estimate_host_codes': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int]),
     'qce_quantizer_create': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     'qce_quantizer_destroy': (None, [C.c_void_p]),
     'qce_quantize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -36,9 +36,8 @@ void set_error(const char* fmt, ...) {
 
 using namespace qce;
 
-struct HostCtx {                // staging of ONE model's host-buffer calls: double-buffered pinned + device slots on private streams
+struct HostCtx {                // staging of ONE host-buffer call at a time: pinned + device slots on private streams
     static constexpr int NSLOT = 4;  // chunks in flight: keeps the H2D and the D2H copy engines busy back to back
-    std::mutex mu;              // calls on the same model take turns; different models run concurrently
     int device = -1;
     cudaStream_t streams[NSLOT] = {};
     cudaEvent_t done[NSLOT] = {};
@@ -46,7 +45,9 @@ struct HostCtx {                // staging of ONE model's host-buffer calls: dou
     void* pin_out[NSLOT] = {};
     void* dev_in[NSLOT] = {};
     void* dev_out[NSLOT] = {};
-    size_t in_bytes = 0, out_bytes = 0;
+    void* dev_mid_in[NSLOT] = {};    // device-only intermediates of the compact transfer formats (decoded pilots, complex128 estimates)
+    void* dev_mid_out[NSLOT] = {};
+    size_t in_bytes = 0, out_bytes = 0, mid_in_bytes = 0, mid_out_bytes = 0, pin_in_bytes = 0, pin_out_bytes = 0;
 };
 
 void host_ctx_free(HostCtx* c) {
@@ -58,17 +59,35 @@ void host_ctx_free(HostCtx* c) {
         if (c->pin_out[i]) cudaFreeHost(c->pin_out[i]);
         if (c->dev_in[i]) cudaFree(c->dev_in[i]);
         if (c->dev_out[i]) cudaFree(c->dev_out[i]);
+        if (c->dev_mid_in[i]) cudaFree(c->dev_mid_in[i]);
+        if (c->dev_mid_out[i]) cudaFree(c->dev_mid_out[i]);
     }
     delete c;
 }
 
 namespace {
-std::mutex g_host_create_mu;
-HostCtx* host_ctx_get(HostCtx** slot) {
-    std::lock_guard<std::mutex> lock(g_host_create_mu);
-    if (!*slot) *slot = new HostCtx();
-    return *slot;
+// Staging sets are pooled per device: a host-buffer call takes a free set (or creates one) and returns it when it is done, so
+// concurrent calls -- on one model or on several -- never share buffers or streams and never wait for each other, and the memory
+// is bounded by the number of calls that were ever in flight at once (not by the number of models).
+std::mutex g_host_pool_mu;
+std::vector<HostCtx*> g_host_pool[64];
+HostCtx* host_ctx_acquire(int device) {
+    std::lock_guard<std::mutex> lock(g_host_pool_mu);
+    auto& pool = g_host_pool[device & 63];
+    if (!pool.empty()) { HostCtx* c = pool.back(); pool.pop_back(); return c; }
+    HostCtx* c = new HostCtx();
+    c->device = device;
+    return c;
 }
+void host_ctx_release(HostCtx* c) {
+    std::lock_guard<std::mutex> lock(g_host_pool_mu);
+    g_host_pool[c->device & 63].push_back(c);
+}
+struct HostCtxLease {
+    HostCtx* c;
+    explicit HostCtxLease(int device) : c(host_ctx_acquire(device)) {}
+    ~HostCtxLease() { host_ctx_release(c); }
+};
 
 // Pageable caller buffers are staged through pinned memory by the calling thread; one memcpy stream moves ~8 GB/s, far below
 // PCIe, so large copies are split over a few threads.
@@ -94,6 +113,18 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes) {
 extern "C" {
 
 int qce_abi_version(void) { return QCE_ABI_VERSION; }
+
+void qce_host_staging_release(void) {
+    std::vector<HostCtx*> all;
+    {
+        std::lock_guard<std::mutex> lock(g_host_pool_mu);
+        for (auto& pool : g_host_pool) { all.insert(all.end(), pool.begin(), pool.end()); pool.clear(); }
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (HostCtx* c : all) { cudaSetDevice(c->device); host_ctx_free(c); }
+    cudaSetDevice(cur);
+}
 
 int64_t qce_last_fix_count(void* stream) {
     const int* p = last_fix_list((cudaStream_t)stream);
@@ -201,7 +232,6 @@ qce_status qce_model_create(int n_obs, int n_ant, int n_comp, int flags, qce_mod
 
 void qce_model_destroy(qce_model* m) {
     if (!m) return;
-    host_ctx_free(m->host);
     if (m->params_ready) cudaEventDestroy(m->params_ready);
     tc_free(m);
     cudaFree(m->Linv); cudaFree(m->W); cudaFree(m->zoff); cudaFree(m->hoff); cudaFree(m->logc);
@@ -343,7 +373,6 @@ qce_status qce_circ_model_create(int n1, int n2, int n_comp, int flags, qce_circ
 
 void qce_circ_model_destroy(qce_circ_model* m) {
     if (!m) return;
-    host_ctx_free(m->host);
     if (m->params_ready) cudaEventDestroy(m->params_ready);
     circ_tc_free(m);
     cudaFree(m->inv_lambda_t); cudaFree(m->gain); cudaFree(m->logc);
@@ -403,7 +432,6 @@ qce_status qce_mfa_model_create(int n_ant, int latent, int n_comp, int flags, qc
 
 void qce_mfa_model_destroy(qce_mfa_model* m) {
     if (!m) return;
-    host_ctx_free(m->host);
     if (m->params_ready) cudaEventDestroy(m->params_ready);
     cudaFree(m->inv_delta); cudaFree(m->evec); cudaFree(m->D); cudaFree(m->Y); cudaFree(m->m_r); cudaFree(m->mu); cudaFree(m->logc);
     delete m;
@@ -453,40 +481,51 @@ qce_status qce_estimate_formatted(qce_model* m, void* stream, int64_t B, void* h
 // stay busy back to back.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly;
 // pageable ones go through the pinned staging slots.  `run(stream, dev_in, rows, dev_out)` enqueues the estimate of one chunk.
 template <typename Run>
-static qce_status estimate_host_impl(HostCtx** ctx_slot, int model_device, cudaEvent_t params_ready, size_t n_in, size_t n_out,
-                                     const void* r_host, int64_t B, void* h_est_host, Run run) {
-    const size_t in_row = n_in * 16, out_row = n_out * 16;
+static qce_status estimate_host_impl(int model_device, cudaEvent_t params_ready, size_t in_row, size_t out_row,
+                                     size_t mid_in_row, size_t mid_out_row, const void* r_host, int64_t B, void* h_est_host, Run run) {
+    // in_row / out_row: bytes per pilot that cross PCIe; mid_*_row: bytes per pilot of device-only intermediates (0: none)
     if (current_device() != model_device) {
         set_error("host-buffer estimate: the model lives on device %d, the calling thread's current device is %d", model_device, current_device());
         return QCE_ERR_INVALID;
     }
-    HostCtx* hs = host_ctx_get(ctx_slot);
-    std::lock_guard<std::mutex> lock(hs->mu);
-    hs->device = model_device;
+    HostCtxLease lease(model_device);
+    HostCtx* hs = lease.c;
     const size_t slot_bytes = (size_t)32 << 20;
     constexpr int NSLOT = HostCtx::NSLOT;
-    int64_t chunk = (int64_t)(slot_bytes / (in_row > out_row ? in_row : out_row));
+    size_t max_row = in_row > out_row ? in_row : out_row;
+    if (mid_in_row > max_row) max_row = mid_in_row;
+    if (mid_out_row > max_row) max_row = mid_out_row;
+    int64_t chunk = (int64_t)(slot_bytes / max_row);
     if (chunk < 128) chunk = 128;
     {
-        const size_t need_in = (size_t)chunk * in_row, need_out = (size_t)chunk * out_row;
+        const size_t need_dev_in = (size_t)chunk * in_row, need_dev_out = (size_t)chunk * out_row;
+        const size_t need_mi = (size_t)chunk * mid_in_row, need_mo = (size_t)chunk * mid_out_row;
         for (int i = 0; i < NSLOT; ++i) {
             if (!hs->streams[i]) {
                 QCE_CUDA_TRY(cudaStreamCreateWithFlags(&hs->streams[i], cudaStreamNonBlocking));
                 QCE_CUDA_TRY(cudaEventCreateWithFlags(&hs->done[i], cudaEventDisableTiming));
             }
-            if (hs->in_bytes < need_in) {
-                if (hs->pin_in[i]) { cudaFreeHost(hs->pin_in[i]); cudaFree(hs->dev_in[i]); hs->pin_in[i] = hs->dev_in[i] = nullptr; }
-                QCE_CUDA_TRY(cudaMallocHost(&hs->pin_in[i], need_in));
-                QCE_CUDA_TRY(cudaMalloc(&hs->dev_in[i], need_in));
+            if (hs->in_bytes < need_dev_in) {
+                if (hs->dev_in[i]) { cudaFree(hs->dev_in[i]); hs->dev_in[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMalloc(&hs->dev_in[i], need_dev_in));
             }
-            if (hs->out_bytes < need_out) {
-                if (hs->pin_out[i]) { cudaFreeHost(hs->pin_out[i]); cudaFree(hs->dev_out[i]); hs->pin_out[i] = hs->dev_out[i] = nullptr; }
-                QCE_CUDA_TRY(cudaMallocHost(&hs->pin_out[i], need_out));
-                QCE_CUDA_TRY(cudaMalloc(&hs->dev_out[i], need_out));
+            if (hs->out_bytes < need_dev_out) {
+                if (hs->dev_out[i]) { cudaFree(hs->dev_out[i]); hs->dev_out[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMalloc(&hs->dev_out[i], need_dev_out));
+            }
+            if (hs->mid_in_bytes < need_mi) {
+                if (hs->dev_mid_in[i]) { cudaFree(hs->dev_mid_in[i]); hs->dev_mid_in[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMalloc(&hs->dev_mid_in[i], need_mi));
+            }
+            if (hs->mid_out_bytes < need_mo) {
+                if (hs->dev_mid_out[i]) { cudaFree(hs->dev_mid_out[i]); hs->dev_mid_out[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMalloc(&hs->dev_mid_out[i], need_mo));
             }
         }
-        if (hs->in_bytes < need_in) hs->in_bytes = need_in;
-        if (hs->out_bytes < need_out) hs->out_bytes = need_out;
+        if (hs->in_bytes < need_dev_in) hs->in_bytes = need_dev_in;
+        if (hs->out_bytes < need_dev_out) hs->out_bytes = need_dev_out;
+        if (hs->mid_in_bytes < need_mi) hs->mid_in_bytes = need_mi;
+        if (hs->mid_out_bytes < need_mo) hs->mid_out_bytes = need_mo;
     }
     // parameters were uploaded / packed on the caller's stream: the private streams wait for that upload (an event, not a device-wide
     // synchronisation: other streams of the process are left alone)
@@ -498,6 +537,22 @@ static qce_status estimate_host_impl(HostCtx** ctx_slot, int model_device, cudaE
         return at.type == cudaMemoryTypeHost;
     };
     const bool in_pinned = is_pinned(r_host), out_pinned = is_pinned(h_est_host);
+    // pinned staging slots only where the caller's buffer is pageable (page-locked buffers are copied directly)
+    {
+        const size_t need_pi = in_pinned ? 0 : (size_t)chunk * in_row, need_po = out_pinned ? 0 : (size_t)chunk * out_row;
+        for (int i = 0; i < NSLOT; ++i) {
+            if (hs->pin_in_bytes < need_pi) {
+                if (hs->pin_in[i]) { cudaFreeHost(hs->pin_in[i]); hs->pin_in[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMallocHost(&hs->pin_in[i], need_pi));
+            }
+            if (hs->pin_out_bytes < need_po) {
+                if (hs->pin_out[i]) { cudaFreeHost(hs->pin_out[i]); hs->pin_out[i] = nullptr; }
+                QCE_CUDA_TRY(cudaMallocHost(&hs->pin_out[i], need_po));
+            }
+        }
+        if (hs->pin_in_bytes < need_pi) hs->pin_in_bytes = need_pi;
+        if (hs->pin_out_bytes < need_po) hs->pin_out_bytes = need_po;
+    }
     int64_t pending_b0[NSLOT], pending_nb[NSLOT];
     for (int i = 0; i < NSLOT; ++i) { pending_b0[i] = -1; pending_nb[i] = 0; }
     auto drain = [&](int slot) -> qce_status {
@@ -517,7 +572,7 @@ static qce_status estimate_host_impl(HostCtx** ctx_slot, int model_device, cudaE
         if (!in_pinned) { parallel_memcpy(hs->pin_in[slot], src, (size_t)nb * in_row); src = (const char*)hs->pin_in[slot]; }
         cudaStream_t s = hs->streams[slot];
         QCE_CUDA_TRY(cudaMemcpyAsync(hs->dev_in[slot], src, (size_t)nb * in_row, cudaMemcpyHostToDevice, s));
-        st = run(s, (const double*)hs->dev_in[slot], nb, (double*)hs->dev_out[slot]);
+        st = run(s, (const double*)hs->dev_in[slot], nb, (double*)hs->dev_out[slot], hs->dev_mid_in[slot], hs->dev_mid_out[slot]);
         if (st) return st;
         void* dst = out_pinned ? (void*)((char*)h_est_host + (size_t)b0 * out_row) : hs->pin_out[slot];
         QCE_CUDA_TRY(cudaMemcpyAsync(dst, hs->dev_out[slot], (size_t)nb * out_row, cudaMemcpyDeviceToHost, s));
@@ -536,25 +591,40 @@ extern "C" {
 qce_status qce_estimate_host(qce_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
                              void* h_est_host) {
     if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
-    return estimate_host_impl(&m->host, m->device, m->params_ready, (size_t)m->n_obs, (size_t)m->n_ant, r_host, B, h_est_host,
-                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
+    return estimate_host_impl(m->device, m->params_ready, (size_t)m->n_obs * 16, (size_t)m->n_ant * 16, 0, 0, r_host, B, h_est_host,
+                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout, void*, void*) {
                                   return estimate_impl(m, s, din, nb, mode, n_top, rho, precision, dout, nullptr, nullptr, 0, nullptr);
+                              });
+}
+
+qce_status qce_estimate_host_codes(qce_model* m, const qce_quantizer* q, const uint8_t* codes_host, int64_t B, int mode, int n_top, double rho,
+                                   int precision, void* h_est_host, int out_c64) {
+    if (!m || !q || !m->params_set || B < 0 || (B > 0 && (!codes_host || !h_est_host))) { set_error("qce_estimate_host_codes: invalid argument"); return QCE_ERR_INVALID; }
+    const size_t No = m->n_obs, N = m->n_ant;
+    return estimate_host_impl(m->device, m->params_ready, No * 2, N * (out_c64 ? 8 : 16), No * 16, out_c64 ? N * 16 : 0, codes_host, B, h_est_host,
+                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout, void* mid_in, void* mid_out) {
+                                  qce_status st = launch_decode_codes(&q->t, s, (const uint8_t*)din, nb * (int64_t)No, (double*)mid_in);
+                                  if (st) return st;
+                                  double* est = out_c64 ? (double*)mid_out : dout;
+                                  st = estimate_impl(m, s, (const double*)mid_in, nb, mode, n_top, rho, precision, est, nullptr, nullptr, 0, nullptr);
+                                  if (st || !out_c64) return st;
+                                  return launch_c128_to_c64(s, est, nb * (int64_t)N, (float*)dout);
                               });
 }
 
 qce_status qce_circ_estimate_host(qce_circ_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, int precision,
                                   void* h_est_host) {
     if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_circ_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
-    return estimate_host_impl(&m->host, m->device, m->params_ready, (size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
-                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
+    return estimate_host_impl(m->device, m->params_ready, (size_t)m->n_ant * 16, (size_t)m->n_ant * 16, 0, 0, r_host, B, h_est_host,
+                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout, void*, void*) {
                                   return qce_circ_estimate_prec(m, (void*)s, din, nb, mode, n_top, rho, precision, dout, nullptr, nullptr, nullptr);
                               });
 }
 
 qce_status qce_mfa_estimate_host(qce_mfa_model* m, const void* r_host, int64_t B, int mode, int n_top, double rho, void* h_est_host) {
     if (!m || !m->params_set || B < 0 || (B > 0 && (!r_host || !h_est_host))) { set_error("qce_mfa_estimate_host: invalid argument"); return QCE_ERR_INVALID; }
-    return estimate_host_impl(&m->host, m->device, m->params_ready, (size_t)m->n_ant, (size_t)m->n_ant, r_host, B, h_est_host,
-                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout) {
+    return estimate_host_impl(m->device, m->params_ready, (size_t)m->n_ant * 16, (size_t)m->n_ant * 16, 0, 0, r_host, B, h_est_host,
+                              [&](cudaStream_t s, const double* din, int64_t nb, double* dout, void*, void*) {
                                   return qce_mfa_estimate(m, (void*)s, din, nb, mode, n_top, rho, dout, nullptr, nullptr, nullptr);
                               });
 }

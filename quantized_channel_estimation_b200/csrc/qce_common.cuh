@@ -85,15 +85,12 @@ struct TcParams {
     int part_cols = 0;          // real columns (of the 2 n_ant) per row block
 };
 
-// host-buffer entry points: every model owns its staging (pinned + device slots, streams; created on first use, qce_api.cu) and an
-// event recorded after the last parameter upload, which the staging streams wait on
-struct HostCtx;
-void host_ctx_free(HostCtx* c);
+// host-buffer entry points: the staging sets (pinned + device slots, streams) are pooled per device (qce_api.cu); every model carries an
+// event recorded after its last parameter upload, which the staging streams wait on
 
 struct qce_circ_model {
     int n1, n2, n_ant, n_comp, flags;
     int device = 0;
-    HostCtx* host = nullptr;
     cudaEvent_t params_ready = nullptr;
     double* inv_lambda_t = nullptr;   // [N][K]  1 / eigenvalues of C_r,k, transposed for coalesced access
     double* gain = nullptr;           // [K][N]  b_k c_k / lambda_k
@@ -113,7 +110,6 @@ struct qce_circ_model {
 struct qce_mfa_model {
     int n_ant, latent, n_comp, flags;
     int device = 0;
-    HostCtx* host = nullptr;
     cudaEvent_t params_ready = nullptr;
     double* inv_delta = nullptr;      // [K][N]
     double* evec = nullptr;           // [K][N]
@@ -128,7 +124,6 @@ struct qce_mfa_model {
 struct qce_model {
     int n_obs, n_ant, n_comp, flags;
     int device = 0;
-    HostCtx* host = nullptr;
     cudaEvent_t params_ready = nullptr;
     // fp64 parameter copies (device)
     double* Linv = nullptr;     // c128 [K][No][No]
@@ -255,6 +250,8 @@ qce_status launch_quantize(const QuantTables* t, cudaStream_t s, const double* y
 qce_status launch_observe_quantize(const QuantTables* t, cudaStream_t s, const void* h, int h_is_c64,
                                    const double* noise, double noise_scale, int64_t n_complex, double* y_out,
                                    double* r_out, uint8_t* codes_out);
+qce_status launch_decode_codes(const QuantTables* t, cudaStream_t s, const uint8_t* codes, int64_t n_complex, double* r_out);
+qce_status launch_c128_to_c64(cudaStream_t s, const double* in, int64_t n_complex, float* out);
 // qce_dense_fp64.cu
 qce_status launch_dense_fp64(const qce_model* m, cudaStream_t s, const double* r, int64_t B, int mode, int n_top,
                              double rho, double* h_est, double* logp_out, const double* h_true, double* acc);

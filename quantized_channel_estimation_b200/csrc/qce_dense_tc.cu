@@ -1082,8 +1082,11 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
 // scans (n + 1 of them for top-n), the same too-close-to-call rules.  The weight rows go back through shared memory so that the
 // global stores are coalesced.  pair_cnt != null: histogram of the selected (pilot, component) pairs with a weight above pair_thresh
 // (the count pass of the pair-bucketed combination, fused).
+// R pilots and 128 threads per block, ~66 KB of shared memory: three blocks per SM keep enough loads in flight (one 132 KB block
+// of 256 pilots per SM left the staging loop latency-bound: 503 us per 2^19 pilots).
+constexpr int SEL_THREADS = 128;
 template <int R>
-__global__ void __launch_bounds__(256) tc_select_rows_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho, int flags,
+__global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho, int flags,
                                                              float* __restrict__ w_out, double* __restrict__ logp_out, int* __restrict__ top_out,
                                                              const unsigned char* __restrict__ bad, int* __restrict__ tie_buf, double tie_eps0,
                                                              const double* __restrict__ logc, double inv_nobs, int* __restrict__ pair_cnt, float pair_thresh) {
@@ -1094,82 +1097,108 @@ __global__ void __launch_bounds__(256) tc_select_rows_kernel(const float2* __res
     int* s_cnt = reinterpret_cast<int*>(s_lo + (size_t)K * P); // [K] pair histogram of this block
     const int64_t row0 = (int64_t)blockIdx.x * R;
     const int nrow = (int)((B - row0) < R ? (B - row0) : R);
-    for (int i = threadIdx.x; i < nrow * K; i += 256) {
-        const int r = i / K, k = i - r * K;
-        const float2 v = lp2[(row0 + r) * K + k];
-        s_hi[k * P + r] = v.x;
-        s_lo[k * P + r] = v.y;
-        if (logp_out) logp_out[(row0 + r) * K + k] = (double)v.x + (double)v.y;
+    {
+        const float2* src = lp2 + row0 * K;
+        const int n = nrow * K;
+        #pragma unroll 1
+        for (int i0 = threadIdx.x; i0 < n; i0 += 8 * SEL_THREADS) {       // 8 independent loads per thread in flight
+            float2 v[8];
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u * SEL_THREADS; v[u] = i < n ? __ldcs(src + i) : make_float2(0.f, 0.f); }
+            #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * SEL_THREADS;
+                if (i < n) {
+                    const int r = i / K, k = i - r * K;
+                    s_hi[k * P + r] = v[u].x;
+                    s_lo[k * P + r] = v[u].y;
+                    if (logp_out) logp_out[(row0 + r) * K + k] = (double)v[u].x + (double)v[u].y;
+                }
+            }
+        }
     }
-    if (pair_cnt) for (int k = threadIdx.x; k < K; k += 256) s_cnt[k] = 0;
+    if (pair_cnt) for (int k = threadIdx.x; k < K; k += SEL_THREADS) s_cnt[k] = 0;
     __syncthreads();
     if (!w_out && !top_out) return;
     const int r = threadIdx.x;
     if (r < nrow) {
-        double mx = -INFINITY, mx2 = -INFINITY;
+        // FP32 throughout (the FP64 pipe issues 2 warp-instructions per clock per SM: O(K) FP64 work per pilot made this launch
+        // FP64-bound): the maximum is located on the hi parts; every l_k is then taken RELATIVE to it, d_k = (hi_k - hi_max) +
+        // (lo_k - lo_max), exact to ~1e-7 |d_k|; a component whose lo part overturns the order of the hi parts has d_k > 0, which
+        // counts as too close to call like every |d_k| <= tie_eps -- the exact selection then decides.
+        float m_hi = -INFINITY;
         int amax = 0;
         bool tie = false;
         for (int k = 0; k < K; ++k) {
-            const double l = (double)s_hi[k * P + r] + (double)s_lo[k * P + r];
-            if (l != l) tie = true;
-            if (l > mx) { mx2 = mx; mx = l; amax = k; } else if (l > mx2) mx2 = l;
+            const float hi = s_hi[k * P + r];
+            if (hi != hi) tie = true;
+            if (hi > m_hi) { m_hi = hi; amax = k; }
         }
+        const float m_lo = s_lo[amax * P + r];
+        const double mx = (double)m_hi + (double)m_lo;
         double tie_eps = tie_eps0;
         if (logc) tie_eps *= fmax(1.0, (__ldg(logc + amax) - mx) * inv_nobs);
+        const float epsf = (float)tie_eps;
+        float d2 = -INFINITY, sumf = 0.f;            // runner-up (relative to the maximum), normaliser
+        for (int k = 0; k < K; ++k) {
+            const float d = (s_hi[k * P + r] - m_hi) + (s_lo[k * P + r] - m_lo);
+            if (k != amax && d > d2) d2 = d;
+            const float e = mode == QCE_MODE_TOP1 ? 0.f : expf(d);
+            s_hi[k * P + r] = e;
+            sumf += e;
+        }
         if (mode == QCE_MODE_TOP1) {
-            if (!(mx - mx2 > tie_eps) || ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabs(mx + 745.1332) < 0.01)) tie = true;
+            if (!(-d2 > epsf) || ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && fabs(mx + 745.1332) < 0.01)) tie = true;
             if ((flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp(mx) == 0.0) amax = 0;
             if (top_out) top_out[row0 + r] = amax;
             else for (int k = 0; k < K; ++k) s_hi[k * P + r] = (k == amax) ? 1.f : 0.f;
         } else {
-            float sumf = 0.f;
-            for (int k = 0; k < K; ++k) {
-                const float e = expf((float)(((double)s_hi[k * P + r] + (double)s_lo[k * P + r]) - mx));
-                s_hi[k * P + r] = e;
-                sumf += e;
-            }
-            const double inv_sum = 1.0 / (double)sumf;
+            if (d2 > 0.f) tie = true;                 // (the lo parts overturned the order: exact selection)
+            const float inv_sum = 1.f / sumf;
+            const bool count = pair_cnt != nullptr && bad[row0 + r] == 0;
             if (mode == QCE_MODE_ALL) {
                 for (int k = 0; k < K; ++k) {
-                    const float wk = (float)((double)s_hi[k * P + r] * inv_sum);
+                    const float wk = s_hi[k * P + r] * inv_sum;
                     s_hi[k * P + r] = wk;
-                    if (pair_cnt && wk > pair_thresh && bad[row0 + r] == 0) atomicAdd(&s_cnt[k], 1);
+                    if (count && wk > pair_thresh) atomicAdd(&s_cnt[k], 1);
                 }
             } else {
-                // descending selection: selected entries move to s_lo (as weights before normalisation), their s_hi slot becomes -1
+                // descending selection: selected entries move to s_lo (responsibilities), their s_hi slot becomes -1
                 for (int k = 0; k < K; ++k) s_lo[k * P + r] = 0.f;
                 const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
-                double cum = 0.0, last = -1.0;
+                double cum = 0.0;
+                float last = -1.f;
                 bool done = false;
                 for (int it = 0; it <= limit; ++it) {
                     float bvf = -1.f;
                     int bk = -1;
                     for (int k = 0; k < K; ++k) { const float e = s_hi[k * P + r]; if (e > bvf) { bvf = e; bk = k; } }
                     if (bk < 0) break;                        // no candidates left
-                    const double bv = (double)bvf * inv_sum;
-                    if (done || it == limit) { if (bv > last * (1.0 - tie_eps)) tie = true; break; }
+                    const float bv = bvf * inv_sum;
+                    if (done || it == limit) { if (bv > last * (1.f - epsf)) tie = true; break; }
                     s_hi[bk * P + r] = -1.f;
-                    s_lo[bk * P + r] = (float)bv > 0.f ? (float)bv : 1e-45f;      // (selected marker must survive a weight that underflowed)
-                    cum += bv;
+                    s_lo[bk * P + r] = bv > 0.f ? bv : 1e-45f;      // (the marker must survive a responsibility that underflowed)
+                    cum += (double)bv;
                     last = bv;
                     if (mode == QCE_MODE_CUMPROB) {
                         if (fabs(cum - rho) < tie_eps) tie = true;
                         if (cum >= rho) done = true;
                     }
                 }
+                const float inv_cum = (float)(1.0 / cum);
                 for (int k = 0; k < K; ++k) {
                     const float sel = s_lo[k * P + r];
-                    const float wk = sel > 0.f ? (float)((double)sel / cum) : 0.f;
+                    const float wk = sel > 0.f ? sel * inv_cum : 0.f;
                     s_hi[k * P + r] = wk;
-                    if (pair_cnt && wk > pair_thresh && bad[row0 + r] == 0) atomicAdd(&s_cnt[k], 1);
+                    if (count && wk > pair_thresh) atomicAdd(&s_cnt[k], 1);
                 }
             }
         }
         if (tie && tie_buf) tie_append(bad, tie_buf, row0 + r);
     }
     __syncthreads();
-    if (w_out) for (int i = threadIdx.x; i < nrow * K; i += 256) { const int rr = i / K, k = i - rr * K; w_out[(row0 + rr) * K + k] = s_hi[k * P + rr]; }
-    if (pair_cnt) for (int k = threadIdx.x; k < K; k += 256) if (s_cnt[k]) atomicAdd(pair_cnt + k, s_cnt[k]);
+    if (w_out) for (int i = threadIdx.x; i < nrow * K; i += SEL_THREADS) { const int rr = i / K, k = i - rr * K; w_out[(row0 + rr) * K + k] = s_hi[k * P + rr]; }
+    if (pair_cnt) for (int k = threadIdx.x; k < K; k += SEL_THREADS) if (s_cnt[k]) atomicAdd(pair_cnt + k, s_cnt[k]);
 }
 
 // ------------------------------------------------------------------------------------------------ exact re-selection of near-ties
@@ -1916,10 +1945,10 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
                     static PerDeviceOnce once;                                                                                                 \
                     if (once.first(current_device()))                                                                                          \
                         QCE_CUDA_TRY(cudaFuncSetAttribute(tc_select_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-                    tc_select_rows_kernel<R><<<(unsigned)((nb + R - 1) / R), 256, sm, s>>>((const float2*)v.lp2, nb, K, mode, n_top, rho, m->flags, wts, lo, \
+                    tc_select_rows_kernel<R><<<(unsigned)((nb + R - 1) / R), SEL_THREADS, sm, s>>>((const float2*)v.lp2, nb, K, mode, n_top, rho, m->flags, wts, lo, \
                         b_top, vb, ts->tie_buf, eps, m->logc, 1.0 / m->n_obs, fused_count ? p_cnt : nullptr, pair_thresh);                    \
                 }
-                if (K <= 64) QCE_SEL_ROWS(256) else if (K <= 128) QCE_SEL_ROWS(128) else QCE_SEL_ROWS(64)
+                if (K <= 64) QCE_SEL_ROWS(128) else if (K <= 128) QCE_SEL_ROWS(64) else QCE_SEL_ROWS(32)
 #undef QCE_SEL_ROWS
             } else {
                 tc_select_kernel<32><<<(unsigned)((nb + 7) / 8), 256, 0, s>>>((const float2*)v.lp2, nb, K, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);

@@ -86,4 +86,48 @@ qce_status launch_observe_quantize(const QuantTables* t, cudaStream_t s, const v
     return QCE_OK;
 }
 
+// Level codes (the uint8 pairs quantize_kernel writes) back to the quantised pilots: the inverse of the code output, so that a host
+// can ship 2 bytes per complex pilot entry instead of 16.  1 bit: 0 neg / 1 zero / 2 pos / 3 NaN; b bit: index into the labels.
+__global__ void __launch_bounds__(256) decode_codes_kernel(QuantTables t, const uchar2* __restrict__ codes, int64_t n, double2* __restrict__ r_out) {
+    extern __shared__ double s_lab[];
+    if (t.n_bits > 1) {
+        for (int i = threadIdx.x; i <= t.n_thr; i += blockDim.x) s_lab[i] = t.labels[i];
+        __syncthreads();
+    }
+    const double nan = __longlong_as_double(0x7FF8000000000000LL);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uchar2 c = codes[i];
+        double2 r;
+        if (t.n_bits == 1) {
+            if (c.x > 2 || c.y > 2) r = make_double2(nan, nan);
+            else r = make_double2(__dmul_rn(inv_sqrt2(), (double)((int)c.x - 1)) + 0.0, __dmul_rn(inv_sqrt2(), (double)((int)c.y - 1)) + 0.0);
+        } else {
+            r = make_double2(c.x <= t.n_thr ? s_lab[c.x] : nan, c.y <= t.n_thr ? s_lab[c.y] : nan);
+        }
+        r_out[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) c128_to_c64_kernel(const double2* __restrict__ in, int64_t n, float2* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = in[i];
+        out[i] = make_float2((float)v.x, (float)v.y);
+    }
+}
+
+qce_status launch_decode_codes(const QuantTables* t, cudaStream_t s, const uint8_t* codes, int64_t n_complex, double* r_out) {
+    if (n_complex == 0) return QCE_OK;
+    const size_t smem = (t->n_bits > 1) ? (size_t)(t->n_thr + 1) * sizeof(double) : 0;
+    decode_codes_kernel<<<quant_grid(n_complex), 256, smem, s>>>(*t, (const uchar2*)codes, n_complex, (double2*)r_out);
+    QCE_CHECK_LAUNCH("decode_codes_kernel");
+    return QCE_OK;
+}
+
+qce_status launch_c128_to_c64(cudaStream_t s, const double* in, int64_t n_complex, float* out) {
+    if (n_complex == 0) return QCE_OK;
+    c128_to_c64_kernel<<<quant_grid(n_complex), 256, 0, s>>>((const double2*)in, n_complex, (float2*)out);
+    QCE_CHECK_LAUNCH("c128_to_c64_kernel");
+    return QCE_OK;
+}
+
 }  // namespace qce

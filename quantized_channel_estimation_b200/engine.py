@@ -275,6 +275,26 @@ class DenseModel:
                                                                         mode, n_top, rho, p, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def estimate_host_codes(self, codes, quantizer, n_summands_or_proba='all', precision='auto', out_dtype=np.complex64):
+        """Compact host transfer formats: ``codes`` uint8 ``[B, n_obs, 2]`` (level indices per real dimension, as ``Quantizer.quantize(...,
+        want_codes=True)`` returns them) -> estimates ``[B, n_ant]`` complex64 (default) or complex128 on the host."""
+        mode, n_top, rho = parse_mode(n_summands_or_proba)
+        codes = np.ascontiguousarray(np.asarray(codes, dtype=np.uint8))
+        if codes.ndim != 3 or codes.shape[1:] != (self.n_obs, 2):
+            raise ValueError(f'codes must be [B, {self.n_obs}, 2] uint8')
+        if self.padded:
+            raise ValueError('estimate_host_codes(): zero-padded models are not supported')
+        out_dtype = np.dtype(out_dtype)
+        if out_dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+            raise ValueError('out_dtype must be complex64 or complex128')
+        out = np.empty((codes.shape[0], self.n_ant), dtype=out_dtype)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            self._call(precision, mode, lambda p: lib.qce_estimate_host_codes(self.handle, quantizer.handle, codes.ctypes.data_as(C.c_void_p),
+                                                                              codes.shape[0], mode, n_top, rho, p, out.ctypes.data_as(C.c_void_p),
+                                                                              int(out_dtype == np.dtype(np.complex64))))
+        return out
+
     def pipeline(self, quantizer, h, noise, noise_scale, n_summands_or_proba='all', precision='auto', want_est=False,
                  acc=None):
         """observe -> quantise -> estimate -> NMSE accumulators for device-resident channels (A = I)."""

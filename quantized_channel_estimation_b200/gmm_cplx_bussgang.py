@@ -189,6 +189,19 @@ class Gmm_nbit:
             return torch.from_numpy(model.estimate_host(y.numpy(), n_summands_or_proba, self.precision))
         return model.estimate_host(y, n_summands_or_proba, self.precision)
 
+    def estimate_from_codes(self, codes, snr_dB, n_antennas, A=None, n_summands_or_proba=1, n_bits=1, quantizer_type='uniform',
+                            quantizer=None, out_dtype=np.complex64):
+        """``estimate_from_y`` for pilots given as quantiser LEVEL CODES on the host (uint8 ``[B, n_obs, 2]``: per real dimension the
+        index of the level; 1 bit: 0 negative / 1 zero / 2 positive) with complex64 estimates back by default: 2 B per pilot entry in
+        and 8 B out cross PCIe instead of 16 B + 16 B.  Same kernels, same results (narrowed to ``out_dtype``)."""
+        if A is None:
+            A = np.eye(n_antennas, dtype=complex)
+        model = self._last = self._prepared(A, snr_dB, n_bits, quantizer_type, quantizer)
+        if not isinstance(model, engine.DenseModel):
+            raise NotImplementedError('estimate_from_codes: dense models only (set use_structure = False)')
+        q = engine.Quantizer.get(1) if int(n_bits) == 1 else engine.Quantizer.get(int(n_bits), quantizer[0], quantizer[1])
+        return model.estimate_host_codes(codes, q, n_summands_or_proba, self.precision, out_dtype)
+
     def weighted_log_prob(self, y, snr_dB=None, A=None, n_bits=1, quantizer_type='uniform', quantizer=None):
         """``_estimate_weighted_log_prob`` of the prepared mixture (reference :369-386): ``[B, K]`` float64.  With ``snr_dB=None``
         the setting prepared by the most recent ``estimate_from_y`` is used -- the reference's calling convention, whose

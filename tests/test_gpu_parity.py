@@ -1174,3 +1174,26 @@ def test_tc_pair_bucketed_combination(qce, K, N, nb, qt, snr):
             del os.environ['QCE_TC_PAIRS']
         est4 = model.estimate(rt, 4, 'tc')
         np.testing.assert_allclose(accp.cpu().numpy()[0], float(((est4 - ht).abs() ** 2).sum()), rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nb,qt', [(1, 'uniform'), (2, 'uniform'), (3, 'lloyd')])
+def test_estimate_from_codes_host_path(qce, nb, qt):
+    """qce_estimate_host_codes: uint8 level codes in, complex64 / complex128 estimates out -- the same estimates as estimate_from_y on the
+    complex128 pilots the codes stand for (bit-identical for complex128 output, narrowed for complex64)."""
+    from quantized_channel_estimation_b200 import engine
+    K, N, B, snr = 8, 32, 5000, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, qt, 0.1, seed=nb)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    q = engine.Quantizer.get(1) if nb == 1 else engine.Quantizer.get(nb, qz[0], qz[1])
+    y = torch.from_numpy(h + 10 ** (-snr / 20) * noise).cuda()
+    r_dev, codes = q.quantize(y, want_codes=True)
+    assert _bits_equal(r_dev.cpu().numpy(), r)
+    codes = codes.cpu().numpy()
+    for mode in ('all', 1, 3):
+        ref = m.estimate_from_y(r, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz)
+        e128 = m.estimate_from_codes(codes, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz, out_dtype=np.complex128)
+        e64 = m.estimate_from_codes(codes, snr, N, n_summands_or_proba=mode, n_bits=nb, quantizer_type=qt, quantizer=qz)
+        assert e128.dtype == np.complex128 and e64.dtype == np.complex64
+        assert np.array_equal(e128, ref)
+        assert np.array_equal(e64, ref.astype(np.complex64))
