@@ -17,13 +17,25 @@ _SUPPORTED_TYPES = ('full', 'circulant', 'block-circulant', 'toeplitz', 'block-t
 
 
 def _fingerprint(a):
-    """Cheap content key of a parameter array (identity alone would serve stale GPU handles after an in-place edit of
-    ``means_cplx`` / ``covs_cplx`` / ``gm.weights_``): shape, XOR of the 64-bit words, sum."""
+    """Key of a parameter array for the prepared-model cache.  Identity alone would serve stale GPU handles after an in-place edit
+    of ``means_cplx`` / ``covs_cplx`` / ``gm.weights_``; a full content hash costs milliseconds per ``estimate_from_y`` call at the
+    BASELINE shapes (16 MB of covariances at config 4) while the GPU idles.  So: ``set_parameters`` / ``fit`` make the arrays
+    READ-ONLY (an in-place edit raises; assigning a new array changes the identity), and for arrays a caller assigned directly the
+    key also carries the bytes of a strided sample of 1024 elements, which follows any edit that touches the array broadly
+    (scaling, re-fitting in place)."""
     if a is None:
         return None
-    a = np.ascontiguousarray(a)
-    words = a.view(np.uint64).ravel() if a.dtype.itemsize % 8 == 0 else np.frombuffer(a.tobytes(), dtype=np.uint8)
-    return (a.shape, a.dtype.str, int(np.bitwise_xor.reduce(words)) if words.size else 0, complex(a.sum()))
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    sample = flat[::max(1, flat.size // 1024)][:1024]
+    return (id(a), a.__array_interface__['data'][0], a.shape, a.dtype.str, hash(sample.tobytes()))
+
+
+def _frozen(a, dtype):
+    """A private read-only copy: the prepared-model cache may then key on identity (see _fingerprint)."""
+    a = np.array(a, dtype=dtype)
+    a.setflags(write=False)
+    return a
 
 
 def _table_key(quantizer):
@@ -88,9 +100,9 @@ class Gmm_nbit:
         """Install fitted parameters.  ``detect_structure``: test whether the covariances are (block-)circulant
         (the reference fits those types in the DFT domain and then densifies them, gmm:104-136) and, if so, remember
         the DFT-domain eigenvalues so that ``estimate_from_y`` can use the structured kernel."""
-        self.means_cplx = np.array(means, dtype=complex)
-        self.covs_cplx = np.array(covs, dtype=complex)
-        self.gm.weights_ = np.array(weights, dtype=float)
+        self.means_cplx = _frozen(means, complex)
+        self.covs_cplx = _frozen(covs, complex)
+        self.gm.weights_ = _frozen(weights, float)
         self.blocks, self.fft_covs = (None, None)
         if detect_structure and self.covs_cplx.shape[-1] <= 1024:
             self.blocks, self.fft_covs = precompute.detect_blocks(self.covs_cplx)

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from . import _lib, engine, precompute
-from .gmm_cplx_bussgang import _PreparedCache, _fingerprint, _table_key
+from .gmm_cplx_bussgang import _PreparedCache, _fingerprint, _frozen, _table_key
 
 
 class Mofa:
@@ -44,16 +44,16 @@ class Mofa:
         return new
 
     def set_parameters(self, means, lambdas, psis, amps, covs=None):
-        self.means = np.array(means, dtype=complex)
-        self.lambdas = np.array(lambdas, dtype=complex)
-        self.psis = np.array(psis, dtype=float)
-        self.amps = np.array(amps, dtype=float)
+        self.means = _frozen(means, complex)
+        self.lambdas = _frozen(lambdas, complex)
+        self.psis = _frozen(psis, float)
+        self.amps = _frozen(amps, float)
         self.n_components, self.D = self.means.shape
         self.M = self.lambdas.shape[-1]
         if covs is None:          # C_k = Lambda Lambda^H + diag(psi)   (reference :313-319)
             covs = self.lambdas @ np.transpose(self.lambdas.conj(), [0, 2, 1]) + np.stack([np.diag(p) for p in self.psis])
         lr = self.lambdas @ np.transpose(self.lambdas.conj(), [0, 2, 1]) + np.stack([np.diag(p) for p in self.psis])
-        self.covs = np.array(covs, dtype=complex)
+        self.covs = _frozen(covs, complex)
         # the Woodbury kernel is only valid if the covariances really are Lambda Lambda^H + diag(psi)
         self._covs_are_low_rank = bool(np.allclose(self.covs, lr, rtol=1e-10, atol=1e-12))
         self._cache.clear()

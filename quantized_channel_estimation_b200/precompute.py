@@ -51,6 +51,14 @@ def data_scale_for(snr_dB, n_bits, quantizer_type):
     return float(quant_uni.get_uniform_quant_step(snr_dB, n_bits)) / 2      # labels are odd multiples of step/2
 
 
+def _t(x, dtype, device):
+    """numpy -> torch on ``device`` (the model's parameter arrays are read-only: torch warns when it wraps those without a copy)."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', UserWarning)
+        return torch.as_tensor(np.asarray(x), dtype=dtype, device=device)
+
+
 def prepare(means, covs, weights, A, snr_dB, n_bits=1, quantizer_type='uniform', quantizer=None, device=None):
     """Return the parameter blocks as a dict of contiguous torch tensors on ``device``.
 
@@ -60,10 +68,10 @@ def prepare(means, covs, weights, A, snr_dB, n_bits=1, quantizer_type='uniform',
     if device is None:
         device = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
     cd, fd = torch.complex128, torch.float64
-    mu = torch.as_tensor(np.asarray(means), dtype=cd, device=device)
-    Ch = torch.as_tensor(np.asarray(covs), dtype=cd, device=device)
-    w = torch.as_tensor(np.asarray(weights), dtype=fd, device=device)
-    Am = torch.as_tensor(np.asarray(A), dtype=cd, device=device)
+    mu = _t(means, cd, device)
+    Ch = _t(covs, cd, device)
+    w = _t(weights, fd, device)
+    Am = _t(A, cd, device)
     K, N = mu.shape
     No = Am.shape[0]
     sigma2 = 10 ** (-snr_dB / 10)
@@ -174,10 +182,10 @@ def prepare_mfa_woodbury(means, lambdas, psis, amps, snr_dB, n_bits, quantizer_t
     if device is None:
         device = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
     cd, fd = torch.complex128, torch.float64
-    mu = torch.as_tensor(np.asarray(means), dtype=cd, device=device)
-    Lam = torch.as_tensor(np.asarray(lambdas), dtype=cd, device=device)               # [K,N,M]
-    psi = torch.as_tensor(np.asarray(psis), dtype=fd, device=device)                  # [K,N]
-    w = torch.as_tensor(np.asarray(amps), dtype=fd, device=device)
+    mu = _t(means, cd, device)
+    Lam = _t(lambdas, cd, device)               # [K,N,M]
+    psi = _t(psis, fd, device)                  # [K,N]
+    w = _t(amps, fd, device)
     K, N, M = Lam.shape
     sigma2 = 10 ** (-snr_dB / 10)
     d = (Lam.real ** 2 + Lam.imag ** 2).sum(-1) + psi + sigma2                        # diag C_y            (mofa:167-169)

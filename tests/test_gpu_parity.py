@@ -1020,7 +1020,12 @@ def test_prepared_cache_follows_in_place_parameter_edits(qce):
     m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
     m.precision = 'fp64'
     e0 = m.estimate_from_y(r, snr, N, n_summands_or_proba='all')
-    m.means_cplx *= 0.5                       # in place: same object identity
+    with pytest.raises(ValueError):           # set_parameters froze the arrays: an in-place edit cannot go unnoticed
+        m.means_cplx *= 0.5
+    buf = np.array(means)                     # a caller-owned, writable array assigned directly ...
+    m.means_cplx = buf
+    assert relerr(m.estimate_from_y(r, snr, N, n_summands_or_proba='all'), e0) < 1e-14
+    buf *= 0.5                                # ... and edited in place: same identity, the strided content sample follows the edit
     e1 = m.estimate_from_y(r, snr, N, n_summands_or_proba='all')
     ref = orc.gmm_estimate_from_y(0.5 * means, covs, w, r, snr, n_summands_or_proba='all', n_bits=1)
     assert relerr(e1, ref) < TOL_FP64 and relerr(e0, ref) > 1e-3
