@@ -1202,3 +1202,35 @@ def test_estimate_from_codes_host_path(qce, nb, qt):
         assert e128.dtype == np.complex128 and e64.dtype == np.complex64
         assert np.array_equal(e128, ref)
         assert np.array_equal(e64, ref.astype(np.complex64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('K,blocks,mode', [(128, (16, 16), 'all'), (64, (16, 16), 3), (128, (1, 256), 0.9), (64, (1, 256), 'all')])
+def test_circulant_tcgen05_variant(qce, K, blocks, mode):
+    """QCE_CIRC_UMMA=1: the two contractions of the DFT-domain kernel on tcgen05 (TMEM accumulators, rt parked in TMEM, bulk-TMA parameter
+    ring) against the mma.sync version of the same kernel and the complex128 kernel -- ragged batch, both transform variants, K = 64 / 128."""
+    import os
+    N, B, snr, nb, qt = 256, 1000 + 17, 8, 3, 'lloyd'
+    from quantized_channel_estimation_b200 import synthetic
+    c, _, w, _ = synthetic.circulant_gmm(K, *blocks, seed=K, dense=False)
+    qz = orc.get_quantizer([snr], nb, qt)[snr]
+    g = torch.Generator(device='cuda').manual_seed(5)
+    y = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float64)) * 0.8
+    r = qce.quant(y, nb, qz[0], qz[1])
+    h = torch.view_as_complex(torch.randn((B, N, 2), generator=g, device='cuda', dtype=torch.float64))
+    m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant')
+    m.set_circulant_parameters(c, w, blocks)
+    model = m._prepared(np.eye(N), snr, nb, qt, qz)
+    os.environ['QCE_CIRC_UMMA'] = '1'
+    try:
+        e1, lp1, acc1 = model.estimate(r, mode, 'tc', want_logp=True, h_true=h)
+    finally:
+        del os.environ['QCE_CIRC_UMMA']
+    e0, lp0, acc0 = model.estimate(r, mode, 'tc', want_logp=True, h_true=h)
+    e64 = model.estimate(r, mode, 'fp64')
+    per = (e1 - e64).norm(dim=1) / e64.norm(dim=1).clamp(min=1e-300)
+    assert float((e1 - e64).norm() / e64.norm()) < TOL_TC and float(per.max()) < 1e-4
+    assert float((e1 - e0).norm() / e0.norm()) < TOL_TC
+    assert float((lp1 - lp0).abs().max()) < 2e-3
+    np.testing.assert_allclose(acc1.cpu().numpy(), acc0.cpu().numpy(), rtol=1e-4)
+    assert acc1[2].item() == B

@@ -66,7 +66,7 @@ def main():
         for mode in ('all', 1, 4, 0.9):
             ms = timeit(lambda: m.estimate_from_y(r, snr, 64, n_summands_or_proba=mode))
             out.append(dict(config=f'C2 GMM full 1-bit N=64 K=64 mode={mode}, {tag}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3,
-                            path='tc fused' if mode == 'all' else ('tc bucketed top-1' if mode == 1 else 'tc whitening -> selection -> pair-bucketed combine')))
+                            path='tc fused' if mode == 'all' else ('tc whitening (label) -> bucket -> one-component combine' if mode == 1 else 'tc whitening -> selection -> weighted combine')))
     # C3: block-circulant 16x16, 3-bit Lloyd, N=256, K=128
     c, _, w, _ = synthetic.circulant_gmm(128, 16, 16, seed=0)
     qz = qce.get_quantizer([snr], 3, 'lloyd')[snr]
@@ -102,7 +102,7 @@ def main():
             for k in env:
                 os.environ.pop(k)
             out.append(dict(config=f'C4 MFA N=128 K=64 M=16 2-bit uniform mode={mode}, {tag}' + (' [dense weighted launch]' if env else ''), B=r.shape[0], ms=ms,
-                            est_per_s=r.shape[0] / ms * 1e3, path='dense tc split', tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9,
+                            est_per_s=r.shape[0] / ms * 1e3, path='dense tc split' + ('' if env or mode == 1 else ', pair-bucketed combine'), tflops_dense_equiv=16 * 64 * 128 * 128 * r.shape[0] / ms / 1e9,
                             tflops_woodbury_equiv=(32 * 64 * 128 * 16 + 8 * 64 * 16 * 16) * r.shape[0] / ms / 1e9))
     # C4 shape with a 3-bit Lloyd-Max quantiser: pilots off the integer grid -> (hi, lo) tile pairs, three passes, one tile per CTA
     qzl = qce.get_quantizer([snr], 3, 'lloyd')[snr]
