@@ -220,8 +220,10 @@ class Gmm_nbit:
         ``predict_proba_cplx(X)`` reads the state ``_prepare_for_prediction`` left in ``self.gm``."""
         if snr_dB is None:
             if self._last is None:
-                raise RuntimeError('Gmm_nbit: call estimate_from_y first (or pass snr_dB, n_bits, ...), like the reference, whose '
-                                   'predict_proba_cplx uses the state left by _prepare_for_prediction')
+                # no observation setting prepared yet: the trained mixture itself (the state fit() leaves in the reference's self.gm)
+                if self.means_cplx is None or self.covs_cplx is None:
+                    raise RuntimeError('Gmm_nbit: the model is not fitted (means_cplx / covs_cplx missing)')
+                self._last = self._prepared(np.eye(self.means_cplx.shape[1], dtype=complex), np.inf, np.inf, 'uniform', None)
             model = self._last
         else:
             if A is None:

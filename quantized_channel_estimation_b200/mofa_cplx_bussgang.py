@@ -115,8 +115,11 @@ class Mofa:
 
     def _log_resp(self, data):
         if self._last is None:
-            raise RuntimeError('Mofa.predict_proba: call estimate_from_y (or _prepared) first, like the reference, '
-                               'whose predict_proba uses the state left by _prepare_for_prediction')
+            # no observation setting prepared yet: the trained mixture itself, which is what the reference's predict_proba sees
+            # right after fit() (mofa:109-111: _means / _covs / _inv_covs hold the fitted channel-domain parameters)
+            if self.means is None or self.covs is None:
+                raise RuntimeError('Mofa.predict_proba: the model is not fitted')
+            self._prepared(np.eye(self.D, dtype=complex), np.inf, np.inf, 'uniform', None)
         dt = data if isinstance(data, torch.Tensor) and data.is_cuda else torch.as_tensor(np.asarray(data)).cuda()
         return self._last.log_prob(dt, self.precision)
 

@@ -103,11 +103,30 @@ def get_quantizer_gauss(snrs, n_bits, quantizer_type='lloyd', params=None):
     return get_quantizer(snrs, n_bits, quantizer_type)
 
 
-def get_pilot_matrix(n_antennas, n_pilots=1, pilots=None):
-    """``A = kron(x, I_N)`` for a length-``n_pilots`` pilot sequence ``x`` (reference :366).  ``pilots=None``
-    gives the all-ones sequence (1 pilot: the identity, as in every script)."""
-    x = np.ones(n_pilots, dtype=complex) if pilots is None else np.asarray(pilots, dtype=complex).reshape(n_pilots)
-    return np.kron(x[:, None], np.eye(n_antennas)).astype(complex)
+def get_pilot_matrix(n_antennas, n_pilots=1, n_bits=1, pilot_type='angle_amp', return_vector=False, *, pilots=None):
+    """``A = kron(x, I_N)`` for a length-``n_pilots`` pilot sequence ``x`` -- the reference's signature and pilot types
+    (modules/utils.py:337-367): unquantised (``n_bits = inf``) and ``'ones'``: all ones; ``'angle'``: unit-modulus phases spread over
+    [0, pi/2); ``'angle_amp'`` (default): the same phases with amplitudes rising linearly from 0.5 to 1, scaled to total power
+    ``n_pilots``; ``'rand'``: one complex Gaussian draw (numpy's global generator, like the reference) scaled to that power.
+    ``return_vector``: the column ``x [n_pilots, 1]`` instead of the matrix.  ``pilots=`` (keyword only, not in the reference)
+    supplies a custom sequence."""
+    if pilots is not None:
+        x = np.asarray(pilots, dtype=complex).reshape(n_pilots, 1)
+    elif n_bits == np.inf or n_bits == 'inf' or pilot_type == 'ones':
+        x = np.ones((n_pilots, 1))
+    elif pilot_type in ('angle', 'angle_amp'):
+        phase = np.linspace(0.0, np.pi / 2, num=n_pilots, endpoint=False)
+        x = np.exp(1j * phase)
+        if pilot_type == 'angle_amp':
+            x = np.linspace(0.5, 1.0, num=n_pilots, endpoint=True) * x
+            x = x * (np.sqrt(n_pilots) / np.linalg.norm(x))
+        x = x[:, None]
+    elif pilot_type == 'rand':
+        x = np.random.randn(n_pilots, 1) + 1j * np.random.randn(n_pilots, 1)
+        x = x * (np.sqrt(n_pilots) / np.linalg.norm(x))
+    else:
+        raise NotImplementedError(f'Pilot type {pilot_type} is not implemented!')
+    return x if return_vector else np.kron(x, np.eye(n_antennas))
 
 
 def toeplitz(c, r=None):

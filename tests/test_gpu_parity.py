@@ -1234,3 +1234,33 @@ def test_circulant_tcgen05_variant(qce, K, blocks, mode):
     assert float((lp1 - lp0).abs().max()) < 2e-3
     np.testing.assert_allclose(acc1.cpu().numpy(), acc0.cpu().numpy(), rtol=1e-4)
     assert acc1[2].item() == B
+
+
+@pytest.mark.gpu
+def test_predict_proba_right_after_set_parameters_uses_the_trained_mixture(qce):
+    """with no observation setting prepared yet, predict_proba / predict_proba_cplx are the responsibilities under the
+    trained (channel-domain) mixture -- what the reference computes right after fit() -- instead of an error."""
+    from fit_common import make_data
+    h, (w, means, covs) = make_data('full_mean')
+
+    def resp(x):
+        lp = np.empty((x.shape[0], len(w)))
+        for k in range(len(w)):
+            d = x - means[k]
+            lp[:, k] = np.log(w[k]) - x.shape[1] * np.log(np.pi) - np.linalg.slogdet(covs[k])[1] - np.real(np.sum(d.conj() * np.linalg.solve(covs[k], d.T).T, axis=1))
+        lp -= lp.max(1, keepdims=True)
+        return np.exp(lp) / np.exp(lp).sum(1, keepdims=True)
+    ref = resp(h[:500])
+    g = qce.Gmm_nbit(n_components=3).set_parameters(means, covs, w, detect_structure=False)
+    np.testing.assert_allclose(g.predict_proba_cplx(h[:500]), ref, atol=2e-4)
+    g.precision = 'fp64'
+    g._cache.clear(); g._last = None
+    np.testing.assert_allclose(g.predict_proba_cplx(h[:500]), ref, atol=1e-10)
+    hm, (wm, mm, cm) = make_data('mfa')
+    m = qce.Mofa(3, 2, verbose=False)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m.fit(hm[:1500], zero_mean=False)
+    p = m.predict_proba(hm[:200])
+    assert p.shape == (200, 3) and np.allclose(p.sum(1), 1.0, atol=1e-6)

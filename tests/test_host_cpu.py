@@ -218,3 +218,27 @@ def test_toeplitz_helper_matches_scipy():
     r = rng.standard_normal(4) + 1j * rng.standard_normal(4)
     assert np.array_equal(utils.toeplitz(c), scipy.linalg.toeplitz(c))
     assert np.array_equal(utils.toeplitz(c, r), scipy.linalg.toeplitz(c, r))
+
+
+def test_get_pilot_matrix_has_the_reference_signature_and_pilot_types():
+    """every reference script calls get_pilot_matrix(n_antennas, n_pilots, n_bits, pilot_type=...) (modules/utils.py:337-367)."""
+    import numpy as np
+    from quantized_channel_estimation_b200 import utils as u
+    x = u.get_pilot_matrix(4, 2, 1, pilot_type='angle_amp', return_vector=True)
+    raw = np.array([0.5, 1.0]) * np.exp(1j * np.array([0.0, np.pi / 4]))
+    np.testing.assert_allclose(x[:, 0], raw * np.sqrt(2) / np.linalg.norm(raw), atol=1e-15)
+    assert abs(np.linalg.norm(x) ** 2 - 2) < 1e-12                      # power constraint
+    np.testing.assert_allclose(u.get_pilot_matrix(3, 3, 2, 'angle', True)[:, 0], np.exp(1j * np.array([0, np.pi / 6, np.pi / 3])), atol=1e-15)
+    A = u.get_pilot_matrix(3, 2, 1)                                     # positional n_bits, default type
+    assert A.shape == (6, 3) and np.allclose(A[:3], x[0, 0] * np.eye(3)) and np.allclose(A[3:], x[1, 0] * np.eye(3))
+    assert np.array_equal(u.get_pilot_matrix(5, 1, 1), np.eye(5))       # one pilot: the identity (every script's default)
+    assert np.array_equal(u.get_pilot_matrix(2, 3, np.inf, 'angle'), np.kron(np.ones((3, 1)), np.eye(2)))
+    assert np.allclose(u.get_pilot_matrix(2, 2, 1, pilots=[1, 1j]), np.kron(np.array([[1], [1j]]), np.eye(2)))
+    with pytest.raises(NotImplementedError):
+        u.get_pilot_matrix(2, 2, 1, pilot_type='zadoff')
+    from oracle import build_ref
+    if build_ref.available():                                           # and against the vendored reference itself
+        _, _, ru = build_ref.import_reference()
+        for pt in ('angle', 'angle_amp', 'ones'):
+            for npil in (1, 2, 5):
+                np.testing.assert_allclose(u.get_pilot_matrix(4, npil, 2, pilot_type=pt), ru.get_pilot_matrix(4, npil, 2, pilot_type=pt), atol=1e-15)
