@@ -1871,7 +1871,9 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
     const bool sparse_all = mode == QCE_MODE_ALL && m->tc.split && !(getenv("QCE_TC_SPARSE_ALL") && atoi(getenv("QCE_TC_SPARSE_ALL")) == 0);
     const bool pair_mode_ok = (mode == QCE_MODE_TOPN && n_top <= pair_cap) || mode == QCE_MODE_CUMPROB || sparse_all;
     const bool pairs = pair_on && pair_cap >= 1 && want_est && pair_mode_ok && m->n_comp >= 8 && B >= 16 * unit_rows;
-    const float pair_thresh = mode == QCE_MODE_ALL ? 1e-9f : 0.f;
+    // (a selected component whose renormalised weight is below 1e-9 -- the tail of a top-n / cumulative selection at a peaked posterior
+    // -- is not a pair either: it cannot change the FP32 row the pairs are added into)
+    const float pair_thresh = 1e-9f;
     if (pairs && chunk > ((int64_t)1 << 19)) chunk = (int64_t)1 << 19;      // (the regrouped pilot tiles take pair_cap x the chunk's tiles)
     if (chunk > B) chunk = B;
     qce_status st = tc_scratch_aux(ts, (size_t)chunk, (size_t)m->n_comp);
