@@ -257,8 +257,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
     // work unit: CG * TILES tiles (256 pilots per CTA); the cluster (CG CTAs) walks the units round-robin
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
     int64_t n_units = (a.B + CG * NTILES * TILE_M - 1) / (CG * NTILES * TILE_M);
-    const bool bucket = (EPI == 2) && a.unit_comp != nullptr;      // one component per work unit (bucketed top-1)
+    // regrouped pilots (slot -> pilot through perm): one component per work unit (bucketed top-1, pair mode), or -- listed -- the
+    // components some pilot of the unit has a non-zero weight for (top-n / cumulative: pilots grouped by their best component share
+    // most of their selections)
+    const bool listed = (EPI == 2) && a.unit_list != nullptr;
+    const bool bucket = (EPI == 2) && (a.unit_comp != nullptr || listed);
     if (bucket) n_units = __ldg(a.n_units_dev);
+    // components of a unit: (first, count) and, when listed, the list
+    auto unit_comps = [&](int64_t unit, int& kb, int& nk, const int*& ul) {
+        kb = 0; nk = a.K; ul = nullptr;
+        if (listed) { nk = __ldg(a.unit_nk + unit); ul = a.unit_list + unit * a.K; }
+        else if (bucket) { kb = __ldg(a.unit_comp + unit); nk = 1; }
+    };
     const int64_t unit0 = blockIdx.x / CG, unit_step = gridDim.x / CG;
     // the SM-pair variant is only launched for triangular Linv (the common, Cholesky case): its offsets are compile-time
     const int tri16 = (CG == 2) ? Cfg::TRI16 : (a.tri ? 16 : 0);
@@ -301,9 +311,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             const unsigned char* img = (CG == 2) ? a.image2 + (size_t)rank * COMP_BYTES : reinterpret_cast<const unsigned char*>(a.image);
             constexpr size_t COMP_STRIDE = COMP_BYTES * CG;      // CG=2: [k][rank]
             for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
-                int kb = 0, ke = a.K;
-                if (bucket) { kb = __ldg(a.unit_comp + unit); ke = kb + 1; }
-                for (int k = kb; k < ke; ++k) {
+                int kb, nk;
+                const int* ul;
+                unit_comps(unit, kb, nk, ul);
+                for (int ki = 0; ki < nk; ++ki) {
+                    const int k = ul ? __ldg(ul + ki) : kb + ki;
                     const unsigned char* comp = img + (size_t)k * COMP_STRIDE;
                     #pragma unroll
                     for (int q = 0; q < Cfg::NCHUNK; ++q) {
@@ -354,7 +366,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 a_phase ^= 1;
                 tc_fence_after();
                 w_a += QCE_CLK() - ca;
-                const int nk = bucket ? 1 : a.K;
+                const int nk = listed ? __ldg(a.unit_nk + unit) : (bucket ? 1 : a.K);
                 for (int k = 0; k < nk; ++k) {
                     if (ORDER == 0) {
                     #pragma unroll
@@ -424,7 +436,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 mbar_wait(smem_u32(&ctrl->a_full), a_phase);
                 a_phase ^= 1;
                 mbar_arrive_cluster(smem_u32(&ctrl->a_full), 0);
-                const int nk = bucket ? 1 : a.K;
+                const int nk = listed ? __ldg(a.unit_nk + unit) : (bucket ? 1 : a.K);
                 for (int k = 0; k < nk; ++k) {
                     #pragma unroll
                     for (int q = 0; q < Cfg::NCHUNK; ++q) {
@@ -477,20 +489,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             // the pilot this thread handles, and the components of this unit
             int64_t src = tile_base + row;
             bool valid = src < a.B;
-            int kb = 0, ke = a.K;
+            int kb, nk;
+            const int* ul;
+            unit_comps(unit, kb, nk, ul);
             if (bucket) {
-                kb = __ldg(a.unit_comp + unit); ke = kb + 1;
                 src = __ldg(a.perm + tile_base + row);
                 valid = src >= 0;
             }
-            float zs_n = __ldg(a.zscale + kb), hs_n = __ldg(a.hscale + kb);
-            float2 lc_n = __ldg(a.logc2 + kb);
+            int k_n = (ul && nk > 0) ? __ldg(ul) : kb;     // the component of the next iteration (its scalars are fetched one ahead)
+            float zs_n = __ldg(a.zscale + k_n), hs_n = __ldg(a.hscale + k_n);
+            float2 lc_n = __ldg(a.logc2 + k_n);
             const int64_t grow = valid ? src : 0;     // rows past the end read row 0, never write
-            float w_n = (EPI == 2) ? (bucket ? (valid ? (a.slot_w ? __ldg(a.slot_w + tile_base + row) : 1.f) : 0.f) : __ldg(a.w_in + grow * a.K)) : 0.f;
+            float w_n = 0.f;
+            if (EPI == 2) {
+                if (listed) w_n = valid ? __ldg(a.w_in + grow * a.K + k_n) : 0.f;
+                else if (bucket) w_n = valid ? (a.slot_w ? __ldg(a.slot_w + tile_base + row) : 1.f) : 0.f;
+                else w_n = __ldg(a.w_in + grow * a.K);
+            }
             const bool fmt_next = PRO && (unit + unit_step < n_units);
             const int64_t fmt_tile0 = ((unit + unit_step) * CG + rank) * NTILES;
             if (fmt_next && fmt_slot == 0 && lane == 0) fmt_prefetch_unit(a, fmt_tile0, NTILES, Cfg::KD);
-            for (int k = kb; k < ke; ++k) {
+            for (int ki = 0; ki < nk; ++ki) {
+                const int k = k_n;
                 // PRO: this warp's share of the NEXT unit's pilot tiles: loads issued here, consumed after the accumulator is released
                 FmtItem fit;
                 const bool fmt_now = fmt_next && (k % fmt_every == 0);
@@ -503,9 +523,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 const float zs = zs_n, hs = hs_n;
                 const float2 lc = lc_n;
                 const float w_k = w_n;
-                if (k + 1 < ke) {
-                    zs_n = __ldg(a.zscale + k + 1); hs_n = __ldg(a.hscale + k + 1); lc_n = __ldg(a.logc2 + k + 1);
-                    if (EPI == 2) w_n = __ldg(a.w_in + grow * a.K + k + 1);
+                if (ki + 1 < nk) {
+                    k_n = ul ? __ldg(ul + ki + 1) : k + 1;
+                    zs_n = __ldg(a.zscale + k_n); hs_n = __ldg(a.hscale + k_n); lc_n = __ldg(a.logc2 + k_n);
+                    if (EPI == 2) w_n = (listed && !valid) ? 0.f : __ldg(a.w_in + grow * a.K + k_n);
                 }
                 // ---- whitened residual -> quadratic form
                 c0 = QCE_CLK();
@@ -576,7 +597,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     p = 0.f;
                 } else {
                 // ---- lazily rescaled online softmax (reference maximum moves only on jumps > 8)
-                if (k == 0) {
+                if (ki == 0) {
                     mref_hi = l_hi; mref_lo = l_lo; p = 1.f; ssum = 1.f;
                 } else {
                     float df = (l_hi - mref_hi) + (l_lo - mref_lo);
@@ -1099,7 +1120,9 @@ template <int R>
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho, int flags,
                                                              float* __restrict__ w_out, double* __restrict__ logp_out, int* __restrict__ top_out,
                                                              const unsigned char* __restrict__ bad, int* __restrict__ tie_buf, double tie_eps0,
-                                                             const double* __restrict__ logc, double inv_nobs, int* __restrict__ pair_cnt, float pair_thresh) {
+                                                             const double* __restrict__ logc, double inv_nobs, int* __restrict__ pair_cnt, float pair_thresh,
+                                                             int* __restrict__ key_out) {
+    // key_out != null: also the best component of every pilot (the grouping key of the listed combination)
     extern __shared__ __align__(16) unsigned char sel_smem[];
     constexpr int P = R + 1;                                   // pitch: thread = pilot reads column `pilot` of every row k
     float* s_hi = reinterpret_cast<float*>(sel_smem);          // [K][P]  l_hi, later e_k = exp(l_k - max), later the weight
@@ -1146,6 +1169,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float
         }
         const float m_lo = s_lo[amax * P + r];
         const double mx = (double)m_hi + (double)m_lo;
+        if (key_out) key_out[row0 + r] = amax;
         double tie_eps = tie_eps0;
         if (logc) tie_eps *= fmax(1.0, (__ldg(logc + amax) - mx) * inv_nobs);
         const float epsf = (float)tie_eps;
@@ -1382,6 +1406,44 @@ __global__ void __launch_bounds__(256) tc_bucket_gather_kernel(const unsigned ch
     for (int c = threadIdx.x / TILE_M; c < copies * kbs; c += 256 / TILE_M) {
         const uint4 v = src >= 0 ? __ldg(reinterpret_cast<const uint4*>(from + (size_t)c * TILE_M * 16)) : make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(to + (size_t)c * TILE_M * 16) = v;
+    }
+}
+
+// ---- listed combination: which components does a work unit of regrouped pilots need?  One block per unit; the slots' weight rows are
+// OR-ed into a K-bit mask in shared memory, the set bits become the unit's component list (ascending).
+__global__ void __launch_bounds__(256) tc_unit_list_kernel(const float* __restrict__ w, const int* __restrict__ perm, const int* __restrict__ n_units,
+                                                           int unit_rows, int K, int* __restrict__ unit_list, int* __restrict__ unit_nk) {
+    const int u = blockIdx.x;
+    if (u >= __ldg(n_units)) return;
+    __shared__ unsigned s_mask[32];                 // K <= 1024
+    __shared__ int s_n;
+    if (threadIdx.x < 32) s_mask[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int sl = warp; sl < unit_rows; sl += 8) {              // a warp per slot, lanes over the components (coalesced weight rows)
+        const int b = __ldg(perm + (size_t)u * unit_rows + sl);
+        if (b < 0) continue;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            const bool on = k < K && w[(size_t)b * K + k] != 0.f;       // (NaN weights count: their pilots are answered elsewhere)
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (lane == 0 && m && (s_mask[k0 >> 5] | m) != s_mask[k0 >> 5]) atomicOr(&s_mask[k0 >> 5], m);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // ascending list: word by word
+        for (int wd = 0; wd * 32 < K; ++wd) {
+            const unsigned m = s_mask[wd];
+            const bool on = (m >> lane) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (on) unit_list[(size_t)u * K + s_n + __popc(bal & ((1u << lane) - 1u))] = wd * 32 + lane;
+            __syncwarp();
+            if (lane == 0) s_n += __popc(bal);
+            __syncwarp();
+        }
+        if (lane == 0) unit_nk[u] = s_n;
     }
 }
 
@@ -1768,7 +1830,7 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     a.h_stride = 2 * m->n_ant; a.h_col0 = 0; a.count_rows = 1;
     const char* th = getenv("QCE_TC_SKIP");                 // tuning knob (read per launch); measured: no effect up to 1e-9
     a.skip_thresh = th ? (float)atof(th) : 1e-30f;
-    a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr;
+    a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr; a.unit_list = nullptr; a.unit_nk = nullptr;
     a.slot_w = nullptr; a.run_flag = nullptr; a.run_flag_want = 0; a.pair_acc = nullptr;
     a.top_out = nullptr; a.top_flags = m->flags;
     a.fix_cnt = ts->fix_buf; a.fix_idx = ts->fix_buf + 2; a.tie_buf = ts->tie_buf;
@@ -1778,13 +1840,14 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
 static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, int epi, int part, double* h_est,
                                const void* h_true, int h_true_c64, double* acc, const int* unit_comp = nullptr, const int* perm = nullptr,
                                const int* n_units_dev = nullptr, const void* bucket_img = nullptr, int* top_out = nullptr, const float* slot_w = nullptr, const int* run_flag = nullptr,
-                               int run_flag_want = 0) {
+                               int run_flag_want = 0, const int* unit_list = nullptr, const int* unit_nk = nullptr) {
     const TcParams& p = m->tc;
     TcArgs a;
     tc_fill_args(m, ts, B, h_est, h_true, h_true_c64, acc, &a);
     a.slot_w = slot_w; a.run_flag = run_flag; a.run_flag_want = run_flag_want;
     a.pair_acc = (float*)ts->tmp_est;
-    if (unit_comp) { a.unit_comp = unit_comp; a.perm = perm; a.n_units_dev = n_units_dev; a.a_img = (const __half*)bucket_img; }
+    if (unit_comp || unit_list) { a.unit_comp = unit_comp; a.perm = perm; a.n_units_dev = n_units_dev; a.a_img = (const __half*)bucket_img; }
+    a.unit_list = unit_list; a.unit_nk = unit_nk;
     a.top_out = top_out;
     a.image2 = (const unsigned char*)(epi == 1 ? p.image_z : p.image_h[part]);
     a.h_col0 = part * p.part_cols;
@@ -1903,6 +1966,24 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
         b_top = (int*)ts->bidx; b_perm = b_top + chunk; b_ucomp = b_perm + cap_rows; b_cnt = b_ucomp + cap_units;
         b_off = b_cnt + m->n_comp; b_cur = b_off + m->n_comp; b_nu = b_cur + m->n_comp;
     }
+    // Listed combination (top-n / cumulative rho where the pair path does not pay, i.e. the fused shapes): the pilots are regrouped by
+    // their best component like top-1, every unit then runs only the components its pilots selected (their union over 512 pilots
+    // of one bucket is a fraction of K), with the dense weight rows -- each pilot is still answered once, no atomics.
+    // Opt-in (QCE_TC_LISTED=1): on the random-PSD mixtures of the benchmark the runner-up components of a bucket's pilots are not
+    // clustered -- the union over 512 pilots is nearly all K -- and the launch is slower than the weighted one (config 2 top-4:
+    // 3.19 vs 2.84 ms per 2^19 pilots, combine launch 1.51 vs 1.35 ms, profiles/r02_modes.jsonl); mixtures whose components have
+    // few neighbours each (angular clusters of a channel model) are where it pays.
+    const bool listed = (getenv("QCE_TC_LISTED") && atoi(getenv("QCE_TC_LISTED")) == 1) && want_est && !bucketed && !pairs &&
+                        (mode == QCE_MODE_TOPN || mode == QCE_MODE_CUMPROB) && m->n_comp >= 8 && m->n_comp <= 256 && chunk >= 4 * (int64_t)bucket_rows;
+    // (K <= 256: the grouping key comes from the thread-per-pilot selection kernel)
+    int *l_key = nullptr, *l_perm = nullptr, *l_ucomp = nullptr, *l_cnt = nullptr, *l_off = nullptr, *l_cur = nullptr, *l_nu = nullptr, *l_list = nullptr, *l_nk = nullptr;
+    if (listed) {      // key[rows] | perm[slots] | unit_comp[units] | cnt[K] off[K] cursor[K] | n_units | unit_nk[units] | unit_list[units][K]
+        st = tc_scratch_bucket(ts, (size_t)(cap_rows / TILE_M + 4) * tile_bytes,
+                               (size_t)(chunk + cap_rows + 2 * cap_units + 3 * m->n_comp + 1 + cap_units * m->n_comp));
+        if (st) return st;
+        l_key = (int*)ts->bidx; l_perm = l_key + chunk; l_ucomp = l_perm + cap_rows; l_cnt = l_ucomp + cap_units;
+        l_off = l_cnt + m->n_comp; l_cur = l_off + m->n_comp; l_nu = l_cur + m->n_comp; l_nk = l_nu + 1; l_list = l_nk + cap_units;
+    }
     // pair mode: perm[slots] | slot_w[slots] | unit_comp[units] | cnt[K] off[K] cursor[K] | n_units | dense_flag
     const int64_t p_units = (int64_t)pair_cap * (chunk / bucket_rows) + m->n_comp + 1, p_rows = p_units * bucket_rows;
     int *p_perm = nullptr, *p_ucomp = nullptr, *p_cnt = nullptr, *p_off = nullptr, *p_cur = nullptr, *p_nu = nullptr, *p_dense = nullptr;
@@ -1958,7 +2039,8 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
                     if (once.first(current_device()))                                                                                          \
                         QCE_CUDA_TRY(cudaFuncSetAttribute(tc_select_rows_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
                     tc_select_rows_kernel<R><<<(unsigned)((nb + R - 1) / R), SEL_THREADS, sm, s>>>((const float2*)v.lp2, nb, K, mode, n_top, rho, m->flags, wts, lo, \
-                        b_top, vb, ts->tie_buf, eps, m->logc, 1.0 / m->n_obs, fused_count ? p_cnt : nullptr, pair_thresh);                    \
+                        b_top, vb, ts->tie_buf, eps, m->logc, 1.0 / m->n_obs, fused_count ? p_cnt : nullptr, pair_thresh,                     \
+                        listed ? l_key : nullptr);                                                                                             \
                 }
                 if (K <= 64) QCE_SEL_ROWS(128) else if (K <= 128) QCE_SEL_ROWS(64) else QCE_SEL_ROWS(32)
 #undef QCE_SEL_ROWS
@@ -1996,6 +2078,25 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
             QCE_CHECK_LAUNCH("tc_bucket kernels");
             for (int part = 0; part < m->tc.h_parts; ++part) {
                 st = tc_run_split(m, &v, s, cap_rows, 2, part, he, ht, h_true_c64, acc, b_ucomp, b_perm, b_nu, ts->img2);
+                if (st) return st;
+            }
+            continue;
+        }
+        if (listed) {
+            const unsigned g1 = (unsigned)((nb + 1023) / 1024);
+            QCE_CUDA_TRY(cudaMemsetAsync(l_cnt, 0, m->n_comp * sizeof(int), s));
+            QCE_CUDA_TRY(cudaMemsetAsync(l_perm, 0xFF, (size_t)cap_rows * sizeof(int), s));        // -1 = padding slot
+            tc_bucket_count_kernel<<<g1, 1024, 0, s>>>(l_key, nb, m->n_comp, l_cnt);
+            tc_bucket_scan_kernel<<<1, 1024, 0, s>>>(l_cnt, m->n_comp, bucket_rows, l_off, l_cur, l_ucomp, l_nu);
+            tc_bucket_place_kernel<<<g1, 1024, 0, s>>>(l_key, nb, m->n_comp, l_off, l_cur, l_perm);
+            tc_bucket_gather_kernel<<<(unsigned)(cap_rows / TILE_M), 256, 0, s>>>((const unsigned char*)v.img, l_perm, l_nu, tiles_per_unit,
+                                                                                  2 * m->n_obs / 8, m->tc.split_a ? 2 : 1, (unsigned char*)ts->img2);
+            tc_unit_list_kernel<<<(unsigned)cap_units, 256, 0, s>>>((const float*)v.wts, l_perm, l_nu, bucket_rows, m->n_comp, l_list, l_nk);
+            QCE_CHECK_LAUNCH("listed combination: bucket / list kernels");
+            count_launch(4);
+            for (int part = 0; part < m->tc.h_parts; ++part) {
+                st = tc_run_split(m, &v, s, cap_rows, 2, part, he, ht, h_true_c64, acc, nullptr, l_perm, l_nu, ts->img2, nullptr, nullptr, nullptr, 0,
+                                  l_list, l_nk);
                 if (st) return st;
             }
             continue;

@@ -68,6 +68,11 @@ struct TcArgs {
     const int* unit_comp;      // [*n_units_dev]
     const int* perm;           // [B] (B = slot capacity of the launch)
     const int* n_units_dev;    // number of work units actually filled (device-side: the bucket sizes are data)
+    // listed combination (EPI=2; top-n / cumulative modes at the fused shapes): the pilots are regrouped by their BEST component (perm,
+    // n_units_dev as above), unit u runs the unit_nk[u] components unit_list[u * K ..] -- those some pilot of the unit has a non-zero
+    // weight for -- with the dense weight rows w_in[pilot][k]
+    const int* unit_list;      // [units][K]
+    const int* unit_nk;        // [units]
     // pair mode of the bucketed combination (top-n / cumulative / sparse 'all'): a slot is one (pilot, component) pair with the
     // combination weight slot_w[slot]; a pilot has several slots in different units, so the weighted LMMSE rows are ADDED to the
     // pilot's (zero-initialised) FP32 row with vector reductions; tc_pair_finish_kernel turns the rows into estimates + NMSE sums

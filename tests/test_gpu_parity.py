@@ -1264,3 +1264,28 @@ def test_predict_proba_right_after_set_parameters_uses_the_trained_mixture(qce):
         m.fit(hm[:1500], zero_mean=False)
     p = m.predict_proba(hm[:200])
     assert p.shape == (200, 3) and np.allclose(p.sum(1), 1.0, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', [2, 4, 0.9])
+def test_tc_listed_combination(qce, mode):
+    """QCE_TC_LISTED=1: top-n / cumulative rho with the pilots regrouped by their best component and every work unit running only the
+    components its pilots selected -- same estimates as the weighted launch over all K components, and the oracle's."""
+    import os
+    K, N, B, snr = 32, 64, 12000, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.1, seed=77)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    m.precision = 'tc'
+    rt, ht = torch.from_numpy(r).cuda(), torch.from_numpy(h).cuda()
+    model = m._prepared(np.eye(N), snr, 1, 'uniform', None)
+    est0, acc0 = model.estimate(rt, mode, 'tc', h_true=ht)
+    os.environ['QCE_TC_LISTED'] = '1'
+    try:
+        est1, acc1 = model.estimate(rt, mode, 'tc', h_true=ht)
+    finally:
+        del os.environ['QCE_TC_LISTED']
+    assert torch.equal(est0, est1)                     # same weights, same accumulation order per pilot
+    np.testing.assert_allclose(acc1.cpu().numpy(), acc0.cpu().numpy(), rtol=1e-9)
+    ref = orc.gmm_estimate_from_y(means, covs, w, r[:2000], snr, n_summands_or_proba=mode, n_bits=1)
+    per = np.linalg.norm(est1[:2000].cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert per.max() < 1e-4
