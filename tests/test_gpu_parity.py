@@ -1289,3 +1289,30 @@ def test_tc_listed_combination(qce, mode):
     ref = orc.gmm_estimate_from_y(means, covs, w, r[:2000], snr, n_summands_or_proba=mode, n_bits=1)
     per = np.linalg.norm(est1[:2000].cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1)
     assert per.max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_two_gpus_in_one_process(qce):
+    """scratch, fix lists, shared-memory attributes and host staging are per device -- a process may drive several GPUs.
+    (Skipped on one-GPU boxes; `gpurun --gpus 2` runs it.)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    K, N, B, snr = 8, 32, 3000, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.1, seed=5)
+    ref = {mode: orc.gmm_estimate_from_y(means, covs, w, r[:500], snr, n_summands_or_proba=mode, n_bits=1) for mode in ('all', 1, 3)}
+    models = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+            models.append((m, torch.from_numpy(r).to(f'cuda:{d}')))
+    for rep in range(2):                      # interleaved: both devices use the default stream (handle 0 on each)
+        for d, (m, rt) in enumerate(models):
+            with torch.cuda.device(d):
+                for mode in ('all', 1, 3):
+                    for prec in ('tc', 'fp64'):
+                        m.precision = prec
+                        est = m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode)
+                        assert est.device.index == d
+                        assert relerr(est[:500].cpu().numpy(), ref[mode]) < TOL_TC
+                m.precision = 'tc'
+                assert relerr(m.estimate_from_y(r[:500], snr, N, n_summands_or_proba='all'), ref['all']) < TOL_TC      # host path on device d
