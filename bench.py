@@ -408,6 +408,7 @@ def main():
     l0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.nvtx.range_push('qce_timed_region')      # lets `ncu --nvtx --nvtx-include qce_timed_region/` list exactly these launches
     ev0.record()
     for i in range(args.steps):
         step(i)
@@ -415,6 +416,7 @@ def main():
         dist.all_reduce(acc_sweep.copy_(acc))
         acc_total.add_(acc_sweep)
     ev1.record()
+    torch.cuda.nvtx.range_pop()
     barrier()
     launches = _lib.launch_count() - l0
     ms = max_over_ranks(ev0.elapsed_time(ev1))
