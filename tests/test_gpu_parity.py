@@ -1316,3 +1316,35 @@ def test_two_gpus_in_one_process(qce):
                         assert relerr(est[:500].cpu().numpy(), ref[mode]) < TOL_TC
                 m.precision = 'tc'
                 assert relerr(m.estimate_from_y(r[:500], snr, N, n_summands_or_proba='all'), ref['all']) < TOL_TC      # host path on device d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('K,N,nb,qt,B', [(8, 64, 1, 'uniform', 900), (6, 128, 2, 'uniform', 700), (5, 48, 3, 'lloyd', 500), (4, 40, 1, 'uniform', 300)])
+def test_tc_launch_time_knobs_do_not_change_results(qce, K, N, nb, qt, B, monkeypatch):
+    """Every launch-time knob of the tensor-core path (DESIGN.md knobs table) selects another route to the SAME estimates: all pilots sent
+    through the complex128 re-selection (QCE_TC_TIE_EPS=0.5), pair-bucketed / listed / weighted combination, bucketed top-1 off -- on the
+    fused shape, the split path, the three-pass path and a zero-padded shape, all four modes, with some pilots off the grid."""
+    snr = 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, qt, 0.1, seed=K)
+    r = r.copy()
+    r[::7] *= 1.37                                              # off the declared grid: re-evaluated in complex128 inside the call
+    rt = torch.from_numpy(r).cuda()
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    kw = dict(n_bits=nb, quantizer_type=qt, quantizer=qz)
+    modes = ('all', 1, 3, 0.9)
+    m.precision = 'fp64'
+    ref = {mode: m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode, **kw) for mode in modes}
+    m.precision = 'tc'
+    base = {mode: m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode, **kw) for mode in modes}
+    for mode in modes:
+        assert relerr(base[mode].cpu().numpy(), ref[mode].cpu().numpy()) < TOL_TC
+    for knob, val in (('QCE_TC_TIE_EPS', '0.5'), ('QCE_TC_PAIRS', '1'), ('QCE_TC_PAIRS', '0'), ('QCE_TC_LISTED', '1'), ('QCE_TC_BUCKET', '0')):
+        monkeypatch.setenv(knob, val)
+        for mode in modes:
+            got = m.estimate_from_y(rt, snr, N, n_summands_or_proba=mode, **kw)
+            assert relerr(got.cpu().numpy(), ref[mode].cpu().numpy()) < TOL_TC, (knob, val, mode)
+            # hard selections are the same selections, whatever the route
+            if mode != 'all':
+                rows = (got - base[mode]).norm(dim=1) / base[mode].norm(dim=1).clamp(min=1e-300)
+                assert float(rows.max()) < 1e-4, (knob, val, mode, float(rows.max()))
+        monkeypatch.delenv(knob)
