@@ -11,7 +11,7 @@
 
 namespace qce {
 static thread_local char g_err[512] = "";
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
 
 // fix list (count first) of the most recent tensor-core estimate per (device, stream): qce_last_fix_count
 static std::mutex g_fix_mu;
@@ -135,7 +135,7 @@ int64_t qce_last_fix_count(void* stream) {
     return (int64_t)n[0] + n[1];
 }
 const char* qce_last_error_string(void) { return g_err; }
-int64_t qce_launch_count(void) { return g_launch_count; }
+int64_t qce_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 int qce_device_ok(void) {
     int n = 0;

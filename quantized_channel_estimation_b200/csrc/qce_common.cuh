@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "qce_b200.h"
@@ -13,8 +14,8 @@ namespace qce {
 void set_error(const char* fmt, ...);
 void note_fix_list(cudaStream_t s, const int* fix_buf);      // qce_last_fix_count bookkeeping (qce_api.cu)
 const int* last_fix_list(cudaStream_t s);
-extern int64_t g_launch_count;
-inline void count_launch(int n = 1) { g_launch_count += n; }
+extern std::atomic<int64_t> g_launch_count;          // calls may come from several host threads (one per stream / device)
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 
 #define QCE_CUDA_TRY(expr)                                                                      \
     do {                                                                                        \

@@ -1348,3 +1348,49 @@ def test_tc_launch_time_knobs_do_not_change_results(qce, K, N, nb, qt, B, monkey
                 rows = (got - base[mode]).norm(dim=1) / base[mode].norm(dim=1).clamp(min=1e-300)
                 assert float(rows.max()) < 1e-4, (knob, val, mode, float(rows.max()))
         monkeypatch.delenv(knob)
+
+
+@pytest.mark.gpu
+def test_concurrent_host_threads_on_their_own_streams(qce):
+    """SURVEY 8b threading contract: a model handle is immutable after set_params and qce_estimate is stream-ordered and re-entrant across
+    streams and handles.  Four host threads, each on its own stream, share one model and own another; all modes, tensor-core and complex128
+    paths, device tensors and host arrays; results equal the serial ones."""
+    import threading
+    K, N, B, snr = 16, 64, 6000, 10
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, 1, 'uniform', 0.1, seed=11)
+    shared = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    shared.precision = 'tc'
+    rt = torch.from_numpy(r).cuda()
+    modes = ('all', 1, 3, 0.9)
+    serial = {mode: shared.estimate_from_y(rt, snr, N, n_summands_or_proba=mode) for mode in modes}
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(i):
+        try:
+            st = torch.cuda.Stream()
+            own = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+            own.precision = 'tc' if i % 2 else 'fp64'
+            sl = slice(i * 1000, i * 1000 + 1500)
+            with torch.cuda.stream(st):
+                mine = rt[sl].clone()
+                for rep in range(6):
+                    for mode in modes:
+                        a = shared.estimate_from_y(mine, snr, N, n_summands_or_proba=mode)
+                        b = own.estimate_from_y(mine, snr, N, n_summands_or_proba=mode)
+                        c = shared.estimate_from_y(r[sl], snr, N, n_summands_or_proba=mode)        # host arrays: the library's copies
+                        st.synchronize()
+                        ref = serial[mode][sl]
+                        for got, tol in ((a, 1e-6), (b, TOL_TC), (torch.from_numpy(c).cuda(), 1e-6)):
+                            e = float((got - ref).norm() / ref.norm())
+                            if not e < tol:
+                                errors.append((i, rep, mode, e))
+        except Exception as exc:                                  # noqa: BLE001 -- reported by the main thread
+            errors.append((i, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
