@@ -2,6 +2,8 @@
 against (a) the golden vectors produced by the unmodified reference and (b) the numpy oracle on seeded
 inputs.  Tolerances: quantised pilots bit-exact; estimates 1e-4 relative (north_star) -- the complex128
 kernel is held to 1e-10, the tensor-core kernel to 1e-5."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -1394,3 +1396,68 @@ def test_concurrent_host_threads_on_their_own_streams(qce):
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+def _tail_invariance(m, r, snr, N, modes, kw, tail=6000):
+    """Estimates of rows at the start, across rows 2^20 and 2^21 and at the very end of one big call == the same rows in small calls."""
+    B = r.shape[0]
+    spots = [p for p in (0, (1 << 20) - tail // 2, (1 << 21) - tail // 2, B // 2 + 1, B - tail) if 0 <= p and p + tail <= B]
+    for mode in modes:
+        full = m.estimate_from_y(r, snr, N, n_summands_or_proba=mode, **kw)
+        assert full.shape == (B, N)
+        for p in spots:
+            part = m.estimate_from_y(r[p:p + tail].contiguous(), snr, N, n_summands_or_proba=mode, **kw)
+            err = float((full[p:p + tail] - part).norm() / part.norm())
+            assert err < 1e-6, (mode, p, err)                  # FP32 atomics of the pair path: order-dependent in the last bits
+        del full
+
+
+@pytest.mark.gpu
+def test_batches_beyond_4_gib_dense(qce):
+    """Maximum sizes: one call whose pilot and estimate arrays exceed 4 GiB each (32-bit byte offsets would wrap at row 2^21 for
+    N = 64 / 128): the fused kernel, the chunked mode paths, the split path and the complex128 kernel index in 64 bits."""
+    snr = 10
+    # N = 64: 2 KiB per row -> 2^21 rows = 4 GiB; 3.2 M pilots
+    K, N, B = 8, 64, (1 << 21) + (1 << 20) + 77
+    means, covs, w = orc.random_psd_gmm(K, N, seed=3)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    r, _ = _grid_pilots(B, N, 2, 1 / np.sqrt(2), seed=1)
+    assert r.numel() * 16 > (1 << 32)
+    m.precision = 'tc'
+    _tail_invariance(m, r, snr, N, ('all', 1, 3, 0.9), {})
+    m.precision = 'fp64'
+    _tail_invariance(m, r, snr, N, ('all',), {}, tail=2000)
+    del r, m
+    torch.cuda.empty_cache()
+    # N = 128 split path, 2-bit uniform: 2 KiB per row again
+    K, N, B = 4, 128, (1 << 21) + 333
+    means, covs, w = orc.random_psd_gmm(K, N, seed=4)
+    qz = orc.get_quantizer([snr], 2, 'uniform')[snr]
+    step = float(qz[1][1] - qz[1][0])
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    r, _ = _grid_pilots(B, N, 4, step / 2, seed=2)
+    m.precision = 'tc'
+    _tail_invariance(m, r, snr, N, ('all', 1, 2), dict(n_bits=2, quantizer_type='uniform', quantizer=qz))
+
+
+@pytest.mark.gpu
+def test_batches_beyond_4_gib_circulant(qce):
+    """The same for the DFT-domain kernels (N = 256: 4 KiB per row -> 2^20 rows = 4 GiB), both tensor-core variants."""
+    from quantized_channel_estimation_b200 import synthetic
+    K, N, B, snr = 64, 256, (1 << 20) + (1 << 18) + 5, 10
+    c, _, w, _ = synthetic.circulant_gmm(K, 16, 16, seed=2, dense=False)
+    qz = orc.get_quantizer([snr], 3, 'lloyd')[snr]
+    m = qce.Gmm_nbit(n_components=K, covariance_type='block-circulant').set_circulant_parameters(c, w, (16, 16))
+    g = torch.Generator(device='cuda').manual_seed(3)
+    r = torch.empty((B, N), dtype=torch.complex128, device='cuda')
+    for i in range(0, B, 1 << 18):
+        y = torch.view_as_complex(torch.randn((min(1 << 18, B - i), N, 2), generator=g, device='cuda', dtype=torch.float64)) * 0.8
+        r[i:i + (1 << 18)] = qce.quant(y, 3, qz[0], qz[1])
+    del y
+    kw = dict(n_bits=3, quantizer_type='lloyd', quantizer=qz)
+    _tail_invariance(m, r, snr, N, ('all', 1, 0.9), kw, tail=3000)
+    os.environ['QCE_CIRC_UMMA'] = '1'
+    try:
+        _tail_invariance(m, r, snr, N, ('all',), kw, tail=3000)
+    finally:
+        del os.environ['QCE_CIRC_UMMA']
