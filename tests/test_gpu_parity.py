@@ -1401,7 +1401,7 @@ def test_concurrent_host_threads_on_their_own_streams(qce):
 def _tail_invariance(m, r, snr, N, modes, kw, tail=6000):
     """Estimates of rows at the start, across rows 2^20 and 2^21 and at the very end of one big call == the same rows in small calls."""
     B = r.shape[0]
-    spots = [p for p in (0, (1 << 20) - tail // 2, (1 << 21) - tail // 2, B // 2 + 1, B - tail) if 0 <= p and p + tail <= B]
+    spots = [p for p in (0, (1 << 20) - tail // 2, (1 << 21) - tail // 2, (1 << 22) - tail // 2, B // 2 + 1, B - tail) if 0 <= p and p + tail <= B]
     for mode in modes:
         full = m.estimate_from_y(r, snr, N, n_summands_or_proba=mode, **kw)
         assert full.shape == (B, N)
@@ -1414,11 +1414,11 @@ def _tail_invariance(m, r, snr, N, modes, kw, tail=6000):
 
 @pytest.mark.gpu
 def test_batches_beyond_4_gib_dense(qce):
-    """Maximum sizes: one call whose pilot and estimate arrays exceed 4 GiB each (32-bit byte offsets would wrap at row 2^21 for
-    N = 64 / 128): the fused kernel, the chunked mode paths, the split path and the complex128 kernel index in 64 bits."""
+    """Maximum sizes: one call whose pilot and estimate arrays exceed 4 GiB each (32-bit byte offsets would wrap at row 2^22 for
+    N = 64, 2^21 for N = 128): the fused kernel, the chunked mode paths, the split path and the complex128 kernel index in 64 bits."""
     snr = 10
-    # N = 64: 2 KiB per row -> 2^21 rows = 4 GiB; 3.2 M pilots
-    K, N, B = 8, 64, (1 << 21) + (1 << 20) + 77
+    # N = 64: 1 KiB per row -> 2^22 rows = 4 GiB; 5.2 M pilots
+    K, N, B = 8, 64, (1 << 22) + (1 << 20) + 77
     means, covs, w = orc.random_psd_gmm(K, N, seed=3)
     m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
     r, _ = _grid_pilots(B, N, 2, 1 / np.sqrt(2), seed=1)
@@ -1429,7 +1429,7 @@ def test_batches_beyond_4_gib_dense(qce):
     _tail_invariance(m, r, snr, N, ('all',), {}, tail=2000)
     del r, m
     torch.cuda.empty_cache()
-    # N = 128 split path, 2-bit uniform: 2 KiB per row again
+    # N = 128 split path, 2-bit uniform: 2 KiB per row
     K, N, B = 4, 128, (1 << 21) + 333
     means, covs, w = orc.random_psd_gmm(K, N, seed=4)
     qz = orc.get_quantizer([snr], 2, 'uniform')[snr]
