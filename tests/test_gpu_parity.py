@@ -1461,3 +1461,28 @@ def test_batches_beyond_4_gib_circulant(qce):
         _tail_invariance(m, r, snr, N, ('all',), kw, tail=3000)
     finally:
         del os.environ['QCE_CIRC_UMMA']
+
+
+@pytest.mark.gpu
+def test_host_arrays_beyond_4_gib(qce):
+    """qce_estimate_host / qce_estimate_host_codes with host arrays past 4 GiB: chunk offsets are 64-bit, head / middle / tail rows equal
+    the device path."""
+    from quantized_channel_estimation_b200 import engine
+    K, N, B, snr = 4, 64, (1 << 22) + 333, 10
+    means, covs, w = orc.random_psd_gmm(K, N, seed=5)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    r, _ = _grid_pilots(B, N, 2, 1 / np.sqrt(2), seed=9)
+    _, codes = engine.Quantizer.get(1).quantize(r, want_codes=True)
+    r_host, codes_host = r.cpu().numpy(), codes.cpu().numpy()
+    assert r_host.nbytes > (1 << 32)
+    tail = 5000
+    spots = (0, (1 << 21) - tail // 2, (1 << 22) - tail // 2, B - tail)
+    for mode in ('all', 1):
+        est = m.estimate_from_y(r_host, snr, N, n_summands_or_proba=mode)
+        e64 = m.estimate_from_codes(codes_host, snr, N, n_summands_or_proba=mode)
+        assert est.shape == (B, N) and e64.shape == (B, N)
+        for p in spots:
+            ref = m.estimate_from_y(r[p:p + tail].contiguous(), snr, N, n_summands_or_proba=mode).cpu().numpy()
+            assert np.array_equal(est[p:p + tail], ref), (mode, p)
+            assert np.array_equal(e64[p:p + tail], ref.astype(np.complex64)), (mode, p)
+        del est, e64
