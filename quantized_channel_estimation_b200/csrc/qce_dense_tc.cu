@@ -54,7 +54,16 @@ __host__ __device__ constexpr int tc2_rank_comp_bytes(int nt, int tri16, int ksp
 // launches of the large shapes, whose pilot tiles leave less than 100 KB for the ring)
 // AC = 2: pilots that are not on an integer grid (Lloyd-Max labels, unquantised data) are staged as an FP16 (hi, lo) pair of tile
 // images; the hi parameter image is then multiplied with both (three tensor passes instead of two)
-template <int KD_, int NZ, int NH, int CG, int ORDER = 0, int AC = 1>
+// ACCB = 2: two TMEM accumulators per pilot tile.  The whitening-only launch of the fused shapes (NZ <= 128, NH = 0) uses 256 of the
+// 512 columns and its MMAs per component are short (N' = 128 ... 16), so with one accumulator per tile the chain MMA(k) -> epilogue(k)
+// -> MMA(k+1) of a tile was the cycle: tensor pipe 61 % active (profiles/r02_top1_whitening_ncu_summary.txt).  With two, the MMAs of
+// component k+1 run while the epilogue drains component k.  (The row-block launches of these shapes -- NZ = 0, NH <= 128 -- would fit
+// two accumulators as well; measured, neither the weighted nor the bucketed form gains: 1350 / 275 us either way.)
+__host__ __device__ constexpr int tc_accb(int epi, int kd, int nz, int nh, int order, int ac) {
+    return (epi == 1 && nh == 0 && order == 0 && 2 * ((ac == 2 && kd > 128) ? 1 : TILES) * nz <= 512) ? 2 : 1;
+}
+
+template <int KD_, int NZ, int NH, int CG, int ORDER = 0, int AC = 1, int ACCB_ = 1>
 struct TcCfg {
     static constexpr int KD = KD_;                                  // GEMM reduction length 2*n_obs
     static constexpr int NT = NZ + NH;                              // fused MMA N: Z columns then H columns
@@ -72,10 +81,13 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = (CG == 2) ? (CB0 + CB1) : NT * (KD / 2) * 2;
     static constexpr int CTRL_BYTES = 1024;
     static constexpr int STAGES_FIT = (SMEM_LIMIT - NTILES * A_TILE_BYTES - CTRL_BYTES) / STAGE_BYTES;
+    // (more than 8 stages do not help -- the whitening-only launch waits as long for operands with 16 -- and the weighted combine
+    // launch of the fused shapes got 12 % SLOWER with 10 instead of 8: profiles/r02_whitening_notes.md)
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int SMEM_BYTES = NTILES * A_TILE_BYTES + STAGES * STAGE_BYTES + CTRL_BYTES;
     static constexpr int COMP_HALFS = 2 * NT * KD;                  // CG=1: halfs per component image: hi then lo
-    static constexpr int TMEM_COLS_USED = NTILES * NT;
+    static constexpr int ACCB = ACCB_;
+    static constexpr int TMEM_COLS_USED = NTILES * NT * ACCB;
     static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
                                      : TMEM_COLS_USED <= 256 ? 256 : 512;
     static_assert(STAGES >= (ORDER == 0 ? NCHUNK + 1 : 2), "tile-major schedule keeps the chunks of a component resident plus one prefetch");
@@ -89,7 +101,7 @@ struct TcCfg {
 // control block at the end of dynamic smem
 struct TcCtrl {
     uint64_t full[8], empty[8];
-    uint64_t acc_full[TILES], acc_empty[TILES];
+    uint64_t acc_full[2 * TILES], acc_empty[2 * TILES];      // [tile * ACCB + buffer]
     uint64_t a_full, a_free;
     uint32_t tmem_base;
     uint32_t pad;
@@ -244,7 +256,11 @@ __device__ __noinline__ bool pair_greater_f64(float hi_a, float lo_a, float hi_b
 template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC, bool PRO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a) {
     constexpr int NZ = 32 * NCHZ, NH = 32 * NCHH;
-    using Cfg = TcCfg<32 * KDC, NZ, NH, CG, ORDER, AC>;
+    constexpr int ACCB = tc_accb(EPI, 32 * KDC, NZ, NH, ORDER, AC);
+    // (a second issuer warp, one per tile, was tried for this launch: the UTCHMMA issue of one thread is not the limit -- with two
+    // issuers each spends as long issuing half as many MMAs, i.e. the issue stalls on the tensor pipe's queue -- and the launch got
+    // 2 % slower: profiles/r02_whitening_notes.md)
+    using Cfg = TcCfg<32 * KDC, NZ, NH, CG, ORDER, AC, ACCB>;
     constexpr int S = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         // CG=2: the leader's "full" barriers also collect one remote arrival from the peer CTA ("my half has landed too")
         const uint32_t full_count = (CG == 2 && rank == 0) ? 2 : 1;
         for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&ctrl->full[i]), full_count); mbar_init(smem_u32(&ctrl->empty[i]), 1); }
-        for (int t = 0; t < TILES; ++t) {
+        for (int t = 0; t < 2 * TILES; ++t) {
             mbar_init(smem_u32(&ctrl->acc_full[t]), 1);
             mbar_init(smem_u32(&ctrl->acc_empty[t]), 4 * CG);       // one arrival per epilogue warp (of both CTAs)
         }
@@ -359,6 +375,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             int stage0 = 0;                          // ring slot / parity of chunk 0 of the current component
             uint32_t phase0 = 0, a_phase = 0;
             uint32_t eph0 = 0, eph1 = 0;             // parity of acc_empty[t] waited on next
+            uint32_t ephb = 0, accn = 0;             // ACCB = 2: parity bits per (tile, buffer), components issued so far
             long long w_empty = 0, w_full = 0, w_a = 0, t_begin = QCE_CLK();
             for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
                 const long long ca = QCE_CLK();
@@ -373,11 +390,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     for (int t = 0; t < NTILES; ++t) {
                         // the first MMA overwrites the accumulator: the epilogue must have drained component k-1
                         long long c0 = QCE_CLK();
-                        if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
+                        uint32_t ai = t;                        // accumulator of this (tile, component)
+                        if (ACCB == 2) {
+                            ai = t * 2 + (accn & 1u);
+                            mbar_wait(smem_u32(&ctrl->acc_empty[0]) + 8u * ai, ((ephb >> ai) & 1u) ^ 1u);
+                            ephb ^= 1u << ai;
+                        } else if (t == 0) { mbar_wait(smem_u32(&ctrl->acc_empty[0]), eph0 ^ 1); eph0 ^= 1; }
                         else { mbar_wait(smem_u32(&ctrl->acc_empty[1]), eph1 ^ 1); eph1 ^= 1; }
                         tc_fence_after();
                         w_empty += QCE_CLK() - c0;
-                        const uint32_t d_tile = tmem_base + t * NT;
+                        const uint32_t d_tile = tmem_base + ai * NT;
                         const uint32_t a_lo_t = a_lo0 + t * (Cfg::A_TILE_BYTES >> 4);
                         int stage = stage0;
                         uint32_t phase = phase0;
@@ -393,10 +415,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                             if (t == NTILES - 1 && elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->empty[stage])); else tc_commit(smem_u32(&ctrl->empty[stage])); }
                             if (++stage == S) { stage = 0; phase ^= 1; }
                         }
-                        if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->acc_full[t])); else tc_commit(smem_u32(&ctrl->acc_full[t])); }
+                        if (elected) { if (CG == 2) tc_commit2(smem_u32(&ctrl->acc_full[0]) + 8u * ai); else tc_commit(smem_u32(&ctrl->acc_full[0]) + 8u * ai); }
                         __syncwarp();
                         if (t == NTILES - 1) { stage0 = stage; phase0 = phase; }
                     }
+                    ++accn;
                     } else {
                     // chunk-major: a chunk feeds both tiles and is released at once
                     #pragma unroll
@@ -453,9 +476,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
         const int t = (warp - 4) >> 2;                 // tile within the pair
         const int wq = warp & 3;                       // TMEM lane quadrant of this warp
         const int row = wq * 32 + lane;
-        const uint32_t tz = tmem_base + ((uint32_t)(wq * 32) << 16) + t * (NZ + NH);
+        const uint32_t tz = tmem_base + ((uint32_t)(wq * 32) << 16) + t * ACCB * (NZ + NH);
         const uint32_t th = tz + NZ;
-        uint32_t fph = 0;
+        uint32_t fph = 0;                              // parity of acc_full (one bit per accumulator buffer of this tile)
+        uint32_t accn = 0;                             // components drained so far (ACCB = 2: buffer = accn & 1)
         const int N = a.N;
         // PRO: items of a work unit per epilogue warp, and how they are spread over the components of the previous unit
         constexpr int FMT_IPW = NTILES * (TILE_M / 8) * (Cfg::KD / 8) / 8;
@@ -530,24 +554,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 }
                 // ---- whitened residual -> quadratic form
                 c0 = QCE_CLK();
-                mbar_wait(smem_u32(&ctrl->acc_full[t]), fph);
-                fph ^= 1;
+                const uint32_t ab = (ACCB == 2) ? (accn & 1u) : 0u;
+                const uint32_t ai = t * ACCB + ab;
+                ++accn;
+                mbar_wait(smem_u32(&ctrl->acc_full[0]) + 8u * ai, (fph >> ab) & 1u);
+                fph ^= 1u << ab;
+                const uint32_t tzk = tz + ab * (NZ + NH), thk = th + ab * (NZ + NH);
                 tc_fence_after();
                 long long c1 = QCE_CLK();
                 w_acc += c1 - c0;
                 float va[32], vb[32];
                 float p;
+                // whitening-only launch with at most 128 whitened columns: the whole row fits in registers (there is no estimate row to
+                // keep), so it is fetched at once and the accumulator is handed back to the tensor core BEFORE the arithmetic
+                constexpr bool EARLY = (EPI == 1 && NCHZ <= 4);
+                float vall[EARLY ? NCHZ : 1][32];
                 if (EPI != 2) {
                 float q_hi = 0.f, q_lo = 0.f;        // quadratic form as an unevaluated FP32 pair (TwoSum accumulation)
+                if (EARLY) {
+                    #pragma unroll
+                    for (int ch = 0; ch < NCHZ; ++ch) tmem_ld32(tzk + ch * 32, vall[EARLY ? ch : 0]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(smem_u32(&ctrl->acc_empty[0]) + 8u * ai, 0); else mbar_arrive(smem_u32(&ctrl->acc_empty[0]) + 8u * ai);
+                    }
+                } else {
                 // TMEM loads are double-buffered: chunk ch+1 (and finally the first H chunk) is in flight while chunk ch is
                 // reduced, so their latency stays off the accumulator-release critical path
-                tmem_ld32(tz, va);
+                tmem_ld32(tzk, va);
                 tmem_ld_wait();
+                }
                 #pragma unroll
                 for (int ch = 0; ch < NCHZ; ++ch) {
-                    float (&v)[32] = (ch & 1) ? vb : va;
+                    float (&v)[32] = EARLY ? vall[EARLY ? ch : 0] : ((ch & 1) ? vb : va);
                     float (&vn)[32] = (ch & 1) ? va : vb;
-                    if (ch + 1 < NCHZ) tmem_ld32(tz + (ch + 1) * 32, vn); else if (EPI == 0) tmem_ld32(th, vn);
+                    if (!EARLY) { if (ch + 1 < NCHZ) tmem_ld32(tzk + (ch + 1) * 32, vn); else if (EPI == 0) tmem_ld32(thk, vn); }
                     #pragma unroll
                     for (int g16 = 0; g16 < 2; ++g16) {
                         float2 s0 = make_float2(0.f, 0.f), s1 = s0;
@@ -572,7 +615,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                             q_hi = tt;
                         }
                     }
-                    tmem_ld_wait();
+                    if (!EARLY) tmem_ld_wait();
                 }
                 if (!OFFS) { const float zs2 = zs * zs; q_hi *= zs2; q_lo *= zs2; }   // power of two: exact
                 // l = logc - q as a pair: hi part plus the exact rounding error of the subtraction
@@ -615,7 +658,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 }
                 } else {
                     p = w_k;                         // given weight; the first H chunk has to be fetched here
-                    if (__any_sync(0xffffffffu, p != 0.f)) { tmem_ld32(th, (NCHZ & 1) ? vb : va); tmem_ld_wait(); }
+                    if (__any_sync(0xffffffffu, p != 0.f)) { tmem_ld32(thk, (NCHZ & 1) ? vb : va); tmem_ld_wait(); }
                 }
                 long long c2 = QCE_CLK();
                 c_z += c2 - c1;
@@ -627,7 +670,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     for (int ch = 0; ch < NCHH; ++ch) {
                         float (&v)[32] = ((NCHZ + ch) & 1) ? vb : va;
                         float (&vn)[32] = ((NCHZ + ch) & 1) ? va : vb;
-                        if (ch + 1 < NCHH && any) tmem_ld32(th + (ch + 1) * 32, vn);
+                        if (ch + 1 < NCHH && any) tmem_ld32(thk + (ch + 1) * 32, vn);
                         if (any) {
                             #pragma unroll
                             for (int u = 0; u < 16; ++u) {
@@ -641,10 +684,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         tmem_ld_wait();
                     }
                 }
+                if (!EARLY) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {        // one arrival per warp on the LEADER's barrier
-                    if (CG == 2) mbar_arrive_cluster(smem_u32(&ctrl->acc_empty[t]), 0); else mbar_arrive(smem_u32(&ctrl->acc_empty[t]));
+                    if (CG == 2) mbar_arrive_cluster(smem_u32(&ctrl->acc_empty[0]) + 8u * ai, 0); else mbar_arrive(smem_u32(&ctrl->acc_empty[0]) + 8u * ai);
+                }
                 }
                 if (PRO && fmt_now) { if (a.obs_h_c64) fmt_store<true>(a, fmt_tile0, Cfg::KD, fmt_item, lane, fit); else fmt_store<false>(a, fmt_tile0, Cfg::KD, fmt_item, lane, fit); }
                 c_h += QCE_CLK() - c2;
@@ -1752,7 +1797,7 @@ qce_status tc_pack_params(qce_model* m, cudaStream_t s) {
 
 template <int KDC, int NCHZ, int NCHH, bool OFFS, int CG, int EPI, int ORDER, int AC = 1, bool PRO = false>
 static qce_status launch_cfg(const TcArgs& a, cudaStream_t s) {
-    using Cfg = TcCfg<32 * KDC, 32 * NCHZ, 32 * NCHH, CG, ORDER, AC>;
+    using Cfg = TcCfg<32 * KDC, 32 * NCHZ, 32 * NCHH, CG, ORDER, AC, tc_accb(EPI, 32 * KDC, 32 * NCHZ, 32 * NCHH, ORDER, AC)>;
     static PerDeviceOnce once;
     auto kern = dense_tc_kernel<KDC, NCHZ, NCHH, OFFS, CG, EPI, ORDER, AC, PRO>;
     const int dev = current_device();
@@ -1853,12 +1898,29 @@ static qce_status tc_run_split(const qce_model* m, const TileScratch* ts, cudaSt
     a.h_col0 = part * p.part_cols;
     a.count_rows = part == 0;
     const int cz = m->n_obs / 16, ch = p.part_cols / 32;
-#define QCE_TC_SPLIT_CASE(Z, H) if (cz == Z && ch == H) return launch_split<Z, H>(a, p.has_offsets, epi, p.split_a, s);
+    // QCE_TC_PROF (with a -DQCE_TC_PROFILE build): per-role cycle counters of CTA 0, printed per launch
+    static long long* prof = nullptr;
+    static const bool want_prof = getenv("QCE_TC_PROF") != nullptr;
+    if (want_prof && !prof) { cudaMalloc(&prof, 16 * sizeof(long long)); }
+    if (want_prof) { cudaMemsetAsync(prof, 0, 16 * sizeof(long long), s); a.prof = prof; }
+    qce_status st = QCE_ERR_UNSUPPORTED;
+    bool hit = false;
+#define QCE_TC_SPLIT_CASE(Z, H) if (!hit && cz == Z && ch == H) { st = launch_split<Z, H>(a, p.has_offsets, epi, p.split_a, s); hit = true; }
     QCE_TC_SPLIT_CASE(8, 4) QCE_TC_SPLIT_CASE(6, 3)
     QCE_TC_SPLIT_CASE(4, 4) QCE_TC_SPLIT_CASE(2, 2) QCE_TC_SPLIT_CASE(1, 1) QCE_TC_SPLIT_CASE(3, 3) QCE_TC_SPLIT_CASE(4, 2) QCE_TC_SPLIT_CASE(2, 1)
 #undef QCE_TC_SPLIT_CASE
-    set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant);
-    return QCE_ERR_UNSUPPORTED;
+    if (!hit) {
+        set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant);
+        return QCE_ERR_UNSUPPORTED;
+    }
+    if (want_prof && st == QCE_OK) {
+        long long h[16];
+        cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "[qce tc prof] epi %d B=%lld K=%d | mma: total %lld wait_acc_empty %lld wait_full %lld wait_a %lld | epi t0: wait %lld z %lld h %lld | epi t1: wait %lld z %lld h %lld\n",
+                epi, (long long)B, a.K, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8], h[9], h[10]);
+    }
+    return st;
 }
 
 static qce_status tc_run(const qce_model* m, const TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
