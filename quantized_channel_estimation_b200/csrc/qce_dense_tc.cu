@@ -724,9 +724,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     for (int j = 0; j < NH / 4; ++j) atomicAdd(out + j, make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y));
                 } else {
                 if (a.h_est) {
+                    // 256-bit stores (sm_100: st.global.v4.f64): every lane writes whole 32-byte sectors of its own row, and half as many
+                    // stores wait for the register pair of the previous conversion to be read (the F2F -> STG chain was 83 % of the
+                    // one-component combine launch, profiles/r02_whitening_notes.md).  Rows are 32-byte aligned (N is a multiple of 2).
                     double2* out = a.h_est + g * N + (a.h_col0 >> 1);
                     #pragma unroll
-                    for (int j = 0; j < NH / 2; ++j) out[j] = make_double2((double)(acc[j].x * invs), (double)(acc[j].y * invs));
+                    for (int j = 0; j < NH / 2; j += 2)
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out + j), "d"((double)(acc[j].x * invs)), "d"((double)(acc[j].y * invs)),
+                                     "d"((double)(acc[j + 1].x * invs)), "d"((double)(acc[j + 1].y * invs)) : "memory");
                 }
                 if (a.acc && a.h_true) {
                     float errf = 0.f, pwf = 0.f;
