@@ -727,26 +727,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                     // 256-bit stores (sm_100: st.global.v4.f64): every lane writes whole 32-byte sectors of its own row, and half as many
                     // stores wait for the register pair of the previous conversion to be read (the F2F -> STG chain was 83 % of the
                     // one-component combine launch, profiles/r02_whitening_notes.md).  Rows are 32-byte aligned (N is a multiple of 2).
+                    // (caller's buffers that are only 16-byte aligned take the 128-bit form)
                     double2* out = a.h_est + g * N + (a.h_col0 >> 1);
-                    #pragma unroll
-                    for (int j = 0; j < NH / 2; j += 2)
-                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out + j), "d"((double)(acc[j].x * invs)), "d"((double)(acc[j].y * invs)),
-                                     "d"((double)(acc[j + 1].x * invs)), "d"((double)(acc[j + 1].y * invs)) : "memory");
+                    if (a.wide_io) {
+                        #pragma unroll
+                        for (int j = 0; j < NH / 2; j += 2)
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out + j), "d"((double)(acc[j].x * invs)), "d"((double)(acc[j].y * invs)),
+                                         "d"((double)(acc[j + 1].x * invs)), "d"((double)(acc[j + 1].y * invs)) : "memory");
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < NH / 2; ++j) out[j] = make_double2((double)(acc[j].x * invs), (double)(acc[j].y * invs));
+                    }
                 }
                 if (a.acc && a.h_true) {
                     float errf = 0.f, pwf = 0.f;
-                    #pragma unroll
-                    for (int j = 0; j < NH / 2; ++j) {      // full unroll: acc[] must stay in registers
-                        float2 h;
-                        if (a.h_true_c64) {
-                            h = reinterpret_cast<const float2*>(a.h_true)[g * N + (a.h_col0 >> 1) + j];
-                        } else {
-                            const double2 hd = reinterpret_cast<const double2*>(a.h_true)[g * N + (a.h_col0 >> 1) + j];
-                            h = make_float2((float)hd.x, (float)hd.y);
-                        }
-                        const float dx = acc[j].x * invs - h.x, dy = acc[j].y * invs - h.y;
+                    auto nmse_term = [&](const int j, const float hx, const float hy) {
+                        const float dx = acc[j].x * invs - hx, dy = acc[j].y * invs - hy;
                         errf = fmaf(dx, dx, fmaf(dy, dy, errf));
-                        pwf = fmaf(h.x, h.x, fmaf(h.y, h.y, pwf));
+                        pwf = fmaf(hx, hx, fmaf(hy, hy, pwf));
+                    };
+                    // the true channel row of this pilot, 32 bytes (whole sectors) per load: 256-bit loads as for the stores above
+                    if (!a.wide_io) {
+                        #pragma unroll
+                        for (int j = 0; j < NH / 2; ++j) {      // full unroll: acc[] must stay in registers
+                            if (a.h_true_c64) {
+                                const float2 h = reinterpret_cast<const float2*>(a.h_true)[g * N + (a.h_col0 >> 1) + j];
+                                nmse_term(j, h.x, h.y);
+                            } else {
+                                const double2 hd = reinterpret_cast<const double2*>(a.h_true)[g * N + (a.h_col0 >> 1) + j];
+                                nmse_term(j, (float)hd.x, (float)hd.y);
+                            }
+                        }
+                    } else if (a.h_true_c64) {
+                        const float2* ht = reinterpret_cast<const float2*>(a.h_true) + g * N + (a.h_col0 >> 1);
+                        #pragma unroll
+                        for (int j = 0; j < NH / 2; j += 4) {
+                            float h0, h1, h2, h3, h4, h5, h6, h7;
+                            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=f"(h0), "=f"(h1), "=f"(h2), "=f"(h3), "=f"(h4), "=f"(h5), "=f"(h6), "=f"(h7) : "l"(ht + j));
+                            nmse_term(j, h0, h1); nmse_term(j + 1, h2, h3); nmse_term(j + 2, h4, h5); nmse_term(j + 3, h6, h7);
+                        }
+                    } else {
+                        const double2* ht = reinterpret_cast<const double2*>(a.h_true) + g * N + (a.h_col0 >> 1);
+                        #pragma unroll
+                        for (int j = 0; j < NH / 2; j += 2) {
+                            double d0, d1, d2, d3;
+                            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d0), "=d"(d1), "=d"(d2), "=d"(d3) : "l"(ht + j));
+                            nmse_term(j, (float)d0, (float)d1); nmse_term(j + 1, (float)d2, (float)d3);
+                        }
                     }
                     err += (double)errf;
                     pw += (double)pwf;
@@ -1878,6 +1906,7 @@ static void tc_fill_args(const qce_model* m, const TileScratch* ts, int64_t B, d
     a.tri = p.triangular ? 1 : 0;
     a.prof = nullptr;
     a.h_stride = 2 * m->n_ant; a.h_col0 = 0; a.count_rows = 1;
+    a.wide_io = (reinterpret_cast<uintptr_t>(h_est) % 32 == 0 && reinterpret_cast<uintptr_t>(h_true) % 32 == 0 && m->n_ant % 4 == 0) ? 1 : 0;
     const char* th = getenv("QCE_TC_SKIP");                 // tuning knob (read per launch); measured: no effect up to 1e-9
     a.skip_thresh = th ? (float)atof(th) : 1e-30f;
     a.unit_comp = nullptr; a.perm = nullptr; a.n_units_dev = nullptr; a.unit_list = nullptr; a.unit_nk = nullptr;

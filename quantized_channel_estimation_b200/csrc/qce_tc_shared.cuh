@@ -53,6 +53,7 @@ struct TcArgs {
     int h_stride;              // floats per component in hoff (2N)
     int h_col0;
     int count_rows;            // add the number of rows to acc[2] (only one of the H-part launches does)
+    int wide_io;               // h_est and h_true are 32-byte aligned: rows are written / read with 256-bit accesses
     // fused prologue (PRO kernels): the kernel observes + quantises + formats its own pilot tiles into a_img / bad
     const void* obs_h;         // [B][No] c64 / c128 channels
     const double2* obs_noise;  // [B][No] c128

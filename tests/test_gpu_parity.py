@@ -1486,3 +1486,30 @@ def test_host_arrays_beyond_4_gib(qce):
             assert np.array_equal(est[p:p + tail], ref), (mode, p)
             assert np.array_equal(e64[p:p + tail], ref.astype(np.complex64)), (mode, p)
         del est, e64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [torch.complex64, torch.complex128])
+def test_pipeline_with_buffers_that_are_not_32_byte_aligned(qce, dtype):
+    """Estimate rows and true-channel rows move with 256-bit accesses when the caller's buffers are 32-byte aligned; buffers that are
+    not (a view one element into an allocation) take the 128-bit form: same NMSE accumulators."""
+    from quantized_channel_estimation_b200 import engine, precompute
+    K, N, B, snr = 8, 64, 5000, 10
+    means, covs, w = orc.random_psd_gmm(K, N, seed=2)
+    h, noise, _ = orc.sample_gmm_channels(means, covs, w, B, seed=3)
+    model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, 1, 'uniform', (None, None, None)))
+    quant = engine.Quantizer.get(1)
+    noise_t = torch.from_numpy(noise).cuda()
+    h_al = torch.from_numpy(h).cuda().to(dtype).contiguous()
+    buf = torch.empty(B * N + 1, dtype=dtype, device='cuda')
+    h_off = buf[1:].view(B, N)
+    h_off.copy_(h_al)
+    assert h_al.data_ptr() % 32 == 0 and h_off.data_ptr() % 32 != 0
+    accs = []
+    for hh in (h_al, h_off):
+        for mode in ('all', 1, 3):
+            accs.append(model.pipeline(quant, hh, noise_t, 10 ** (-snr / 20), mode, 'tc').cpu().numpy())
+    half = len(accs) // 2
+    for a, b in zip(accs[:half], accs[half:]):
+        assert a[2] == B and b[2] == B
+        assert np.allclose(a, b, rtol=1e-6, atol=0)
