@@ -57,10 +57,11 @@ __host__ __device__ constexpr int tc2_rank_comp_bytes(int nt, int tri16, int ksp
 // ACCB = 2: two TMEM accumulators per pilot tile.  The whitening-only launch of the fused shapes (NZ <= 128, NH = 0) uses 256 of the
 // 512 columns and its MMAs per component are short (N' = 128 ... 16), so with one accumulator per tile the chain MMA(k) -> epilogue(k)
 // -> MMA(k+1) of a tile was the cycle: tensor pipe 61 % active (profiles/r02_top1_whitening_ncu_summary.txt).  With two, the MMAs of
-// component k+1 run while the epilogue drains component k.  (The row-block launches of these shapes -- NZ = 0, NH <= 128 -- would fit
-// two accumulators as well; measured, neither the weighted nor the bucketed form gains: 1350 / 275 us either way.)
+// component k+1 run while the epilogue drains component k.  The fused launch of the small shapes (N <= 32: Z|H is at most 128 columns)
+// gains the same way: config 1 (N = 32, K = 16) 0.86 -> 0.74 ms per 2^20 pilots.  (The row-block launches -- NZ = 0, NH <= 128 -- would
+// fit two accumulators as well; measured, neither the weighted nor the bucketed form gains: 1350 / 275 us either way.)
 __host__ __device__ constexpr int tc_accb(int epi, int kd, int nz, int nh, int order, int ac) {
-    return (epi == 1 && nh == 0 && order == 0 && 2 * ((ac == 2 && kd > 128) ? 1 : TILES) * nz <= 512) ? 2 : 1;
+    return (((epi == 1 && nh == 0) || epi == 0) && order == 0 && 2 * ((ac == 2 && kd > 128) ? 1 : TILES) * (nz + nh) <= 512) ? 2 : 1;
 }
 
 template <int KD_, int NZ, int NH, int CG, int ORDER = 0, int AC = 1, int ACCB_ = 1>
