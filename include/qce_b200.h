@@ -14,6 +14,9 @@
  *   - plain C types only; complex arrays are interleaved (re, im) doubles ("c128") or floats ("c64"),
  *     row-major, exactly numpy's / torch's memory layout;
  *   - "dev" pointers are CUDA device pointers owned by the caller, "host" pointers are host memory;
+ *     device arrays need the alignment of their element type (16 bytes for c128, 8 for c64); estimate and
+ *     true-channel arrays that are 32-byte aligned (every cudaMalloc / torch allocation is) are moved with
+ *     256-bit accesses by the tensor-core path, others with 128-bit ones -- same results;
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all device work is
  *     enqueued on it and the call returns without synchronising unless stated otherwise;
  *   - every function returns QCE_OK (0) or a negative qce_status; qce_last_error_string() gives
