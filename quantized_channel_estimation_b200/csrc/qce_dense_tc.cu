@@ -1241,6 +1241,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float
         float m_hi = -INFINITY;
         int amax = 0;
         bool tie = false;
+        #pragma unroll 8
         for (int k = 0; k < K; ++k) {
             const float hi = s_hi[k * P + r];
             if (hi != hi) tie = true;
@@ -1253,6 +1254,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float
         if (logc) tie_eps *= fmax(1.0, (__ldg(logc + amax) - mx) * inv_nobs);
         const float epsf = (float)tie_eps;
         float d2 = -INFINITY, sumf = 0.f;            // runner-up (relative to the maximum), normaliser
+        #pragma unroll 8
         for (int k = 0; k < K; ++k) {
             const float d = (s_hi[k * P + r] - m_hi) + (s_lo[k * P + r] - m_lo);
             if (k != amax && d > d2) d2 = d;
@@ -1270,6 +1272,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float
             const float inv_sum = 1.f / sumf;
             const bool count = pair_cnt != nullptr && bad[row0 + r] == 0;
             if (mode == QCE_MODE_ALL) {
+                #pragma unroll 8
                 for (int k = 0; k < K; ++k) {
                     const float wk = s_hi[k * P + r] * inv_sum;
                     s_hi[k * P + r] = wk;
@@ -1277,6 +1280,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float
                 }
             } else {
                 // descending selection: selected entries move to s_lo (responsibilities), their s_hi slot becomes -1
+                #pragma unroll 8
                 for (int k = 0; k < K; ++k) s_lo[k * P + r] = 0.f;
                 const int limit = (mode == QCE_MODE_TOPN) ? (n_top < K ? n_top : K) : K;
                 double cum = 0.0;
@@ -1285,6 +1289,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float
                 for (int it = 0; it <= limit; ++it) {
                     float bvf = -1.f;
                     int bk = -1;
+                    #pragma unroll 8
                     for (int k = 0; k < K; ++k) { const float e = s_hi[k * P + r]; if (e > bvf) { bvf = e; bk = k; } }
                     if (bk < 0) break;                        // no candidates left
                     const float bv = bvf * inv_sum;
@@ -1299,6 +1304,7 @@ __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float
                     }
                 }
                 const float inv_cum = (float)(1.0 / cum);
+                #pragma unroll 8
                 for (int k = 0; k < K; ++k) {
                     const float sel = s_lo[k * P + r];
                     const float wk = sel > 0.f ? sel * inv_cum : 0.f;
