@@ -61,7 +61,7 @@ __host__ __device__ constexpr int tc2_rank_comp_bytes(int nt, int tri16, int ksp
 // gains the same way: config 1 (N = 32, K = 16) 0.86 -> 0.74 ms per 2^20 pilots.  (The row-block launches -- NZ = 0, NH <= 128 -- would
 // fit two accumulators as well; measured, neither the weighted nor the bucketed form gains: 1350 / 275 us either way.)
 __host__ __device__ constexpr int tc_accb(int epi, int kd, int nz, int nh, int order, int ac) {
-    return (((epi == 1 && nh == 0) || epi == 0) && order == 0 && 2 * ((ac == 2 && kd > 128) ? 1 : TILES) * (nz + nh) <= 512) ? 2 : 1;
+    return (((epi == 1 && nh == 0) || epi == 0 || epi == 3) && order == 0 && 2 * ((ac == 2 && kd > 128) ? 1 : TILES) * (nz + nh) <= 512) ? 2 : 1;
 }
 
 template <int KD_, int NZ, int NH, int CG, int ORDER = 0, int AC = 1, int ACCB_ = 1>
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 for (int ch = 0; ch < NCHZ; ++ch) {
                     float (&v)[32] = EARLY ? vall[EARLY ? ch : 0] : ((ch & 1) ? vb : va);
                     float (&vn)[32] = (ch & 1) ? va : vb;
-                    if (!EARLY) { if (ch + 1 < NCHZ) tmem_ld32(tzk + (ch + 1) * 32, vn); else if (EPI == 0) tmem_ld32(thk, vn); }
+                    if (!EARLY) { if (ch + 1 < NCHZ) tmem_ld32(tzk + (ch + 1) * 32, vn); else if (EPI == 0 || EPI == 3) tmem_ld32(thk, vn); }
                     #pragma unroll
                     for (int g16 = 0; g16 < 2; ++g16) {
                         float2 s0 = make_float2(0.f, 0.f), s1 = s0;
@@ -623,8 +623,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 const float l_hi = lc.x - q_hi;
                 const float bq = l_hi - lc.x;
                 const float l_lo = ((lc.x - (l_hi - bq)) + (-q_hi - bq)) + (lc.y - q_lo);
-                if (EPI == 1) {
-                    if (a.top_out) {
+                if (EPI == 1 || EPI == 3) {
+                    if (EPI == 3 || a.top_out) {
                         // top-1 label only.  tc_select_kernel compares the FP64 sums hi + lo; the same decision in FP32 (FP64
                         // arithmetic next to the saturated tensor pipe cost 18 % of this launch): the difference of the pairs,
                         // with the exact FP64 comparison only where its rounding error could change the sign
@@ -637,8 +637,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                         if (__any_sync(0xffffffffu, !safe)) { if (!safe) better = pair_greater_f64(l_hi, l_lo, best_hi, best_lo); }
                         if (better) { second = best_hi + best_lo; best_hi = l_hi; best_lo = l_lo; best_k = k; best_q = q_hi; }
                         else second = fmaxf(second, l_hi + l_lo);
-                    } else if (tile_base + row < a.B) a.lp_out[(tile_base + row) * a.K + k] = make_float2(l_hi, l_lo);
-                    p = 0.f;
+                        p = 0.f;
+                        if (EPI == 3 && better) {      // fused hard selection: the estimate row restarts with this component's LMMSE row
+                            p = 1.f;
+                            #pragma unroll
+                            for (int j = 0; j < NH / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+                        }
+                    } else {
+                        if (tile_base + row < a.B) a.lp_out[(tile_base + row) * a.K + k] = make_float2(l_hi, l_lo);
+                        p = 0.f;
+                    }
                 } else {
                 // ---- lazily rescaled online softmax (reference maximum moves only on jumps > 8)
                 if (ki == 0) {
@@ -705,6 +713,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
             // ---- finalise: normalise, write the estimate row, NMSE accumulators (FP32 per row: FP64 stalls behind the
             // tensor pipe; the per-row sums enter the FP64 accumulators once)
             const int64_t g = src;
+            bool hard_tie = false;          // EPI = 3: this pilot's selection is too close to call -- the exact path answers it
+            if (EPI == 3 && valid && a.tie_buf) {
+                const float gap = (best_hi - second) + best_lo;
+                hard_tie = !(gap > a.tie_eps * fmaxf(1.f, best_q * a.inv_nobs));
+                // MFA argmax-of-exp quirk (label 0 when every exp(l_k) underflows): anything near or below the underflow edge is exact-path work
+                if ((a.top_flags & QCE_FLAG_TOP1_EXP_ARGMAX) && !(best_hi > -745.f)) hard_tie = true;
+                if (hard_tie) tie_append(a.bad, a.tie_buf, g);
+            }
             if (EPI == 1 && a.top_out && valid) {
                 if ((a.top_flags & QCE_FLAG_TOP1_EXP_ARGMAX) && exp((double)best_hi + (double)best_lo) == 0.0) best_k = 0;
                 a.top_out[g] = best_k;
@@ -716,8 +732,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dense_tc_kernel(const TcArgs a
                 if (tie) tie_append(a.bad, a.tie_buf, g);
             }
             // (flags read here, after the last component: with the fused prologue they are written by other warps of this kernel)
-            if (EPI != 1 && valid && (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) == 0) {
-                const float invs = EPI == 2 ? 1.f : 1.f / ssum;
+            if (EPI != 1 && valid && !hard_tie && (PRO ? __ldcg(a.bad + g) : __ldg(a.bad + g)) == 0) {
+                const float invs = (EPI == 2 || EPI == 3) ? 1.f : 1.f / ssum;
                 if (EPI == 2 && a.slot_w) {      // pair mode: this slot's weighted row is one of several addends of the pilot's estimate:
                     // vector reductions (4 floats each) into the FP32 row of the pilot; tc_pair_finish_kernel writes the estimate
                     float4* out = reinterpret_cast<float4*>(a.pair_acc + (size_t)g * 2 * N + a.h_col0);
@@ -2242,6 +2258,157 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
     return QCE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ fused hard top-1 (small shapes)
+// For N <= 32 (any K) and for K <= 16 the three-launch top-1 path (whitening with in-epilogue label -> regroup -> one-component
+// combine) costs more than the fused 'all' launch (config 1: 0.91 vs 0.75 ms per 2^20 pilots): there EPI = 3 runs the fused Z|H
+// launch with a running argmax in place of the online softmax -- a component that beats the best so far REPLACES the estimate row.
+// Pilots whose best two components are too close to call are neither written nor accumulated; they go on the tie list, get their
+// K log-likelihoods in complex128 (tc_refine_kernel) and an exact label (tc_select_kernel<., true>), and this kernel writes their
+// estimate h = hoff_k + W_k r in complex128 (one warp per listed pilot; the list is 1e-5 .. 1e-3 of the batch).
+struct Top1RowsArgs {
+    int No, N, K;
+    const double2* W;           // [K][N][No]
+    const double2* hoff;        // [K][N]
+    RowSource src;
+    int64_t row0;               // batch row of chunk row 0
+    const int* tie_buf;         // [0] count, then chunk rows
+    const int* top;             // [chunk rows] exact labels of the listed rows
+    double2* h_est;             // chunk base or null
+    const void* h_true;         // chunk base or null
+    int h_true_c64;
+    double* acc;
+};
+
+__global__ void __launch_bounds__(256) tc_top1_rows_kernel(const Top1RowsArgs a) {
+    extern __shared__ __align__(16) unsigned char t1_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2* r_s = reinterpret_cast<double2*>(t1_smem) + (size_t)warp * a.No;
+    const int n_list = __ldg(a.tie_buf);
+    double err = 0.0, pw = 0.0, cnt = 0.0;
+    for (int e = blockIdx.x * 8 + warp; e < n_list; e += gridDim.x * 8) {
+        const int crow = __ldg(a.tie_buf + 1 + e);
+        const int k = __ldg(a.top + crow);
+        for (int j = lane; j < a.No; j += 32) {
+            const int64_t idx = (a.row0 + crow) * a.No + j;
+            double2 v;
+            if (a.src.r) {
+                v = reinterpret_cast<const double2*>(a.src.r)[idx];
+            } else {      // get_observation_nbit with A = I (utils.py:241-251), as in tc_refine_kernel
+                double2 h;
+                if (a.src.obs_h_c64) { const float2 hf = reinterpret_cast<const float2*>(a.src.obs_h)[idx]; h = make_double2((double)hf.x, (double)hf.y); }
+                else h = reinterpret_cast<const double2*>(a.src.obs_h)[idx];
+                const double2 wn = reinterpret_cast<const double2*>(a.src.obs_noise)[idx];
+                const double2 y = make_double2(__dadd_rn(h.x, __dmul_rn(a.src.obs_noise_scale, wn.x)), __dadd_rn(h.y, __dmul_rn(a.src.obs_noise_scale, wn.y)));
+                v = quantize_value(a.src.qt.n_bits, a.src.qt.n_thr, a.src.qt.thr, a.src.qt.labels, y, nullptr);
+            }
+            r_s[j] = v;
+        }
+        __syncwarp();
+        const double2* __restrict__ Wk = a.W + (size_t)k * a.N * a.No;
+        for (int i = lane; i < a.N; i += 32) {
+            double2 h = __ldg(a.hoff + (size_t)k * a.N + i);
+            const double2* __restrict__ Wrow = Wk + (size_t)i * a.No;
+            for (int j = 0; j < a.No; ++j) {
+                const double2 w = __ldg(Wrow + j), r = r_s[j];
+                h.x = fma(w.x, r.x, h.x); h.x = fma(-w.y, r.y, h.x);
+                h.y = fma(w.x, r.y, h.y); h.y = fma(w.y, r.x, h.y);
+            }
+            if (a.h_est) a.h_est[(size_t)crow * a.N + i] = h;
+            if (a.acc && a.h_true) {
+                double2 t;
+                if (a.h_true_c64) { const float2 tf = reinterpret_cast<const float2*>(a.h_true)[(size_t)crow * a.N + i]; t = make_double2((double)tf.x, (double)tf.y); }
+                else t = reinterpret_cast<const double2*>(a.h_true)[(size_t)crow * a.N + i];
+                const double dx = h.x - t.x, dy = h.y - t.y;
+                err += dx * dx + dy * dy;
+                pw += t.x * t.x + t.y * t.y;
+            }
+        }
+        if (lane == 0) cnt += 1.0;
+        __syncwarp();
+    }
+    if (!a.acc) return;
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        err += __shfl_xor_sync(0xffffffffu, err, off);
+        pw += __shfl_xor_sync(0xffffffffu, pw, off);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    if (lane == 0 && cnt > 0.0) { atomicAdd(a.acc + 0, err); atomicAdd(a.acc + 1, pw); atomicAdd(a.acc + 2, cnt); }
+}
+
+// shapes the fused hard top-1 launch is used for (QCE_TC_HARD=1 / 0 forces it on / off where it is instantiated)
+static bool tc_hard_top1_ok(const qce_model* m) {
+    if (!tc_instantiated(m) || m->tc.split || m->tc.split_a || !m->tc.triangular) return false;
+    if (const char* e = getenv("QCE_TC_HARD")) return atoi(e) != 0;
+    return m->n_obs <= 32 || m->n_comp <= 16;
+}
+
+static qce_status tc_run_hard_top1(qce_model* m, TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
+                                   double* acc) {
+    const int K = m->n_comp;
+    const int64_t unit_rows = 4 * TILE_M;
+    int64_t chunk = (((int64_t)1 << 27) / K) / unit_rows * unit_rows;
+    if (const char* ce = getenv("QCE_TC_MODE_CHUNK")) chunk = atoll(ce) / unit_rows * unit_rows;      // test hook
+    if (chunk < unit_rows) chunk = unit_rows;
+    if (chunk > B) chunk = (B + unit_rows - 1) / unit_rows * unit_rows;
+    const double eps = tc_tie_eps(m);
+    const bool refine = eps > 0.0 && (ts->src.r || ts->src.obs_h);
+    qce_status st = QCE_OK;
+    if (refine) {
+        st = tc_scratch_aux(ts, (size_t)chunk, (size_t)K);                       // tie list, FP32 pairs of the listed pilots
+        if (st) return st;
+        st = tc_scratch_bucket(ts, 0, (size_t)chunk);                            // exact labels of the listed pilots
+        if (st) return st;
+    }
+    const size_t tile_bytes = (size_t)TILE_M * 2 * m->n_obs * sizeof(__half);
+    const size_t true_row = (size_t)m->n_ant * (h_true_c64 ? 8 : 16);
+    const int cz = m->n_obs / 16, ch = m->n_ant / 16;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device());
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = (B - b0) < chunk ? (B - b0) : chunk;
+        TileScratch v = *ts;
+        v.img = (unsigned char*)ts->img + (size_t)(b0 / TILE_M) * tile_bytes;
+        v.bad = (unsigned char*)ts->bad + b0;
+        double* he = h_est ? h_est + (size_t)b0 * m->n_ant * 2 : nullptr;
+        const void* ht = h_true ? (const void*)((const char*)h_true + (size_t)b0 * true_row) : nullptr;
+        TcArgs a;
+        tc_fill_args(m, &v, nb, he, ht, h_true_c64, acc, &a);
+        if (refine) QCE_CUDA_TRY(cudaMemsetAsync(ts->tie_buf, 0, sizeof(int), s));
+        else a.tie_buf = nullptr;                                              // nobody is handed to the exact path: every pilot is answered here
+        const bool offs = m->tc.has_offsets;
+        bool hit = false;
+#define QCE_TC_HARD_CASE(Z, H) if (!hit && cz == Z && ch == H) { st = offs ? launch_cfg<Z, Z, H, true, 2, 3, 0>(a, s) : launch_cfg<Z, Z, H, false, 2, 3, 0>(a, s); hit = true; }
+        QCE_TC_HARD_CASE(4, 4) QCE_TC_HARD_CASE(2, 2) QCE_TC_HARD_CASE(1, 1) QCE_TC_HARD_CASE(3, 3) QCE_TC_HARD_CASE(4, 2) QCE_TC_HARD_CASE(2, 1)
+#undef QCE_TC_HARD_CASE
+        if (!hit) { set_error("tensor-core kernel: n_obs=%d n_ant=%d not instantiated", m->n_obs, m->n_ant); return QCE_ERR_UNSUPPORTED; }
+        if (st) return st;
+        if (!refine) continue;
+        RefineArgs ra;
+        ra.No = m->n_obs; ra.K = K; ra.tri = 1;
+        ra.Linv = (const double2*)m->Linv; ra.zoff = (const double2*)m->zoff; ra.logc = m->logc;
+        ra.src = ts->src; ra.row0 = b0; ra.tie_buf = ts->tie_buf; ra.tie_total = ts->fix_buf + 1;
+        ra.lp2 = (float2*)ts->lp2; ra.logp_out = nullptr;
+        tc_refine_kernel<<<(unsigned)(4 * sms), 256, (size_t)REFINE_RT * m->n_obs * sizeof(double2), s>>>(ra);
+        QCE_CHECK_LAUNCH("tc_refine_kernel");
+        int* top = (int*)ts->bidx;
+        const unsigned sgrid = (unsigned)sms;
+        if (K <= 64) tc_select_kernel<2, true><<<sgrid, 256, 0, s>>>((const float2*)ts->lp2, nb, K, QCE_MODE_TOP1, 1, 0.0, m->flags, nullptr, nullptr, top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0, nullptr, 0.f);
+        else if (K <= 256) tc_select_kernel<8, true><<<sgrid, 256, 0, s>>>((const float2*)ts->lp2, nb, K, QCE_MODE_TOP1, 1, 0.0, m->flags, nullptr, nullptr, top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0, nullptr, 0.f);
+        else tc_select_kernel<32, true><<<sgrid, 256, 0, s>>>((const float2*)ts->lp2, nb, K, QCE_MODE_TOP1, 1, 0.0, m->flags, nullptr, nullptr, top, nullptr, nullptr, 0.0, ts->tie_buf, nullptr, 0.0, nullptr, 0.f);
+        QCE_CHECK_LAUNCH("tc_select_kernel(list)");
+        Top1RowsArgs ta;
+        ta.No = m->n_obs; ta.N = m->n_ant; ta.K = K;
+        ta.W = (const double2*)m->W; ta.hoff = (const double2*)m->hoff;
+        ta.src = ts->src; ta.row0 = b0; ta.tie_buf = ts->tie_buf; ta.top = top;
+        ta.h_est = (double2*)he; ta.h_true = ht; ta.h_true_c64 = h_true_c64; ta.acc = acc;
+        tc_top1_rows_kernel<<<(unsigned)sms, 256, (size_t)8 * m->n_obs * sizeof(double2), s>>>(ta);
+        QCE_CHECK_LAUNCH("tc_top1_rows_kernel");
+        count_launch(3);
+    }
+    return QCE_OK;
+}
+
 qce_status tc_estimate_formatted(qce_model* m, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64, double* acc) {
     TileScratch* ts = nullptr;
     {
@@ -2268,6 +2435,7 @@ qce_status launch_dense_tc(qce_model* m, cudaStream_t s, const double* r, int64_
     qce_status st = tc_format_into(m, s, r, B, &ts);
     if (st) return st;
     if (mode == QCE_MODE_ALL && !logp_out && !m->tc.split) st = tc_run(m, ts, s, B, h_est, h_true, h_true_c64, acc);
+    else if (mode == QCE_MODE_TOP1 && !logp_out && (h_est || acc) && tc_hard_top1_ok(m)) st = tc_run_hard_top1(m, ts, s, B, h_est, h_true, h_true_c64, acc);
     else st = tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
     if (st) return st;
     return tc_fix_rows(m, ts, s, B, mode, n_top, rho, h_est, logp_out, h_true, h_true_c64, acc);
@@ -2322,6 +2490,7 @@ qce_status launch_pipeline_tc(qce_model* m, const QuantTables* qt, cudaStream_t 
     ts->owner = m; ts->rows = B;
     ts->src = obs_src;
     if (mode == QCE_MODE_ALL && !m->tc.split) st = tc_run(m, ts, s, B, h_est, h, h_is_c64, acc);
+    else if (mode == QCE_MODE_TOP1 && (h_est || acc) && tc_hard_top1_ok(m)) st = tc_run_hard_top1(m, ts, s, B, h_est, h, h_is_c64, acc);
     else st = tc_run_modes(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);
     if (st) return st;
     return tc_fix_rows(m, ts, s, B, mode, n_top, rho, h_est, nullptr, h, h_is_c64, acc);

@@ -1513,3 +1513,45 @@ def test_pipeline_with_buffers_that_are_not_32_byte_aligned(qce, dtype):
     for a, b in zip(accs[:half], accs[half:]):
         assert a[2] == B and b[2] == B
         assert np.allclose(a, b, rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('K,N,nb,qt,ms', [(16, 32, 1, 'uniform', 0.0), (64, 32, 1, 'uniform', 0.1), (8, 64, 1, 'uniform', 0.1), (16, 16, 2, 'uniform', 0.0),
+                                         (12, 48, 1, 'uniform', 0.1), (16, 64, 3, 'uniform', 0.0)])
+def test_tc_fused_hard_top1(qce, K, N, nb, qt, ms, monkeypatch):
+    """Small shapes (N <= 32, or K <= 16): top-1 runs as ONE fused launch with a running argmax in place of the online softmax; pilots
+    whose two best components are too close to call are answered by the exact path (complex128 log-likelihoods, exact label, complex128
+    estimate).  Same estimates as the complex128 kernel (no flipped selection), as the three-launch path (QCE_TC_HARD=0), with every
+    pilot sent through the exact path (QCE_TC_TIE_EPS large), and the same NMSE accumulators in the fused pipeline."""
+    from quantized_channel_estimation_b200 import _lib, engine, precompute
+    import ctypes as C
+    snr, B = 5, 40000 + 77
+    means, covs, w, h, noise, qz, r = _case(K, N, B, snr, nb, qt, ms, seed=K + N)
+    m = qce.Gmm_nbit(n_components=K).set_parameters(means, covs, w, detect_structure=False)
+    kw = dict(n_bits=nb, quantizer_type=qt, quantizer=qz)
+    rt = torch.from_numpy(r).cuda()
+    m.precision = 'fp64'
+    ref = m.estimate_from_y(rt, snr, N, n_summands_or_proba=1, **kw)
+    m.precision = 'tc'
+    got = m.estimate_from_y(rt, snr, N, n_summands_or_proba=1, **kw)
+    rows = (got - ref).norm(dim=1) / ref.norm(dim=1).clamp(min=1e-300)
+    assert float(rows.max()) < 1e-4, float(rows.max())                 # no flipped selection
+    assert relerr(got.cpu().numpy(), ref.cpu().numpy()) < TOL_TC
+    monkeypatch.setenv('QCE_TC_HARD', '0')
+    three = m.estimate_from_y(rt, snr, N, n_summands_or_proba=1, **kw)
+    monkeypatch.delenv('QCE_TC_HARD')
+    rows = (got - three).norm(dim=1) / three.norm(dim=1).clamp(min=1e-300)
+    assert float(rows.max()) < 1e-5
+    monkeypatch.setenv('QCE_TC_TIE_EPS', '1e6')                       # everybody is too close to call: the exact path answers the batch
+    exact = m.estimate_from_y(rt[:3000].contiguous(), snr, N, n_summands_or_proba=1, **kw)
+    monkeypatch.delenv('QCE_TC_TIE_EPS')
+    assert relerr(exact.cpu().numpy(), ref[:3000].cpu().numpy()) < 1e-10
+    # fused pipeline: NMSE accumulators of the hard launch + exact rows == those of the complex128 kernel
+    if nb == 1:
+        model = engine.DenseModel(precompute.prepare(means, covs, w, np.eye(N), snr, 1, 'uniform', (None, None, None)))
+        quant = engine.Quantizer.get(1)
+        ht, nt = torch.from_numpy(h).cuda(), torch.from_numpy(noise).cuda()
+        a_tc = model.pipeline(quant, ht, nt, 10 ** (-snr / 20), 1, 'tc').cpu().numpy()
+        a_64 = model.pipeline(quant, ht, nt, 10 ** (-snr / 20), 1, 'fp64').cpu().numpy()
+        assert a_tc[2] == B and a_64[2] == B
+        assert np.allclose(a_tc, a_64, rtol=1e-6)
