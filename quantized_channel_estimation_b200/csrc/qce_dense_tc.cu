@@ -2259,7 +2259,7 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
 }
 
 // ------------------------------------------------------------------------------------------------ fused hard top-1 (small shapes)
-// For N <= 32 (any K) and for K <= 16 the three-launch top-1 path (whitening with in-epilogue label -> regroup -> one-component
+// For N <= 32 (any K) and for K <= 8 the three-launch top-1 path (whitening with in-epilogue label -> regroup -> one-component
 // combine) costs more than the fused 'all' launch (config 1: 0.91 vs 0.75 ms per 2^20 pilots): there EPI = 3 runs the fused Z|H
 // launch with a running argmax in place of the online softmax -- a component that beats the best so far REPLACES the estimate row.
 // Pilots whose best two components are too close to call are neither written nor accumulated; they go on the tie list, get their
@@ -2340,7 +2340,7 @@ __global__ void __launch_bounds__(256) tc_top1_rows_kernel(const Top1RowsArgs a)
 static bool tc_hard_top1_ok(const qce_model* m) {
     if (!tc_instantiated(m) || m->tc.split || m->tc.split_a || !m->tc.triangular) return false;
     if (const char* e = getenv("QCE_TC_HARD")) return atoi(e) != 0;
-    return m->n_obs <= 32 || m->n_comp <= 16;
+    return m->n_obs <= 32 || m->n_comp <= 8;          // measured (2^20 pilots): N = 64, K = 16 is already faster regrouped (1.42 vs 1.56 ms)
 }
 
 static qce_status tc_run_hard_top1(qce_model* m, TileScratch* ts, cudaStream_t s, int64_t B, double* h_est, const void* h_true, int h_true_c64,
