@@ -52,6 +52,9 @@ def main():
     r = pilots(1 << 20, 32, 1, (None, None))
     ms = timeit(lambda: m.estimate_from_y(r, snr, 32, n_summands_or_proba='all'))
     out.append(dict(config='C1 GMM full 1-bit N=32 K=16', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path='tc'))
+    for mode_, path_ in ((1, 'tc fused launch with a running argmax'), (3, 'tc whitening -> selection -> weighted combine')):
+        ms = timeit(lambda: m.estimate_from_y(r, snr, 32, n_summands_or_proba=mode_))
+        out.append(dict(config=f'C1 GMM full 1-bit N=32 K=16 mode={mode_}', B=r.shape[0], ms=ms, est_per_s=r.shape[0] / ms * 1e3, path=path_))
     # C5 shape: GMM full, 1 bit, N=64, K=256
     means, covs, w = synthetic.random_psd_gmm(256, 64, seed=0)
     m = qce.Gmm_nbit(n_components=256).set_parameters(means, covs, w, detect_structure=False)
