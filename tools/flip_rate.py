@@ -91,6 +91,8 @@ def main():
     dev = torch.device('cuda')
     for tag, K, N, snr, nb, qt, b in (('C2 GMM full N=64 K=64 1-bit 10 dB', 64, 64, 10, 1, 'uniform', B),
                                       ('C2 -10 dB', 64, 64, -10, 1, 'uniform', B), ('C2 30 dB', 64, 64, 30, 1, 'uniform', B),
+                                      ('C1 GMM full N=32 K=16 1-bit 10 dB (top-1: fused launch with a running argmax)', 16, 32, 10, 1, 'uniform', B),
+                                      ('C1 -10 dB', 16, 32, -10, 1, 'uniform', B),
                                       ('C5 shape N=64 K=256 1-bit 10 dB', 256, 64, 10, 1, 'uniform', B // 4),
                                       ('N=128 K=64 2-bit uniform (split path)', 64, 128, 10, 2, 'uniform', B // 4),
                                       ('N=64 K=32 3-bit Lloyd (off-grid, three passes)', 32, 64, 10, 3, 'lloyd', B // 2)):
