@@ -1208,8 +1208,9 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2* __restrict
 // scans (n + 1 of them for top-n), the same too-close-to-call rules.  The weight rows go back through shared memory so that the
 // global stores are coalesced.  pair_cnt != null: histogram of the selected (pilot, component) pairs with a weight above pair_thresh
 // (the count pass of the pair-bucketed combination, fused).
-// R pilots and 128 threads per block, ~66 KB of shared memory: three blocks per SM keep enough loads in flight (one 132 KB block
-// of 256 pilots per SM left the staging loop latency-bound: 503 us per 2^19 pilots).
+// R pilots and 128 threads per block (all of them stage, R of them select).  The staging loop is latency-bound, so small tiles --
+// many blocks, many loads in flight per SM -- win: one 132 KB block of 256 pilots per SM 503 us per 2^19 pilots at K = 64, 128 pilots
+// (66 KB) 265 us, 64: 222 us, 32: 198 us.
 constexpr int SEL_THREADS = 128;
 template <int R>
 __global__ void __launch_bounds__(SEL_THREADS) tc_select_rows_kernel(const float2* __restrict__ lp2, int64_t B, int K, int mode, int n_top, double rho, int flags,
@@ -2161,7 +2162,10 @@ static qce_status tc_run_modes(qce_model* m, TileScratch* ts, cudaStream_t s, in
                         b_top, vb, ts->tie_buf, eps, m->logc, 1.0 / m->n_obs, fused_count ? p_cnt : nullptr, pair_thresh,                     \
                         listed ? l_key : nullptr);                                                                                             \
                 }
-                if (K <= 64) QCE_SEL_ROWS(128) else if (K <= 128) QCE_SEL_ROWS(64) else QCE_SEL_ROWS(32)
+                // pilots per block: the smaller the tile, the more blocks (loads in flight) per SM -- measured at K = 64, 2^19 pilots:
+                // 128 pilots 265 us, 64: 222 us, 32: 198 us (QCE_SEL_R overrides: A/B runs)
+                const int sel_r = getenv("QCE_SEL_R") ? atoi(getenv("QCE_SEL_R")) : 32;
+                if (sel_r == 16) QCE_SEL_ROWS(16) else if (sel_r == 64 && K <= 128) QCE_SEL_ROWS(64) else if (sel_r == 128 && K <= 64) QCE_SEL_ROWS(128) else QCE_SEL_ROWS(32)
 #undef QCE_SEL_ROWS
             } else {
                 tc_select_kernel<32><<<(unsigned)((nb + 7) / 8), 256, 0, s>>>((const float2*)v.lp2, nb, K, mode, n_top, rho, m->flags, wts, lo, b_top, vb, ts->tie_buf, eps, nullptr, m->logc, 1.0 / m->n_obs);
